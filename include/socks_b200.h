@@ -1,0 +1,151 @@
+/*
+ * socks_b200.h — C ABI of libsocksb200.so: fp64 CUDA kernels (sm_100a) for SOCKS's
+ * kernel-embedding hot path.
+ *
+ * The reference (ajthor/socks) is pure Python and has no FFI; what each entry point replaces
+ * is therefore a span of reference Python, cited as gym_socks/<file>:<lines> below.  The
+ * binding a maintainer adds on the reference side is a ctypes stub.
+ *
+ * Conventions
+ *  - Every function returns int: 0 = ok, SOCKS_EINVAL(-k) = argument k invalid (1-based),
+ *    SOCKS_ECUDA = a CUDA call failed; socks_last_error() returns a thread-local message.
+ *  - All data pointers are DEVICE pointers to IEEE float64, row-major, 16-byte aligned.
+ *    The caller owns every buffer, including workspaces (sizes via the *_bytes helpers).
+ *  - `stream` is a cudaStream_t passed as void*; calls only enqueue work (asynchronous).
+ *  - Square factorisation operands are PADDED: a logical n x n matrix lives in an
+ *    np x np buffer, np = socks_padded_dim(n) (next multiple of SOCKS_TILE), leading
+ *    dimension ld >= np, ld even.  socks_gram_sym fills the padding with the identity, so
+ *    chol/inverse of the padded matrix restricted to [0,n) is the chol/inverse of the matrix.
+ *  - Kernel: k(x,y) = exp(|x-y|^2 * scale) if divide == 0, exp(|x-y|^2 / scale) otherwise.
+ *    gym_socks-style callers pass (scale = -2 sigma^2, divide = 1): the reference DIVIDES by -2 sigma^2
+ *    (gym_socks/kernel/metrics.py:135-136) and the Gram builders reproduce that rounding exactly;
+ *    sklearn-style callers pass (scale = -gamma, divide = 0).
+ */
+#ifndef SOCKS_B200_H
+#define SOCKS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOCKS_TILE 128
+#define SOCKS_OK 0
+#define SOCKS_ECUDA 1000
+#define SOCKS_EINVAL(k) (-(k))
+#define SOCKS_MAX_DIM 32     /* largest state/action dimension accepted by the Gram kernels */
+#define SOCKS_SR_ROWS 16     /* coefficient rows (1 normaliser + 15 time steps) per predict launch */
+
+#define SOCKS_PROBLEM_THT 0  /* gym_socks/algorithms/reach/common.py:42-69 */
+#define SOCKS_PROBLEM_FHT 1  /* gym_socks/algorithms/reach/common.py:8-39  */
+
+typedef void* socks_stream_t;
+
+int socks_version(void);
+const char* socks_last_error(void);
+int64_t socks_padded_dim(int64_t n);
+
+/* ---- Gram builders: gym_socks/kernel/metrics.py:119-138 (rbf_kernel) ------------------- */
+
+/* K[i*ldk + j] = rowscale[i] * k(X_i, Y_j), i<n, j<m.  rowscale may be NULL (=1).
+ * With rowscale = diag(W) this is the un-normalised beta of
+ * gym_socks/algorithms/reach/kernel_sr.py:45. */
+int socks_gram_rbf(const double* X, int64_t n, const double* Y, int64_t m, int d, double scale, int divide,
+                   const double* rowscale, double* K, int64_t ldk, socks_stream_t stream);
+
+/* D[i*ldd + j] = |X_i - Y_j|^2 (direct differences, metrics.py:127-128); used for the
+ * sigma=None median heuristic (metrics.py:130-131). */
+int socks_sqdist(const double* X, int64_t n, const double* Y, int64_t m, int d, double* D,
+                 int64_t ldd, socks_stream_t stream);
+
+/* G = K(Z,Z) + diag_add * I written into the LOWER 128-tiles of the padded np x np buffer
+ * (identity in the padding).  Z = X, or [X | U] concatenated for the product Gram
+ * K(X,X) * K(U,U) of metrics.py:268-276.  diag_add = lambda * N (metrics.py:278-280). */
+int socks_gram_sym(const double* Z, int64_t n, int d, double scale, int divide, double diag_add, double* G,
+                   int64_t ldg, socks_stream_t stream);
+
+/* ---- Regularised solve: gym_socks/kernel/metrics.py:278-280 (inv(K + lambda N I)) ------ */
+
+int64_t socks_potrf_work_bytes(int64_t n);   /* dinv: np * 128 doubles                       */
+int64_t socks_trtri_work_bytes(int64_t n);   /* scratch for the recursive triangular inverse */
+int64_t socks_reduce_work_bytes(int64_t cols); /* partial sums for column reductions         */
+
+/* In-place lower Cholesky G = L L^T of the padded matrix (blocked, recursive, DMMA trailing
+ * updates).  dinv receives inv(L_kk) of every 128 x 128 diagonal block.  *info_dev (device
+ * int, caller-zeroed) receives 1 + index of the first non-positive pivot, else stays 0. */
+int socks_potrf(double* G, int64_t n, int64_t ldg, double* dinv, int* info_dev, socks_stream_t stream);
+
+/* M = inv(L), lower triangular, out of place (M's diagonal 128-blocks get explicit zeros above
+ * the diagonal; tiles strictly above the block diagonal are not touched and never read). */
+int socks_trtri(const double* L, int64_t n, int64_t ldl, const double* dinv, double* M, int64_t ldm,
+                double* work, socks_stream_t stream);
+
+/* w[i] = sum_k M[k][i]^2 = diag(inv(G))[i]  (the only part of W the SR algorithms use:
+ * np.einsum("ii,ij->ij", W, CXY), kernel_sr.py:45).  work: socks_reduce_work_bytes(np). */
+int socks_diag_inv(const double* M, int64_t n, int64_t ldm, double* w, double* work, socks_stream_t stream);
+
+/* W = M^T M = inv(G), full symmetric np x np (what regularized_inverse returns). */
+int socks_lauum(const double* M, int64_t n, int64_t ldm, double* W, int64_t ldw, socks_stream_t stream);
+
+/* ---- Stochastic reachability: gym_socks/algorithms/reach/kernel_sr.py:31-69 ------------ */
+
+/* tubes: device array [T][4][d] = (constraint.low, constraint.high, target.low, target.high),
+ * the Boxes' float32 bounds promoted to float64 (gym_socks/utils/__init__.py:42-47). */
+
+/* Fit-phase recursion over a RESIDENT un-normalised beta B (n x m, B = diag(w) K(X,pts)):
+ *   out[T-1] = 1_target(pts);  out[t] = step(pts, (vf[t+1] @ B) / colsum(B))   t = T-2..0
+ * with vf == out (in-place, kernel_sr.py:297-309; then n == m) or vf = fitted values (n rows).
+ * T-1 HBM-bound GEMV passes over B.  work: socks_reduce_work_bytes(m) + m doubles. */
+int socks_sr_recursion(const double* B, int64_t n, int64_t m, int64_t ldb, const double* pts, int d,
+                       const double* tubes, int problem, int T, const double* vf, int64_t ldvf,
+                       double* out, int64_t ldout, double* work, socks_stream_t stream);
+
+/* Fused predict (kernel_sr.py:329-342 without materialising K(X,pts)):
+ *   out[t][j] = step(pts_j, sum_i vf[t+1][i] w_i k(x_i,pts_j) / sum_i w_i k(x_i,pts_j)).
+ * coef: workspace of n * 20 doubles per 15 time steps (packed by the library).
+ * variant: 0 = DMMA contraction (default), 1 = FMA-pipe contraction. */
+int socks_sr_predict(const double* X, const double* w, const double* vf, int64_t ldvf, int64_t n, int d,
+                     double scale, int divide, const double* pts, int64_t m, const double* tubes, int problem, int T,
+                     double* out, int64_t ldout, double* coef, int variant, socks_stream_t stream);
+
+/* ---- Maximal SR: gym_socks/algorithms/reach/kernel_sr_max.py:30-79 --------------------- */
+
+/* Bm[i][c] = coef_r[i] * CUA[i][a] for c = r*P + a, r < R; zero for i >= n or c >= R*P.
+ * coef row 0 = w, rows r >= 1 = vf[t0 + r] * w.  Bm: np x ldbm (the GEMM's right operand). */
+int socks_srmax_pack(const double* CUA, int64_t n, int P, const double* w, const double* vf,
+                     int64_t ldvf, int t0, int R, double* Bm, int64_t np, int64_t ldbm, socks_stream_t stream);
+
+/* C (m x nn) = A^T B with A = Kmat (K x m, row-major: the Gram chunk K(X, pts)), B = Bm (K x nn);
+ * m, nn multiples of 128, K multiple of 16.  DMMA GEMM (kernel_sr_max.py:65-70 as a contraction). */
+int socks_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                  int64_t m, int64_t nn, int64_t K, socks_stream_t stream);
+
+/* out[t0 + r - 1][j] = step(pts_j, max_a Cm[j][r*P + a] / Cm[j][a]) for r = 1..R-1
+ * (kernel_sr_max.py:72-73).  If write_last != 0 also out[T-1][j] = 1_target(pts_j). */
+int socks_srmax_step(const double* Cm, int64_t ldc, int64_t m, int P, int R, int t0, const double* pts,
+                     int d, const double* tubes, int problem, int T, double* out, int64_t ldout,
+                     int write_last, socks_stream_t stream);
+
+/* ---- Forward control: gym_socks/algorithms/control/kernel_control_fwd.py:211-238 ------- */
+
+/* y[r][j] = sum_i V[r][i] * Bmat[i][j] (R <= 2 row vectors, V rows ldv apart; V NULL = ones).
+ * Used for z = W c (W symmetric) and for scores = q^T CUA.  work: R*socks_reduce_work_bytes(m). */
+int socks_gemv_t(const double* Bmat, int64_t n, int64_t m, int64_t ldb, const double* V, int64_t ldv,
+                 int R, double* y, int64_t ldy, double* work, socks_stream_t stream);
+
+/* q[r][i] = z[r][i] * k(X_i, s), r < R (kernel_control_fwd.py:220-222). */
+int socks_fwd_weights(const double* X, int64_t n, int d, double scale, int divide, const double* state,
+                      const double* z, int64_t ldz, int R, double* q, int64_t ldq, socks_stream_t stream);
+
+/* idx = argmin_k C[k] over {k : D[k] <= 0} (all k if D is NULL or the set is empty); first
+ * occurrence on ties (gym_socks/algorithms/control/common.py:96-100, 166-174). idx_dev: device int. */
+int socks_argmin_masked(const double* C, const double* D, int P, int* idx_dev, socks_stream_t stream);
+
+/* ---- Measurement helpers (tools/, bench.py): register-resident FP64 peak probes -------- */
+int socks_probe_fp64(int mode, int iters, double* out_dev, int blocks, socks_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,155 @@
+"""Kernel-based stochastic reachability on the GPU: drop-in for
+`gym_socks/algorithms/reach/kernel_sr.py` (`kernel_sr`, `KernelSR`).
+
+fit  = Gram + Cholesky + triangular inverse -> w = diag(W); B = diag(w) K(X,Y) resident in HBM;
+       T-1 GEMV passes with the FHT/THT step fused (socks_sr_recursion).
+predict = one fused kernel over the test points, K(X,T) never materialised (socks_sr_predict).
+"""
+import logging
+
+import numpy as np
+
+from socks_b200 import _device as dv
+from socks_b200 import _lib
+from socks_b200.algorithms.reach.common import PROBLEM_CODE, pack_tubes
+from socks_b200.kernel.metrics import factorize, gram_dev, resolve_kernel
+from socks_b200.sampling.transform import transpose_sample
+
+logger = logging.getLogger(__name__)
+
+__all__ = ["kernel_sr", "KernelSR"]
+
+
+def kernel_sr(S, T, time_horizon=None, constraint_tube=None, target_tube=None, problem="THT",
+              regularization_param=None, kernel_fn=None, batch_size=None, verbose=False):
+    """One-shot wrapper, `gym_socks/algorithms/reach/kernel_sr.py:116-170`.
+    Returns safety probabilities of shape (time_horizon, len(T))."""
+    alg = KernelSR(time_horizon=time_horizon, constraint_tube=constraint_tube, target_tube=target_tube,
+                   problem=problem, regularization_param=regularization_param, kernel_fn=kernel_fn,
+                   batch_size=batch_size, verbose=verbose)
+    alg.fit(S)
+    return alg.predict(T)
+
+
+class KernelSR:
+    """`gym_socks/algorithms/reach/kernel_sr.py:173-347`: same constructor, `fit(S)`, `predict(T)`,
+    attributes `X`, `W`, `value_functions`.  `batch_size` is accepted for API parity and does not change
+    results (test points are independent columns; the fused predict kernel streams them anyway)."""
+
+    predict_variant = 0  # 0: DMMA contraction, 1: FMA-pipe contraction (csrc/sr.cu)
+
+    def __init__(self, time_horizon=None, constraint_tube=None, target_tube=None, problem="THT", kernel_fn=None,
+                 regularization_param=None, batch_size=None, verbose=False, *args, **kwargs):
+        self.time_horizon = time_horizon
+        self.constraint_tube = constraint_tube
+        self.target_tube = target_tube
+        self.problem = problem
+        self.kernel_fn = kernel_fn
+        self.regularization_param = regularization_param
+        self.batch_size = batch_size
+        self.verbose = verbose
+
+    # -- validation: same order and exception types as kernel_sr.py:224-264
+    def _validate_params(self, S):
+        self._spec = resolve_kernel(self.kernel_fn, default_sigma=0.1)
+        if self.regularization_param is None:
+            self.regularization_param = 1
+        if self.time_horizon is None:
+            raise ValueError("Must supply a time horizon.")
+        assert self.time_horizon >= 0 and isinstance(self.time_horizon, (int, np.integer))
+        if self.constraint_tube is None:
+            raise ValueError("Must supply constraint tube.")
+        if self.target_tube is None:
+            raise ValueError("Must supply target tube.")
+        if self.problem not in ("FHT", "THT"):
+            raise ValueError(f"problem is not in {'THT', 'FHT'}")
+
+    def _validate_data(self, S):
+        if S is None:
+            raise ValueError("Must supply a sample.")
+
+    # -- device state shared with the multi-GPU helpers
+    def _state(self):
+        return {"X": self._Xd, "w": self._w, "vf": self._vf}
+
+    def fit(self, S):
+        self._validate_data(S)
+        self._validate_params(S)
+        X, U, Y = transpose_sample(S)
+        return self.fit_arrays(X, Y)
+
+    def fit_arrays(self, X, Y):
+        """fit() on already transposed samples (avoids building the list of tuples at N = 20k+)."""
+        if not hasattr(self, "_spec"):
+            self._validate_params(None)
+        Xh, Yh = dv.as2d(X), dv.as2d(Y)
+        n, d = Xh.shape
+        T = int(self.time_horizon)
+        self._n, self._d = n, d
+        self._Xh = Xh
+        logger.debug("Computing matrix inverse.")
+        fac = factorize(Xh, None, self._spec, self.regularization_param)
+        self._fac = fac
+        w = fac.diag()
+        fac.check()
+        if not self._keep_factors:
+            fac.release_factors()
+        Xd, Yd = dv.to_dev(Xh), dv.to_dev(Yh)
+        self._Xd, self._w = Xd, w
+        self._tubes = pack_tubes(self.constraint_tube, self.target_tube, T, d)
+        logger.debug("Computing covariance matrix.")
+        ldb = dv.even(n)
+        B = gram_dev(Xd, Yd, self._spec.params_for(Xd, Yd), rowscale=w, ld=ldb)  # un-normalised beta, kernel_sr.py:45
+        logger.debug("Computing value functions.")
+        vf = dv.empty(max(T, 1), n)
+        lib = _lib.load()
+        wk = dv.work(lib.socks_reduce_work_bytes(n) + 8 * (n + 2))
+        if T >= 1:
+            _lib.call("socks_sr_recursion", dv.ptr(B), n, n, ldb, dv.ptr(Yd), d, dv.ptr(self._tubes),
+                      PROBLEM_CODE[self.problem], T, dv.ptr(vf), n, dv.ptr(vf), n, dv.ptr(wk), dv.stream())
+        self._vf = vf[:T]
+        self._vf_host = None
+        del B
+        return self
+
+    _keep_factors = True  # `.W` stays available; set False to free L and M right after fit
+
+    def predict(self, T):
+        self._validate_data(T)
+        out = self.predict_dev(dv.to_dev(dv.as2d(T)))
+        return out.cpu().numpy()
+
+    def predict_dev(self, pts):
+        """Device in, device out: (m, d) test points -> (time_horizon, m) safety probabilities."""
+        m = pts.shape[0]
+        Th = int(self.time_horizon)
+        out = dv.empty(max(Th, 1), max(m, 1))[:Th, :m]
+        if m == 0 or Th == 0:
+            return out
+        scale, divide = self._spec.params_for(self._Xd, pts)
+        coef = dv.work(8 * 20 * (dv.padded(self._n) + 128))
+        _lib.call("socks_sr_predict", dv.ptr(self._Xd), dv.ptr(self._w), dv.ptr(self._vf), self._n, self._n, self._d,
+                  float(scale), int(divide), dv.ptr(pts), m, dv.ptr(self._tubes), PROBLEM_CODE[self.problem], Th,
+                  dv.ptr(out), out.stride(0), dv.ptr(coef), int(self.predict_variant), dv.stream())
+        return out
+
+    # -- attributes the reference exposes (kernel_sr.py:286-309)
+    @property
+    def X(self):
+        return self._Xh
+
+    @property
+    def W(self):
+        """inv(G) as an ndarray; computed on first access (the algorithm itself only needs diag(W))."""
+        if self._fac.L is None and self._fac._W is None:
+            raise AttributeError("factors were released (keep_factors=False); W is unavailable")
+        return self._fac.full()[: self._n, : self._n].cpu().numpy()
+
+    @property
+    def value_functions(self):
+        if self._vf_host is None:
+            self._vf_host = self._vf.cpu().numpy()
+        return self._vf_host
+
+    def score(self):
+        raise NotImplementedError

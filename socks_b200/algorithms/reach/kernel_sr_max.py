@@ -1,0 +1,172 @@
+"""Maximal kernel-based stochastic reachability on the GPU: drop-in for
+`gym_socks/algorithms/reach/kernel_sr_max.py` (`kernel_sr_max`, `KernelMaximalSR`).
+
+The reference's N x M x P tensor (kernel_sr_max.py:45-47) is never formed: each recursion step is a
+DMMA GEMM  K(X,pts)^T [diag(w) CUA | diag(vf w) CUA]  followed by a fused divide + max + step
+(csrc/srmax.cu).  In predict all T-1 steps share one GEMM per chunk of test points.
+"""
+import logging
+
+import numpy as np
+
+from socks_b200 import _device as dv
+from socks_b200 import _lib
+from socks_b200.algorithms.reach.common import PROBLEM_CODE, pack_tubes
+from socks_b200.kernel.metrics import factorize, gram_dev, resolve_kernel
+from socks_b200.sampling.transform import transpose_sample
+
+logger = logging.getLogger(__name__)
+
+__all__ = ["kernel_sr_max", "KernelMaximalSR"]
+
+
+def kernel_sr_max(S, A, T, time_horizon=None, constraint_tube=None, target_tube=None, problem="THT",
+                  regularization_param=None, kernel_fn=None, batch_size=None, verbose=False):
+    """One-shot wrapper, `gym_socks/algorithms/reach/kernel_sr_max.py:142-199`."""
+    alg = KernelMaximalSR(time_horizon=time_horizon, constraint_tube=constraint_tube, target_tube=target_tube,
+                          problem=problem, regularization_param=regularization_param, kernel_fn=kernel_fn,
+                          batch_size=batch_size, verbose=verbose)
+    alg.fit(S, A)
+    return alg.predict(T)
+
+
+class KernelMaximalSR:
+    """`gym_socks/algorithms/reach/kernel_sr_max.py:202-387`.  Note the keyword order of the reference:
+    `regularization_param` precedes `kernel_fn` here (:231-232)."""
+
+    predict_chunk = 8192  # test points per GEMM (multiple of 128)
+
+    def __init__(self, time_horizon=None, constraint_tube=None, target_tube=None, problem="THT",
+                 regularization_param=None, kernel_fn=None, batch_size=None, verbose=False, *args, **kwargs):
+        self.time_horizon = time_horizon
+        self.constraint_tube = constraint_tube
+        self.target_tube = target_tube
+        self.problem = problem
+        self.kernel_fn = kernel_fn
+        self.regularization_param = regularization_param
+        self.batch_size = batch_size
+        self.verbose = verbose
+
+    def _validate_params(self, S=None, A=None):
+        self._spec = resolve_kernel(self.kernel_fn, default_sigma=0.1)
+        if self.regularization_param is None:
+            self.regularization_param = 1
+        if self.time_horizon is None:
+            raise ValueError("Must supply a time horizon.")
+        assert self.time_horizon >= 0 and isinstance(self.time_horizon, (int, np.integer))
+        if self.constraint_tube is None:
+            raise ValueError("Must supply constraint tube.")
+        if self.target_tube is None:
+            raise ValueError("Must supply target tube.")
+        if self.problem not in ("FHT", "THT"):
+            raise ValueError(f"problem is not in {'THT', 'FHT'}")
+
+    def _validate_data(self, S=None):
+        if S is None:
+            raise ValueError("Must supply a sample.")
+
+    def fit(self, S, A):
+        self._validate_params(S, A)
+        self._validate_data(S)
+        self._validate_data(A)
+        X, U, Y = transpose_sample(S)
+        return self.fit_arrays(X, U, Y, A)
+
+    def fit_arrays(self, X, U, Y, A):
+        if not hasattr(self, "_spec"):
+            self._validate_params()
+        Xh, Uh, Yh, Ah = dv.as2d(X), dv.as2d(U), dv.as2d(Y), dv.as2d(A)
+        n, d = Xh.shape
+        P = Ah.shape[0]
+        T = int(self.time_horizon)
+        self._n, self._d, self._P, self._Xh = n, d, P, Xh
+        npad = dv.padded(n)
+        logger.debug("Computing matrix inverse.")
+        fac = factorize(Xh, Uh, self._spec, self.regularization_param)
+        self._fac = fac
+        w = fac.diag()
+        fac.check()
+        Xd, Yd, Ud, Ad = dv.to_dev(Xh), dv.to_dev(Yh), dv.to_dev(Uh), dv.to_dev(Ah)
+        self._Xd, self._w = Xd, w
+        self._tubes = pack_tubes(self.constraint_tube, self.target_tube, T, d)
+        logger.debug("Computing covariance matrices.")
+        CUA = gram_dev(Ud, Ad, self._spec.params_for(Ud, Ad), ld=P)  # (n, P) contiguous, kernel_sr_max.py:332
+        self._CUA = CUA
+        # K(X, Y) as the GEMM's left operand: (K = npad rows) x (m = npad columns), zero padding
+        Kmat = dv.zeros(npad, npad)
+        gram_dev(Xd, Yd, self._spec.params_for(Xd, Yd), out=Kmat, ld=npad)
+        logger.debug("Computing value functions.")
+        vf = dv.empty(max(T, 1), n)
+        ldbm = -(-2 * P // 128) * 128
+        Bm = dv.empty(npad, ldbm)
+        Cm = dv.empty(npad, ldbm)
+        st = dv.stream()
+        prob = PROBLEM_CODE[self.problem]
+        # vf[T-1] = 1_target(Y) first (kernel_sr_max.py:59): the first pack below reads it
+        _lib.call("socks_srmax_step", dv.ptr(Cm), ldbm, n, P, 1, 0, dv.ptr(Yd), d, dv.ptr(self._tubes), prob, T,
+                  dv.ptr(vf), n, 1, st)
+        for t in range(T - 2, -1, -1):
+            # rows: r = 0 -> w (normaliser), r = 1 -> vf[t+1] * w          (kernel_sr_max.py:65-72)
+            _lib.call("socks_srmax_pack", dv.ptr(CUA), n, P, dv.ptr(w), dv.ptr(vf), n, t, 2, dv.ptr(Bm), npad, ldbm, st)
+            _lib.call("socks_gemm_tn", dv.ptr(Kmat), npad, dv.ptr(Bm), ldbm, dv.ptr(Cm), ldbm, npad, ldbm, npad, st)
+            _lib.call("socks_srmax_step", dv.ptr(Cm), ldbm, n, P, 2, t, dv.ptr(Yd), d, dv.ptr(self._tubes), prob, T,
+                      dv.ptr(vf), n, 0, st)
+        self._vf = vf[:T]
+        self._vf_host = None
+        return self
+
+    def predict(self, T):
+        self._validate_data(T)
+        return self.predict_dev(dv.to_dev(dv.as2d(T))).cpu().numpy()
+
+    def predict_dev(self, pts):
+        m = pts.shape[0]
+        Th = int(self.time_horizon)
+        n, d, P = self._n, self._d, self._P
+        npad = dv.padded(n)
+        out = dv.empty(max(Th, 1), max(m, 1))[:Th, :m]
+        if m == 0 or Th == 0:
+            return out
+        st = dv.stream()
+        prob = PROBLEM_CODE[self.problem]
+        kparams = self._spec.params_for(self._Xd, pts)
+        # all rows at once: r = 0 normaliser, r = 1..T-1 time steps 0..T-2
+        R = Th
+        ldbm = -(-R * P // 128) * 128
+        Bm = dv.empty(npad, ldbm)
+        _lib.call("socks_srmax_pack", dv.ptr(self._CUA), n, P, dv.ptr(self._w), dv.ptr(self._vf), n, 0, R, dv.ptr(Bm),
+                  npad, ldbm, st)
+        mc = min(self.predict_chunk, -(-m // 128) * 128)
+        Kmat = dv.zeros(npad, mc)
+        Cm = dv.empty(mc, ldbm)
+        for s in range(0, m, mc):
+            cnt = min(mc, m - s)
+            if cnt < mc:
+                Kmat.zero_()
+            p = pts[s:s + cnt]
+            gram_dev(self._Xd, p, kparams, out=Kmat, ld=mc)
+            _lib.call("socks_gemm_tn", dv.ptr(Kmat), mc, dv.ptr(Bm), ldbm, dv.ptr(Cm), ldbm, mc, ldbm, npad, st)
+            _lib.call("socks_srmax_step", dv.ptr(Cm), ldbm, cnt, P, R, 0, dv.ptr(p), d, dv.ptr(self._tubes), prob, Th,
+                      dv.ptr(out[:, s:]), out.stride(0), 1, st)
+        return out
+
+    @property
+    def X(self):
+        return self._Xh
+
+    @property
+    def W(self):
+        return self._fac.full()[: self._n, : self._n].cpu().numpy()
+
+    @property
+    def CUA(self):
+        return self._CUA.cpu().numpy()
+
+    @property
+    def value_functions(self):
+        if self._vf_host is None:
+            self._vf_host = self._vf.cpu().numpy()
+        return self._vf_host
+
+    def score(self):
+        raise NotImplementedError

@@ -1,0 +1,419 @@
+// Regularised solve: blocked recursive Cholesky, triangular inverse, diag(inv(G)) and inv(G).
+// Replaces `inv(K + lambda N I)` (LAPACK dgesv through numpy.linalg.inv,
+// gym_socks/kernel/metrics.py:278-280).  G is symmetric positive definite (Gram + lambda N I), so
+// the LU inverse of the reference becomes G = L L^T, M = inv(L), W = M^T M; the SR algorithms only
+// ever read diag(W) (kernel_sr.py:45), i.e. the column sums of squares of M.
+//
+// Structure: recursion on the host over 128-aligned splits; every flop outside the 128 x 128
+// diagonal leaves is a DMMA GEMM (gemm_f64.cuh):
+//   potrf(A)  = potrf(A11); A21 <- A21 inv(L11)^T (recursive TRSM); A22 -= A21 A21^T; potrf(A22)
+//   trsm(B,L) = trsm(B1,L11); B2 -= B1 L21^T; trsm(B2,L22)      leaf: B <- B inv(L_kk)^T (GEMM)
+//   trtri     = M11 = inv(L11), M22 = inv(L22), M21 = -(M22 L21) M11
+// Roofline: N^3/3 flops each for potrf, trtri and lauum; FP64 DMMA (tensor pipe) bound.
+#include "gemm_f64.cuh"
+#include "reduce.cuh"
+
+namespace socks {
+
+constexpr int LF = TILE;        // leaf size 128
+constexpr int LF_LD = LF + 1;   // odd smem stride: row and column accesses are both conflict-free
+constexpr int LF_THREADS = 256;
+constexpr int LF_NB = 32;       // inner block: one warp factors a 32 x 32 diagonal block
+constexpr int LF_SC_LD = 97;    // scratch [96][33] (panel) or [32][97] (inverse assembly)
+// S (L, then inv L in place), Dinv[4][32][33], scratch 96*33, rinv[128]  (~192 KB)
+constexpr int LF_SMEM = (LF * LF_LD + 4 * LF_NB * 33 + 96 * 33 + LF) * 8;
+
+// Factor one 128 x 128 diagonal block in shared memory and invert the factor.
+//   A (global, lower part) <- L ;  dinv (dense 128 x 128) <- inv(L) with explicit zeros above.
+// Blocked right-looking over four 32-column panels: (a) warp 0 factors the 32 x 32 diagonal block
+// (left-looking, lane = row, rsqrt pivots), (b) all warps invert it (8 lanes per column), (c) panel
+// solve P <- P inv(D)^T, (d) trailing update; then inv(L) is assembled block row by block row.
+__global__ void __launch_bounds__(LF_THREADS, 1)
+    potf2_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ dinv, int* __restrict__ info,
+                     int col_offset) {
+    extern __shared__ __align__(16) double lf_smem[];
+    double* S = lf_smem;                     // [128][129]  block -> L (lower) -> inv(L), block row by block row
+    double* Di = S + LF * LF_LD;             // [4][32][33] inverses of the diagonal 32-blocks
+    double* Sc = Di + 4 * LF_NB * 33;        // scratch
+    double* rinv = Sc + 96 * 33;             // [128] 1 / L_jj
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int e = tid; e < LF * LF; e += LF_THREADS) {
+        const int r = e >> 7, c = e & 127;
+        S[r * LF_LD + c] = (c <= r) ? A[(int64_t)r * lda + c] : 0.0;
+    }
+    __syncthreads();
+
+    for (int kb = 0; kb < 4; ++kb) {
+        const int o = kb * LF_NB;
+        double* D = Di + kb * LF_NB * 33;
+        // ---- (a) 32 x 32 Cholesky by warp 0: lane i owns row o+i
+        if (warp == 0) {
+            const double* rowi = S + (o + lane) * LF_LD + o;
+            for (int j = 0; j < LF_NB; ++j) {
+                const double* rowj = S + (o + j) * LF_LD + o;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int k = 0;
+                for (; k + 4 <= j; k += 4) {
+                    a0 = fma(rowi[k], rowj[k], a0);
+                    a1 = fma(rowi[k + 1], rowj[k + 1], a1);
+                    a2 = fma(rowi[k + 2], rowj[k + 2], a2);
+                    a3 = fma(rowi[k + 3], rowj[k + 3], a3);
+                }
+                for (; k < j; ++k) a0 = fma(rowi[k], rowj[k], a0);
+                const double v = rowi[j] - ((a0 + a1) + (a2 + a3));
+                double vj = __shfl_sync(0xffffffffu, v, j);
+                if (!(vj > 0.0)) {  // non-positive or NaN pivot: report the first one, continue with 1
+                    if (lane == 0) atomicCAS(info, 0, col_offset + o + j + 1);
+                    vj = 1.0;
+                }
+                const double ri = rsqrt(vj);
+                if (lane == j) {
+                    S[(o + j) * LF_LD + o + j] = vj * ri;
+                    rinv[o + j] = ri;
+                } else if (lane > j) {
+                    S[(o + lane) * LF_LD + o + j] = v * ri;
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // ---- (b) D = inv(L_kk): column c by the 8 lanes {8c' .. 8c'+7} of one warp (column-private)
+        {
+            const int c = tid >> 3, sub = tid & 7;
+            for (int i = 0; i < LF_NB; ++i) {
+                double acc = 0.0;
+                if (i > c)
+                    for (int k = c + sub; k < i; k += 8) acc = fma(S[(o + i) * LF_LD + o + k], D[k * 33 + c], acc);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                if (sub == 0) D[i * 33 + c] = (i < c) ? 0.0 : (i == c ? rinv[o + c] : -acc * rinv[o + i]);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        const int rem = LF - o - LF_NB;  // rows below the diagonal block
+        if (rem > 0) {
+            // ---- (c) panel solve into scratch: X[r][c] = sum_{k <= c} P[r][k] D[c][k]
+            for (int e = tid; e < rem * LF_NB; e += LF_THREADS) {
+                const int r = e >> 5, c = e & 31;
+                const double* prow = S + (o + LF_NB + r) * LF_LD + o;
+                double a0 = 0.0, a1 = 0.0;
+                int k = 0;
+                for (; k + 2 <= c + 1; k += 2) {
+                    a0 = fma(prow[k], D[c * 33 + k], a0);
+                    a1 = fma(prow[k + 1], D[c * 33 + k + 1], a1);
+                }
+                if (k <= c) a0 = fma(prow[k], D[c * 33 + k], a0);
+                Sc[r * 33 + c] = a0 + a1;
+            }
+            __syncthreads();
+            // ---- (d) write the panel back and update the trailing lower triangle (4 x 4 micro-tiles)
+            for (int e = tid; e < rem * LF_NB; e += LF_THREADS) {
+                const int r = e >> 5, c = e & 31;
+                S[(o + LF_NB + r) * LF_LD + o + c] = Sc[r * 33 + c];
+            }
+            const int nt = rem >> 2;  // micro-tiles per side
+            for (int e = tid; e < nt * nt; e += LF_THREADS) {
+                const int ti = e / nt, tj = e % nt;
+                if (tj > ti) continue;
+                const double* xi = Sc + (ti * 4) * 33;
+                const double* xj = Sc + (tj * 4) * 33;
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+                for (int k = 0; k < LF_NB; ++k) {
+                    double va[4], vb[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) { va[a] = xi[a * 33 + k]; vb[a] = xj[a * 33 + k]; }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[a][b] = fma(va[a], vb[b], acc[a][b]);
+                }
+                double* dst = S + (o + LF_NB + ti * 4) * LF_LD + o + LF_NB + tj * 4;
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) dst[a * LF_LD + b] -= acc[a][b];
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- L is final: write it out, then turn S into inv(L) in place.  Block row i of inv(L) only needs
+    //      block row i of L and the finished rows above it:  M_ii = D_i,  M_ij = -D_i (sum_{k=j}^{i-1} L_ik M_kj).
+    for (int e = tid; e < LF * LF; e += LF_THREADS) {
+        const int r = e >> 7, c = e & 127;
+        if (c <= r) A[(int64_t)r * lda + c] = S[r * LF_LD + c];
+    }
+    __syncthreads();
+    for (int e = tid; e < 4 * LF_NB * LF_NB; e += LF_THREADS) {
+        const int b = e >> 10, r = (e >> 5) & 31, c = e & 31;
+        S[(b * LF_NB + r) * LF_LD + b * LF_NB + c] = Di[b * LF_NB * 33 + r * 33 + c];  // zeros above the diagonal
+    }
+    __syncthreads();
+    for (int i = 1; i < 4; ++i) {
+        const int w = i * LF_NB;  // columns 0 .. w-1
+        for (int e = tid; e < LF_NB * w; e += LF_THREADS) {
+            const int r = e / w, cc = e % w;
+            const double* lrow = S + (w + r) * LF_LD;
+            double a0 = 0.0, a1 = 0.0;
+            int kk = cc & ~31;  // M[kk][cc] == 0 for kk < cc; start at the block boundary (explicit zeros)
+            for (; kk + 2 <= w; kk += 2) {
+                a0 = fma(lrow[kk], S[kk * LF_LD + cc], a0);
+                a1 = fma(lrow[kk + 1], S[(kk + 1) * LF_LD + cc], a1);
+            }
+            Sc[r * LF_SC_LD + cc] = a0 + a1;
+        }
+        __syncthreads();
+        const double* D = Di + i * LF_NB * 33;
+        for (int e = tid; e < LF_NB * w; e += LF_THREADS) {
+            const int r = e / w, cc = e % w;
+            double a0 = 0.0;
+            for (int q = 0; q <= r; ++q) a0 = fma(D[r * 33 + q], Sc[q * LF_SC_LD + cc], a0);
+            S[(w + r) * LF_LD + cc] = -a0;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < LF * LF; e += LF_THREADS) {
+        const int r = e >> 7, c = e & 127;
+        dinv[r * LF + c] = (c <= r) ? S[r * LF_LD + c] : 0.0;
+    }
+}
+
+// Leaf TRSM: B (rows x 128, in place) <- B * Minv^T, Minv = inv(L_kk) lower triangular (dense 128x128).
+// One CTA per 64 rows; both operands fully resident in shared memory before any write, so the
+// in-place update is race-free.  out[i][j] = sum_{k <= j} B[i][k] Minv[j][k].
+constexpr int TR_ROWS = 64, TR_LD = LF + 4;  // 132
+constexpr int TR_SMEM = (TR_ROWS + LF) * TR_LD * 8;
+
+__global__ void __launch_bounds__(256, 1)
+    trsm_leaf_kernel(double* __restrict__ Bp, int64_t ldb, const double* __restrict__ Minv) {
+    extern __shared__ __align__(16) double tr_smem[];
+    double* sB = tr_smem;                   // [64][132]
+    double* sM = tr_smem + TR_ROWS * TR_LD;  // [128][132]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* Bg = Bp + (int64_t)blockIdx.x * TR_ROWS * ldb;
+
+    for (int c = tid; c < TR_ROWS * (LF / 2); c += 256) {
+        int r = c >> 6, kc = (c & 63) * 2;
+        cp_async16(sB + r * TR_LD + kc, Bg + (int64_t)r * ldb + kc);
+    }
+    for (int c = tid; c < LF * (LF / 2); c += 256) {
+        int r = c >> 6, kc = (c & 63) * 2;
+        cp_async16(sM + r * TR_LD + kc, Minv + r * LF + kc);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const int wm = (warp >> 2) * 32, wn = (warp & 3) * 32;
+    const int lq = lane >> 2, lr = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+    const int ksteps = (wn + 32) / 4;  // Minv[j][k] == 0 for k > j, j < wn + 32
+    for (int ks = 0; ks < ksteps; ++ks) {
+        const int kk = ks * 4 + lr;
+        double af[4], bf[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) af[mi] = sB[(wm + mi * 8 + lq) * TR_LD + kk];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) bf[ni] = sM[(wn + ni * 8 + lq) * TR_LD + kk];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+            *reinterpret_cast<double2*>(Bg + (int64_t)(wm + mi * 8 + lq) * ldb + wn + ni * 8 + 2 * lr) =
+                make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+}
+
+__global__ void copy_block_kernel(const double* __restrict__ src, int64_t lds, double* __restrict__ dst, int64_t ldd,
+                                  int rows, int cols) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < rows * cols; e += gridDim.x * blockDim.x) {
+        int r = e / cols, c = e % cols;
+        dst[(int64_t)r * ldd + c] = src[(int64_t)r * lds + c];
+    }
+}
+
+
+// Symmetrise: copy the lower triangle of W into the upper one, 32 x 32 tiles through shared memory.
+__global__ void symmetrize_kernel(double* __restrict__ W, int64_t ldw) {
+    __shared__ double t[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    for (int r = ty; r < 32; r += 8) t[r][tx] = W[((int64_t)bi * 32 + r) * ldw + bj * 32 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t row = (int64_t)bj * 32 + r, col = (int64_t)bi * 32 + tx;  // transposed position
+        if (bi != bj || col > row) W[row * ldw + col] = t[tx][r];
+    }
+}
+
+struct CholCtx {
+    cudaStream_t st;
+    cudaError_t err = cudaSuccess;
+    void note(cudaError_t e) {
+        if (err == cudaSuccess && e != cudaSuccess) err = e;
+    }
+};
+
+static inline int64_t split_point(int64_t n) { return ((n / LF) / 2) * LF; }  // n > 128, multiple of 128
+
+// B (m x n, ld) <- B inv(L)^T, L = n x n lower at `L` (ld ldl); dinv indexes inv(L_kk) by diagonal block.
+static void trsm_rec(CholCtx& cx, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t n,
+                     const double* dinv) {
+    if (m == 0) return;
+    if (n == LF) {
+        trsm_leaf_kernel<<<(unsigned)(m / TR_ROWS), 256, TR_SMEM, cx.st>>>(B, ldb, dinv);
+        cx.note(cudaGetLastError());
+        return;
+    }
+    const int64_t n1 = split_point(n), n2 = n - n1;
+    trsm_rec(cx, B, ldb, m, L, ldl, n1, dinv);
+    // B2 -= B1 * L21^T
+    cx.note(gemm_f64<false, true>(B, ldb, L + n1 * ldl, ldl, B + n1, ldb, m, n2, n1, -1.0, 1.0, 0, 0, cx.st));
+    trsm_rec(cx, B + n1, ldb, m, L + n1 * ldl + n1, ldl, n2, dinv + (n1 / LF) * LF * LF);
+}
+
+static void potrf_rec(CholCtx& cx, double* A, int64_t lda, int64_t n, double* dinv, int* info, int64_t off) {
+    if (n == LF) {
+        potf2_inv_kernel<<<1, LF_THREADS, LF_SMEM, cx.st>>>(A, lda, dinv, info, (int)off);
+        cx.note(cudaGetLastError());
+        return;
+    }
+    const int64_t n1 = split_point(n), n2 = n - n1;
+    double* A21 = A + n1 * lda;
+    double* A22 = A21 + n1;
+    potrf_rec(cx, A, lda, n1, dinv, info, off);
+    trsm_rec(cx, A21, lda, n2, A, lda, n1, dinv);
+    cx.note(gemm_f64<false, true>(A21, lda, A21, lda, A22, lda, n2, n2, n1, -1.0, 1.0, 0, 1, cx.st));
+    potrf_rec(cx, A22, lda, n2, dinv + (n1 / LF) * LF * LF, info, off + n1);
+}
+
+static void trtri_rec(CholCtx& cx, const double* L, int64_t ldl, const double* dinv, double* M, int64_t ldm,
+                      int64_t n, double* work) {
+    if (n == LF) {
+        copy_block_kernel<<<16, 256, 0, cx.st>>>(dinv, LF, M, ldm, LF, LF);
+        cx.note(cudaGetLastError());
+        return;
+    }
+    const int64_t n1 = split_point(n), n2 = n - n1;
+    trtri_rec(cx, L, ldl, dinv, M, ldm, n1, work);
+    trtri_rec(cx, L + n1 * ldl + n1, ldl, dinv + (n1 / LF) * LF * LF, M + n1 * ldm + n1, ldm, n2, work);
+    // T (n2 x n1, ld n1) = M22 * L21 ; M21 = -T * M11
+    cx.note(gemm_f64<false, false>(M + n1 * ldm + n1, ldm, L + n1 * ldl, ldl, work, n1, n2, n1, n2, 1.0, 0.0,
+                                   GEMM_A_K_LE_M, 0, cx.st));
+    cx.note(gemm_f64<false, false>(work, n1, M, ldm, M + n1 * ldm, ldm, n2, n1, n1, -1.0, 0.0, GEMM_B_K_GE_N, 0,
+                                   cx.st));
+}
+
+static int chol_configure() {
+    static bool done = false;
+    if (done) return SOCKS_OK;
+    SOCKS_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM));
+    SOCKS_CUDA(cudaFuncSetAttribute(trsm_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
+    done = true;
+    return SOCKS_OK;
+}
+
+}  // namespace socks
+
+using namespace socks;
+
+extern "C" int64_t socks_potrf_work_bytes(int64_t n) { return socks_padded_dim(n) * LF * 8; }
+
+extern "C" int64_t socks_trtri_work_bytes(int64_t n) {
+    const int64_t np = socks_padded_dim(n);
+    if (np <= LF) return 16;
+    const int64_t n1 = split_point(np), n2 = np - n1;
+    return n1 * n2 * 8;
+}
+
+extern "C" int64_t socks_reduce_work_bytes(int64_t cols) { return 2 * CR_MAX_SPLITS * colreduce_ldpart(cols) * 8; }
+
+static int check_square(const void* p, int64_t n, int64_t ld, int argp) {
+    SOCKS_CHECK_ARG(p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15) == 0, argp);
+    SOCKS_CHECK_ARG(n >= 1, argp + 1);
+    SOCKS_CHECK_ARG(ld >= socks_padded_dim(n) && ld % 2 == 0, argp + 2);
+    return SOCKS_OK;
+}
+
+extern "C" int socks_potrf(double* G, int64_t n, int64_t ldg, double* dinv, int* info_dev, socks_stream_t stream) {
+    int rc = check_square(G, n, ldg, 1);
+    if (rc) return rc;
+    SOCKS_CHECK_ARG(dinv != nullptr && (reinterpret_cast<uintptr_t>(dinv) & 15) == 0, 4);
+    SOCKS_CHECK_ARG(info_dev != nullptr, 5);
+    if ((rc = chol_configure())) return rc;
+    CholCtx cx{(cudaStream_t)stream};
+    potrf_rec(cx, G, ldg, socks_padded_dim(n), dinv, info_dev, 0);
+    if (cx.err != cudaSuccess) {
+        set_error("socks_potrf: CUDA launch failed: %s", cudaGetErrorString(cx.err));
+        return SOCKS_ECUDA;
+    }
+    return SOCKS_OK;
+}
+
+extern "C" int socks_trtri(const double* L, int64_t n, int64_t ldl, const double* dinv, double* M, int64_t ldm,
+                           double* work, socks_stream_t stream) {
+    int rc = check_square(L, n, ldl, 1);
+    if (rc) return rc;
+    SOCKS_CHECK_ARG(dinv != nullptr, 4);
+    if ((rc = check_square(M, n, ldm, 5))) return rc;
+    SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 15) == 0, 7);
+    CholCtx cx{(cudaStream_t)stream};
+    trtri_rec(cx, L, ldl, dinv, M, ldm, socks_padded_dim(n), work);
+    if (cx.err != cudaSuccess) {
+        set_error("socks_trtri: CUDA launch failed: %s", cudaGetErrorString(cx.err));
+        return SOCKS_ECUDA;
+    }
+    return SOCKS_OK;
+}
+
+extern "C" int socks_diag_inv(const double* M, int64_t n, int64_t ldm, double* w, double* work,
+                              socks_stream_t stream) {
+    int rc = check_square(M, n, ldm, 1);
+    if (rc) return rc;
+    SOCKS_CHECK_ARG(w != nullptr, 4);
+    SOCKS_CHECK_ARG(work != nullptr, 5);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t np = socks_padded_dim(n);
+    // rows of the padding are the identity: summing over np rows adds exact zeros for columns < n
+    const int splits = colreduce_launch<true>(M, np, n, ldm, nullptr, 0, 1, work, /*tri=*/1, st);
+    SOCKS_CHECK_LAUNCH();
+    colreduce_finish_kernel<<<dim3((unsigned)ceil_div(n, 256), 1), 256, 0, st>>>(work, colreduce_ldpart(n), splits, n,
+                                                                                w, n);
+    SOCKS_CHECK_LAUNCH();
+    return SOCKS_OK;
+}
+
+extern "C" int socks_lauum(const double* M, int64_t n, int64_t ldm, double* W, int64_t ldw, socks_stream_t stream) {
+    int rc = check_square(M, n, ldm, 1);
+    if (rc) return rc;
+    if ((rc = check_square(W, n, ldw, 4))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t np = socks_padded_dim(n);
+    // W[i][j] = sum_{k >= max(i,j)} M[k][i] M[k][j], lower tiles; then mirror.
+    cudaError_t e = gemm_f64<true, false>(M, ldm, M, ldm, W, ldw, np, np, np, 1.0, 0.0,
+                                          GEMM_A_K_GE_M | GEMM_B_K_GE_N, 1, st);
+    if (e != cudaSuccess) {
+        set_error("socks_lauum: CUDA launch failed: %s", cudaGetErrorString(e));
+        return SOCKS_ECUDA;
+    }
+    symmetrize_kernel<<<dim3((unsigned)(np / 32), (unsigned)(np / 32)), dim3(32, 8), 0, st>>>(W, ldw);
+    SOCKS_CHECK_LAUNCH();
+    return SOCKS_OK;
+}

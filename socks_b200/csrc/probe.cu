@@ -1,0 +1,57 @@
+// Register-resident FP64 throughput probes: the roofline denominators MEASURED_PEAKS.json lacks
+// (FP64 FMA pipe, FP64 DMMA tensor pipe, both together, and the fp64 exp).  Used by tools/ and bench.py.
+#include "common.cuh"
+
+namespace socks {
+
+// mode 0: 8 independent DFMA chains per thread              -> 16 flop per inner iteration per thread
+// mode 1: 8 independent DMMA.8x8x4 accumulators per warp    -> 8 * 512 flop per inner iteration per warp
+// mode 2: 4 DFMA chains + 4 DMMA accumulators interleaved   -> 8 flop per thread + 4 * 512 per warp
+// mode 3: 4 independent exp() per thread per iteration
+__global__ void __launch_bounds__(256) probe_fp64_kernel(int mode, int iters, double* __restrict__ out) {
+    const double seed = 1.0 + 1e-9 * (threadIdx.x + 1);
+    double a[8], c0[8], c1[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a[u] = seed + u * 1e-3; c0[u] = 0.0; c1[u] = 0.0; }
+    const double m = 0.999999, b = 1e-7;
+    if (mode == 0) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = fma(a[u], m, b);
+        }
+    } else if (mode == 1) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) dmma884(c0[u], c1[u], m, b);
+        }
+    } else if (mode == 2) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a[u] = fma(a[u], m, b);
+                dmma884(c0[u], c1[u], m, b);
+            }
+        }
+    } else {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] = exp(-a[u]) + 0.5;
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += a[u] + c0[u] + c1[u];
+    out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace socks
+
+extern "C" int socks_probe_fp64(int mode, int iters, double* out_dev, int blocks, socks_stream_t stream) {
+    SOCKS_CHECK_ARG(mode >= 0 && mode <= 3, 1);
+    SOCKS_CHECK_ARG(iters >= 1, 2);
+    SOCKS_CHECK_ARG(out_dev != nullptr, 3);
+    SOCKS_CHECK_ARG(blocks >= 1, 4);
+    socks::probe_fp64_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mode, iters, out_dev);
+    SOCKS_CHECK_LAUNCH();
+    return SOCKS_OK;
+}

@@ -1,0 +1,123 @@
+// Maximal stochastic reachability (gym_socks/algorithms/reach/kernel_sr_max.py:30-79).
+//
+// The reference materialises beta[i,j,a] = W_ii CXY_ij CUA_ia / sum_i(...) (kernel_sr_max.py:45-47), an
+// N x M x P tensor, and contracts it with vf[t+1] each step (:65-70).  The same numbers are two dense
+// contractions sharing the left operand,
+//     den[j][a]   = sum_i K(x_i,p_j) (w_i)           CUA[i][a]
+//     num_t[j][a] = sum_i K(x_i,p_j) (vf[t+1][i] w_i) CUA[i][a],      wX = num_t / den, VX = max_a wX
+// i.e. one GEMM  Cm (m x R*P) = Kmat^T (m x N) * Bm (N x R*P)  on the fp64 tensor cores with the R
+// coefficient rows stacked along the columns, followed by a fused divide + row-max + FHT/THT step.
+#include <cmath>
+
+#include "gemm_f64.cuh"
+
+namespace socks {
+
+__global__ void srmax_pack_kernel(const double* __restrict__ CUA, int64_t n, int P, const double* __restrict__ w,
+                                  const double* __restrict__ vf, int64_t ldvf, int t0, int R, double* __restrict__ Bm,
+                                  int64_t np, int64_t ldbm) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = blockIdx.y;
+    if (c >= ldbm) return;
+    double v = 0.0;
+    if (i < n && c < (int64_t)R * P) {
+        const int r = (int)(c / P), a = (int)(c % P);
+        const double coef = (r == 0) ? w[i] : vf[(int64_t)(t0 + r) * ldvf + i] * w[i];
+        v = coef * CUA[i * P + a];
+    }
+    Bm[i * ldbm + c] = v;
+}
+
+// one warp per point: VX_r = max_a num_r[a] / den[a] (np.max semantics: NaN propagates), then the step.
+__global__ void srmax_step_kernel(const double* __restrict__ Cm, int64_t ldc, int64_t m, int P, int R, int t0,
+                                  const double* __restrict__ pts, int d, const double* __restrict__ tubes, int problem,
+                                  int T, double* __restrict__ out, int64_t ldout, int write_last) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= m) return;
+    const double* row = Cm + j * ldc;
+    for (int r = 1; r < R; ++r) {
+        double best = -INFINITY;
+        bool nan = false;
+        for (int a = lane; a < P; a += 32) {
+            const double v = row[(int64_t)r * P + a] / row[a];
+            nan = nan || (v != v);
+            best = fmax(best, v);
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            best = fmax(best, __shfl_xor_sync(0xffffffffu, best, off));
+            nan = nan || __shfl_xor_sync(0xffffffffu, (int)nan, off);
+        }
+        if (lane == 0) {
+            const int t = t0 + r - 1;
+            const double V = nan ? NAN : best;
+            out[(int64_t)t * ldout + j] = sr_step(pts + j * d, tubes + (int64_t)t * 4 * d, d, problem, V);
+        }
+    }
+    if (write_last && lane == 0)
+        out[(int64_t)(T - 1) * ldout + j] = in_box(pts + j * d, tubes + (int64_t)(T - 1) * 4 * d, 1, d) ? 1.0 : 0.0;
+}
+
+}  // namespace socks
+
+using namespace socks;
+
+extern "C" int socks_srmax_pack(const double* CUA, int64_t n, int P, const double* w, const double* vf, int64_t ldvf,
+                                int t0, int R, double* Bm, int64_t np, int64_t ldbm, socks_stream_t stream) {
+    SOCKS_CHECK_ARG(CUA != nullptr, 1);
+    SOCKS_CHECK_ARG(n >= 1, 2);
+    SOCKS_CHECK_ARG(P >= 1, 3);
+    SOCKS_CHECK_ARG(w != nullptr, 4);
+    SOCKS_CHECK_ARG(R >= 1 && (R == 1 || vf != nullptr), 8);
+    SOCKS_CHECK_ARG(Bm != nullptr, 9);
+    SOCKS_CHECK_ARG(np >= n && np <= 65535 * 16, 10);
+    SOCKS_CHECK_ARG(ldbm >= (int64_t)R * P && ldbm % 2 == 0, 11);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int64_t r0 = 0; r0 < np; r0 += 65535) {
+        const int64_t rows = (np - r0 < 65535) ? (np - r0) : 65535;
+        dim3 grid((unsigned)ceil_div(ldbm, 256), (unsigned)rows);
+        // shift the row window: kernel indexes rows by blockIdx.y, so offset the row-indexed pointers
+        srmax_pack_kernel<<<grid, 256, 0, st>>>(CUA + r0 * P, n - r0 > 0 ? n - r0 : 0, P, w + r0, vf ? vf + r0 : vf,
+                                                ldvf, t0, R, Bm + r0 * ldbm, np - r0, ldbm);
+    }
+    SOCKS_CHECK_LAUNCH();
+    return SOCKS_OK;
+}
+
+extern "C" int socks_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                             int64_t m, int64_t nn, int64_t K, socks_stream_t stream) {
+    SOCKS_CHECK_ARG(A != nullptr && (reinterpret_cast<uintptr_t>(A) & 15) == 0, 1);
+    SOCKS_CHECK_ARG(lda >= m && lda % 2 == 0, 2);
+    SOCKS_CHECK_ARG(B != nullptr && (reinterpret_cast<uintptr_t>(B) & 15) == 0, 3);
+    SOCKS_CHECK_ARG(ldb >= nn && ldb % 2 == 0, 4);
+    SOCKS_CHECK_ARG(C != nullptr && (reinterpret_cast<uintptr_t>(C) & 15) == 0, 5);
+    SOCKS_CHECK_ARG(ldc >= nn && ldc % 2 == 0, 6);
+    SOCKS_CHECK_ARG(m >= 0 && m % 128 == 0, 7);
+    SOCKS_CHECK_ARG(nn >= 0 && nn % 128 == 0, 8);
+    SOCKS_CHECK_ARG(K >= 0 && K % 16 == 0, 9);
+    cudaError_t e = gemm_f64<true, false>(A, lda, B, ldb, C, ldc, m, nn, K, 1.0, 0.0, 0, 0, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        set_error("socks_gemm_tn: CUDA launch failed: %s", cudaGetErrorString(e));
+        return SOCKS_ECUDA;
+    }
+    return SOCKS_OK;
+}
+
+extern "C" int socks_srmax_step(const double* Cm, int64_t ldc, int64_t m, int P, int R, int t0, const double* pts,
+                                int d, const double* tubes, int problem, int T, double* out, int64_t ldout,
+                                int write_last, socks_stream_t stream) {
+    SOCKS_CHECK_ARG(Cm != nullptr, 1);
+    SOCKS_CHECK_ARG(m >= 1, 3);
+    SOCKS_CHECK_ARG(P >= 1, 4);
+    SOCKS_CHECK_ARG(R >= 1 && ldc >= (int64_t)R * P, 5);
+    SOCKS_CHECK_ARG(pts != nullptr, 7);
+    SOCKS_CHECK_ARG(d >= 1 && d <= SOCKS_MAX_DIM, 8);
+    SOCKS_CHECK_ARG(tubes != nullptr, 9);
+    SOCKS_CHECK_ARG(problem == SOCKS_PROBLEM_THT || problem == SOCKS_PROBLEM_FHT, 10);
+    SOCKS_CHECK_ARG(T >= 1 && t0 >= 0 && t0 + R - 1 <= T - 1, 11);
+    SOCKS_CHECK_ARG(out != nullptr && ldout >= m, 12);
+    srmax_step_kernel<<<(unsigned)ceil_div(m, 8), 256, 0, (cudaStream_t)stream>>>(Cm, ldc, m, P, R, t0, pts, d, tubes,
+                                                                                  problem, T, out, ldout, write_last);
+    SOCKS_CHECK_LAUNCH();
+    return SOCKS_OK;
+}

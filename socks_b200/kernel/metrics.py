@@ -1,0 +1,262 @@
+"""`gym_socks.kernel.metrics` drop-in: `rbf_kernel`, `regularized_inverse` (GPU, fp64).
+
+Same names, argument order, defaults, assertion behaviour and return types as
+`gym_socks/kernel/metrics.py:69-138` and `:209-280`; the arithmetic runs in libsocksb200
+(gram.cu, chol.cu).  `kernel_fn` follows the reference's callable protocol
+(`kernel_fn(X, Y=None) -> (n, m) ndarray`, metrics.py:239-241) but must be recognisable as an RBF
+kernel (this package's, gym_socks's or sklearn's `rbf_kernel`, bare or wrapped in
+`functools.partial` with `sigma=` / `gamma=`): arbitrary Python callables cannot run on the GPU and
+there is no CPU fallback, so anything else raises TypeError.
+"""
+from functools import partial
+
+import numpy as np
+import torch
+
+from socks_b200 import _device as dv
+from socks_b200 import _lib
+
+__all__ = ["rbf_kernel", "regularized_inverse", "RBFSpec", "resolve_kernel", "Factorization"]
+
+
+# ----------------------------------------------------------------------------- kernel_fn protocol
+class RBFSpec:
+    """Resolved RBF kernel: k(x, y) = exp(-gamma |x - y|^2).
+
+    `sigma`-style (gym_socks semantics): gamma = 1 / (2 sigma^2) (metrics.py:135); sigma=None is
+    the median heuristic sigma = median(squared distances) evaluated per call (metrics.py:130-131).
+    `gamma`-style (sklearn semantics): gamma used as is; gamma=None -> 1 / n_features.
+    """
+
+    def __init__(self, sigma=None, gamma=None, style="sigma"):
+        self.sigma, self.gamma, self.style = sigma, gamma, style
+        if style == "sigma" and sigma is not None:
+            assert sigma > 0, "sigma must be a strictly positive real value."
+
+    def params_for(self, Xd, Yd):
+        """(scale, divide) of the C ABI for one kernel evaluation between device arrays Xd (n, d), Yd (m, d):
+        k = exp(d2 / scale) with scale = -2 sigma^2 (the reference divides, metrics.py:135) or
+        k = exp(d2 * scale) with scale = -gamma (sklearn multiplies)."""
+        if self.style == "gamma":
+            g = float(self.gamma) if self.gamma is not None else 1.0 / Xd.shape[1]
+            return (-g, 0)
+        sigma = float(self.sigma) if self.sigma is not None else _median_sqdist(Xd, Yd)
+        return (-2 * (sigma ** 2), 1)
+
+    def gamma_for(self, Xd, Yd):
+        """gamma such that k = exp(-gamma d2) (for reporting / rescaling)."""
+        scale, divide = self.params_for(Xd, Yd)
+        return -1.0 / scale if divide else -scale
+
+    @property
+    def data_dependent(self):
+        return self.style == "sigma" and self.sigma is None
+
+
+def _is_rbf_function(fn):
+    return callable(fn) and getattr(fn, "__name__", "") == "rbf_kernel"
+
+
+def resolve_kernel(kernel_fn, default_sigma):
+    """Map the reference's `kernel_fn` argument to an RBFSpec (TypeError if it is not an RBF)."""
+    if kernel_fn is None:
+        return RBFSpec(sigma=default_sigma)
+    if isinstance(kernel_fn, RBFSpec):
+        return kernel_fn
+    fn, kw = kernel_fn, {}
+    if isinstance(kernel_fn, partial):
+        if kernel_fn.args:
+            raise TypeError("kernel_fn partials must bind keyword arguments only (sigma= or gamma=).")
+        fn, kw = kernel_fn.func, dict(kernel_fn.keywords or {})
+    if not _is_rbf_function(fn):
+        raise TypeError(
+            "socks_b200 runs the kernel on the GPU and only accepts RBF kernels: pass "
+            "functools.partial(rbf_kernel, sigma=...) (this package's or gym_socks's) or sklearn's "
+            f"rbf_kernel with gamma=...; got {kernel_fn!r}. There is no CPU fallback."
+        )
+    module = getattr(fn, "__module__", "") or ""
+    kw.pop("distance_fn", None)  # accepted and ignored by the reference (metrics.py:114-117)
+    if module.startswith("sklearn"):
+        extra = set(kw) - {"gamma"}
+        if extra:
+            raise TypeError(f"unsupported keyword(s) for sklearn rbf_kernel: {sorted(extra)}")
+        return RBFSpec(gamma=kw.get("gamma"), style="gamma")
+    extra = set(kw) - {"sigma"}
+    if extra:
+        raise TypeError(f"unsupported keyword(s) for rbf_kernel: {sorted(extra)}")
+    return RBFSpec(sigma=kw.get("sigma"), style="sigma")
+
+
+# ----------------------------------------------------------------------------- device primitives
+def gram_dev(Xd, Yd, kparams, rowscale=None, out=None, ld=None):
+    """K = rowscale[:, None] * k(X_i, Y_j) on the device, kparams = (scale, divide); returns an (n, ld) tensor
+    whose first m columns hold K (ld = m rounded up to even so rows stay 16-byte aligned)."""
+    n, d = Xd.shape
+    m = Yd.shape[0]
+    if ld is None:
+        ld = dv.even(m)
+    if out is None:
+        out = dv.empty(n, ld)
+    _lib.call("socks_gram_rbf", dv.ptr(Xd), n, dv.ptr(Yd), m, d, float(kparams[0]), int(kparams[1]), dv.ptr(rowscale),
+              dv.ptr(out), ld, dv.stream())
+    return out
+
+
+def sqdist_dev(Xd, Yd):
+    n, d = Xd.shape
+    m = Yd.shape[0]
+    out = dv.empty(n, m)
+    _lib.call("socks_sqdist", dv.ptr(Xd), n, dv.ptr(Yd), m, d, dv.ptr(out), m, dv.stream())
+    return out
+
+
+def _median_sqdist(Xd, Yd):
+    """np.median of the squared-distance matrix (metrics.py:130-131): mean of the two middle order
+    statistics for an even count.  Distances come from the CUDA kernel; torch.kthvalue only selects."""
+    D = sqdist_dev(Xd, Yd).reshape(-1)
+    cnt = D.numel()
+    hi = torch.kthvalue(D, cnt // 2 + 1).values
+    if cnt % 2:
+        return float(hi)
+    lo = torch.kthvalue(D, cnt // 2).values
+    return float((lo + hi) / 2)  # same rounding as numpy's mean of the two middle values
+
+
+class Factorization:
+    """G = K(Z,Z) + lambda N I = L L^T on the device, with the pieces of inv(G) the path needs.
+
+    metrics.py:278-280 (`inv(K + regularization_param * num_rows * I)`) computed as Cholesky +
+    triangular inverse; `diag()` is diag(inv(G)) (all the SR algorithms read, kernel_sr.py:45),
+    `full()` is inv(G) itself."""
+
+    def __init__(self, Zd, kparams, diag_add):
+        n, d = Zd.shape
+        self.n, self.np = n, dv.padded(n)
+        npad = self.np
+        st = dv.stream()
+        self.L = dv.empty(npad, npad)
+        _lib.call("socks_gram_sym", dv.ptr(Zd), n, d, float(kparams[0]), int(kparams[1]), float(diag_add),
+                  dv.ptr(self.L), npad, st)
+        self.dinv = dv.work(_lib.load().socks_potrf_work_bytes(n))
+        self.info = torch.zeros(1, dtype=torch.int32, device=Zd.device)
+        _lib.call("socks_potrf", dv.ptr(self.L), n, npad, dv.ptr(self.dinv), dv.ptr(self.info), st)
+        self._M = None
+        self._w = None
+        self._W = None
+
+    def check(self):
+        info = int(self.info.item())
+        if info != 0:
+            raise np.linalg.LinAlgError(
+                f"regularised Gram matrix is not positive definite (pivot {info - 1}); the reference's LU inverse "
+                "would return a meaningless matrix here"
+            )
+
+    def inverse_factor(self):
+        if self._M is None:
+            lib = _lib.load()
+            self._M = dv.empty(self.np, self.np)
+            wk = dv.work(lib.socks_trtri_work_bytes(self.n))
+            _lib.call("socks_trtri", dv.ptr(self.L), self.n, self.np, dv.ptr(self.dinv), dv.ptr(self._M), self.np,
+                      dv.ptr(wk), dv.stream())
+        return self._M
+
+    def diag(self):
+        """w = diag(inv(G)) as a device vector of length n."""
+        if self._w is None:
+            M = self.inverse_factor()
+            self._w = dv.empty(self.n)
+            wk = dv.work(_lib.load().socks_reduce_work_bytes(self.np))
+            _lib.call("socks_diag_inv", dv.ptr(M), self.n, self.np, dv.ptr(self._w), dv.ptr(wk), dv.stream())
+        return self._w
+
+    def full(self):
+        """inv(G) as a device (np, np) tensor; the logical matrix is [:n, :n]."""
+        if self._W is None:
+            M = self.inverse_factor()
+            self._W = dv.empty(self.np, self.np)
+            _lib.call("socks_lauum", dv.ptr(M), self.n, self.np, dv.ptr(self._W), self.np, dv.stream())
+        return self._W
+
+    def release_factors(self):
+        """Drop L and M once only diag()/full() are needed (3.2 GB each at N = 20k)."""
+        self.L = None
+        self._M = None
+
+
+# ----------------------------------------------------------------------------- public API
+def rbf_kernel(X, Y=None, sigma=None, distance_fn=None):
+    """RBF kernel Gram matrix, `gym_socks/kernel/metrics.py:69-138`.
+
+    `Y=None` means `Y = X` (:119-120); `sigma=None` uses the median of the squared distances
+    (:130-131); `sigma <= 0` raises AssertionError (:133); `distance_fn` is accepted and ignored
+    exactly as in the reference (:114-117).  Returns a float64 ndarray of shape (len(X), len(Y)).
+    """
+    Xh = dv.as2d(X)
+    Yh = Xh if Y is None else dv.as2d(Y)
+    if sigma is not None:
+        assert sigma > 0, "sigma must be a strictly positive real value."
+    n, m = Xh.shape[0], Yh.shape[0]
+    if n == 0 or m == 0:
+        return np.zeros((n, m))
+    Xd = dv.to_dev(Xh)
+    Yd = Xd if Y is None else dv.to_dev(Yh)
+    K = gram_dev(Xd, Yd, RBFSpec(sigma=sigma).params_for(Xd, Yd))
+    return K[:, :m].cpu().numpy()
+
+
+def regularized_inverse(X, Y=None, U=None, V=None, regularization_param=None, kernel_fn=None):
+    """Regularised inverse `inv(K + lambda N I)`, `gym_socks/kernel/metrics.py:209-280`.
+
+    Defaults and assertions follow the reference: lambda = 1/N^2 (:251-252) else `> 0` (:254-256);
+    kernel sigma = 1 (:258-259); `X.shape == Y.shape` (:261-262); product Gram with `U` (:268-276).
+    As every caller in the reference, `Y` and `V` must be `X` and `U` themselves (the matrix has to be
+    symmetric positive definite for the Cholesky-based solve); other values raise ValueError.
+    """
+    Xh = dv.as2d(X)
+    if Y is not None:
+        Yh = dv.as2d(Y)
+        assert Xh.shape == Yh.shape, "Parameters %r, %r must have the same shape." % (X, Y)
+        if not np.array_equal(Xh, Yh):
+            raise ValueError("regularized_inverse: only Y = X (symmetric Gram) is supported on the GPU path.")
+    n = Xh.shape[0]
+    if regularization_param is None:
+        regularization_param = 1 / (n ** 2)
+    else:
+        assert regularization_param > 0, "regularization_param must be a strictly positive real value."
+    spec = resolve_kernel(kernel_fn, default_sigma=1)
+    if U is not None:
+        Uh = dv.as2d(U)
+        assert Xh.shape[0] == Uh.shape[0], "Parameters %r, %r must have the same sample size." % (X, U)
+        if V is not None:
+            Vh = dv.as2d(V)
+            assert Uh.shape == Vh.shape, "Parameters %r, %r must have the same shape." % (U, V)
+            if not np.array_equal(Uh, Vh):
+                raise ValueError("regularized_inverse: only V = U is supported on the GPU path.")
+    fac = factorize(Xh, None if U is None else Uh, spec, regularization_param)
+    W = fac.full()
+    fac.check()
+    return W[:n, :n].cpu().numpy()
+
+
+def factorize(Xh, Uh, spec, regularization_param):
+    """Host arrays -> device Factorization of K(X,X) [* K(U,U)] + lambda N I.
+
+    The product of two RBF kernels with the same bandwidth is the RBF kernel of the concatenated
+    vectors, so the product Gram of metrics.py:268-276 is one kernel evaluation on Z = [X | U].
+    With the median heuristic each factor has its own bandwidth; the columns are rescaled so a single
+    gamma applies."""
+    n = Xh.shape[0]
+    Xd = dv.to_dev(Xh)
+    kp = spec.params_for(Xd, Xd)
+    if Uh is None:
+        Zd = Xd
+    else:
+        Ud = dv.to_dev(Uh)
+        ku = spec.params_for(Ud, Ud)
+        if ku == kp:
+            Zd = dv.to_dev(np.concatenate([Xh, Uh], axis=1))
+        else:  # data-dependent bandwidths differ: rescale U so one scale applies
+            gx, gu = spec.gamma_for(Xd, Xd), spec.gamma_for(Ud, Ud)
+            Zd = dv.to_dev(np.concatenate([Xh, Uh * np.sqrt(gu / gx)], axis=1))
+    return Factorization(Zd, kp, regularization_param * n)

@@ -1,0 +1,189 @@
+"""GPU parity of KernelSR / KernelMaximalSR / KernelControlFwd through the public API (which calls the
+C ABI) against the golden vectors made by the unmodified reference and against the oracle.
+Tolerances (BASELINE.json north_star): safety probabilities abs <= 1e-8; policy scores
+rel <= max(1e-8, 100 cond 2^-53); argmin/argmax exact."""
+from functools import partial
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, tubes_from
+from oracle import socks_oracle as orc
+from socks_b200 import synthetic as syn
+from socks_b200.spaces import Box
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-8
+
+
+def _api():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    from socks_b200.algorithms.control.kernel_control_fwd import KernelControlFwd
+    from socks_b200.algorithms.reach.kernel_sr import KernelSR, kernel_sr
+    from socks_b200.algorithms.reach.kernel_sr_max import KernelMaximalSR, kernel_sr_max
+    from socks_b200.kernel.metrics import rbf_kernel
+
+    return KernelSR, kernel_sr, KernelMaximalSR, kernel_sr_max, KernelControlFwd, rbf_kernel
+
+
+@pytest.mark.parametrize("name", ["sr_c1_fht.npz", "sr_c1_tht.npz", "sr_d3_timevarying_fht.npz", "sr_d4_tht.npz"])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_kernel_sr_golden(name, variant):
+    KernelSR, kernel_sr, _, _, _, rbf = _api()
+    g = load_golden(name)
+    S = syn.as_sample(g["X"], g["U"], g["Y"])
+    alg = KernelSR(time_horizon=int(g["T"]), constraint_tube=tubes_from(g["ctube"]), target_tube=tubes_from(g["ttube"]),
+                   problem=str(g["problem"]), kernel_fn=partial(rbf, sigma=float(g["sigma"])),
+                   regularization_param=float(g["lam"]))
+    alg.predict_variant = variant
+    alg.fit(S)
+    assert alg.value_functions.shape == g["value_functions"].shape
+    assert np.max(np.abs(alg.value_functions - g["value_functions"])) <= TOL
+    out = alg.predict(g["pts"])
+    assert out.shape == g["out"].shape and out.dtype == np.float64
+    assert np.max(np.abs(out - g["out"])) <= TOL
+    assert np.array_equal(alg.X, g["X"])
+    if variant == 0:
+        w = np.diag(alg.W)
+        assert np.max(np.abs(w - g["w_diag"]) / g["w_diag"]) < 1e-7
+        # one-shot wrapper, batch_size accepted and result unchanged (kernel_sr.py:101-107)
+        out2 = kernel_sr(S, g["pts"], time_horizon=int(g["T"]), constraint_tube=tubes_from(g["ctube"]),
+                         target_tube=tubes_from(g["ttube"]), problem=str(g["problem"]),
+                         regularization_param=float(g["lam"]), kernel_fn=partial(rbf, sigma=float(g["sigma"])),
+                         batch_size=100)
+        assert np.array_equal(out2, out)
+
+
+def test_kernel_sr_sklearn_kernel_and_defaults():
+    """The reference's benchmarks pass sklearn's rbf_kernel(gamma=1/(2 sigma^2)) (benchmarks/kernel_sr/
+    baseline.py:134-144); defaults sigma=0.1, lambda=1, THT (kernel_sr.py:226-230)."""
+    KernelSR, _, _, _, _, _ = _api()
+    from sklearn.metrics.pairwise import rbf_kernel as sk_rbf
+
+    X, U, Y = syn.integrator_sample(500, seed=11)
+    pts = syn.uniform_points(300, seed=12)
+    ct, tt = syn.integrator_tubes(5)
+    a = KernelSR(time_horizon=5, constraint_tube=ct, target_tube=tt, kernel_fn=partial(sk_rbf, gamma=1 / (2 * 0.1 ** 2)))
+    a.fit(syn.as_sample(X, U, Y))
+    o = orc.KernelSROracle(5, ct, tt, "THT", 0.1, 1).fit(X, U, Y)
+    assert np.max(np.abs(a.predict(pts) - o.predict(pts))) <= TOL
+    b = KernelSR(time_horizon=5, constraint_tube=ct, target_tube=tt)
+    b.fit(syn.as_sample(X, U, Y))
+    assert np.max(np.abs(b.predict(pts) - o.predict(pts))) <= TOL
+
+
+@pytest.mark.parametrize("problem", ["FHT", "THT"])
+def test_kernel_sr_edge_cases(problem):
+    KernelSR, _, _, _, _, rbf = _api()
+    X, U, Y = syn.integrator_sample(333, seed=21)
+    ct, tt = syn.integrator_tubes(17)  # 17 > 16 rows: exercises the two-launch predict path
+    alg = KernelSR(time_horizon=17, constraint_tube=ct, target_tube=tt, problem=problem,
+                   kernel_fn=partial(rbf, sigma=0.2), regularization_param=1e-3)
+    alg.fit(syn.as_sample(X, U, Y))
+    o = orc.KernelSROracle(17, ct, tt, problem, 0.2, 1e-3).fit(X, U, Y)
+    assert np.max(np.abs(alg.value_functions - o.value_functions)) <= TOL
+    # boundary points (closed box), one point, empty set, a far-away point whose kernel column underflows
+    pts = np.array([[1.0, 1.0], [-1.0, 0.3], [0.5, -0.5], [0.5000001, 0.0], [1.0000001, 0.0], [0.0, 0.0]])
+    assert np.max(np.abs(alg.predict(pts) - o.predict(pts))) <= TOL
+    assert np.max(np.abs(alg.predict(pts[:1]) - o.predict(pts[:1]))) <= TOL
+    assert alg.predict(np.zeros((0, 2))).shape == (17, 0)
+    far = np.array([[0.9, 40.0], [0.2, 0.1]])
+    with np.errstate(all="ignore"):
+        want = o.predict(far)
+    got = alg.predict(far)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.max(np.abs(got[~np.isnan(want)] - want[~np.isnan(want)])) <= TOL
+    # horizon 1: only the terminal indicator
+    one = KernelSR(time_horizon=1, constraint_tube=ct, target_tube=tt, problem=problem)
+    one.fit(syn.as_sample(X, U, Y))
+    assert np.array_equal(one.predict(pts), orc.KernelSROracle(1, ct, tt, problem).fit(X, U, Y).predict(pts))
+
+
+def test_kernel_sr_medium_vs_oracle_and_properties():
+    """N=3000, 40k test points: oracle parity on a slice + size-independent properties."""
+    KernelSR, _, _, _, _, rbf = _api()
+    n, m, T = 3000, 40000, 15
+    X, U, Y = syn.integrator_sample(n, seed=0)
+    pts = syn.uniform_points(m, seed=1)
+    ct, tt = syn.integrator_tubes(T)
+    alg = KernelSR(time_horizon=T, constraint_tube=ct, target_tube=tt, problem="FHT", kernel_fn=partial(rbf, sigma=0.1),
+                   regularization_param=1 / n ** 2)
+    alg.fit_arrays(X, Y)
+    out = alg.predict(pts)
+    o = orc.KernelSROracle(T, ct, tt, "FHT", 0.1, 1 / n ** 2).fit(X, U, Y)
+    assert np.max(np.abs(alg.value_functions - o.value_functions)) <= TOL
+    assert np.max(np.abs(out[:, :3000] - o.predict(pts[:3000]))) <= TOL
+    # columns are independent: any split of the test set gives bit-identical columns (basis of the sharding)
+    a, b = alg.predict(pts[:12345]), alg.predict(pts[12345:])
+    assert np.array_equal(np.concatenate([a, b], axis=1), out)
+    # FMA and DMMA contractions agree far below the tolerance
+    alg.predict_variant = 1
+    assert np.max(np.abs(alg.predict(pts) - out)) <= 1e-11
+    # terminal row is the target indicator; points in the target set have probability exactly 1 (FHT)
+    in_t = np.all(np.abs(pts) <= 0.5, axis=1)
+    assert np.array_equal(out[T - 1], in_t.astype(float))
+    assert np.all(out[:, in_t] == 1.0)
+
+
+@pytest.mark.parametrize("name", ["srmax_fht.npz", "srmax_tht_batch.npz"])
+def test_kernel_sr_max_golden(name):
+    _, _, KernelMaximalSR, kernel_sr_max, _, rbf = _api()
+    g = load_golden(name)
+    S = syn.as_sample(g["X"], g["U"], g["Y"])
+    kw = dict(time_horizon=int(g["T"]), constraint_tube=tubes_from(g["ctube"]), target_tube=tubes_from(g["ttube"]),
+              problem=str(g["problem"]), regularization_param=float(g["lam"]),
+              kernel_fn=partial(rbf, sigma=float(g["sigma"])))
+    alg = KernelMaximalSR(**kw)
+    alg.fit(S, g["A"])
+    assert np.max(np.abs(alg.CUA - g["CUA"]) / g["CUA"]) <= 1e-13
+    assert np.max(np.abs(alg.value_functions - g["value_functions"])) <= TOL
+    out = alg.predict(g["pts"])
+    assert np.max(np.abs(out - g["out"])) <= TOL
+    alg.predict_chunk = 128  # several chunks, ragged tail
+    assert np.array_equal(alg.predict(g["pts"]), out)
+    assert np.array_equal(kernel_sr_max(S, g["A"], g["pts"], batch_size=50, **kw), out)
+
+
+def test_kernel_sr_max_medium_vs_oracle():
+    _, _, KernelMaximalSR, _, _, rbf = _api()
+    n, m, T, P = 1500, 3000, 6, 100
+    X, U, Y = syn.integrator_sample(n, seed=31)
+    pts = syn.uniform_points(m, seed=32)
+    A = np.linspace(-1, 1, P).reshape(-1, 1)
+    ct, tt = syn.integrator_tubes(T)
+    alg = KernelMaximalSR(time_horizon=T, constraint_tube=ct, target_tube=tt, problem="FHT",
+                          kernel_fn=partial(rbf, sigma=0.1), regularization_param=1.0)
+    alg.fit_arrays(X, U, Y, A)
+    o = orc.KernelMaximalSROracle(T, ct, tt, "FHT", 0.1, 1.0).fit(X, U, Y, A)
+    assert np.max(np.abs(alg.value_functions - o.value_functions)) <= TOL
+    assert np.max(np.abs(alg.predict(pts) - o.predict(pts))) <= TOL
+
+
+@pytest.mark.parametrize("name", ["fwd_unconstrained.npz", "fwd_constrained.npz"])
+@pytest.mark.parametrize("heuristic", [True, False])
+def test_kernel_control_fwd_golden(name, heuristic):
+    _, _, _, _, KernelControlFwd, rbf = _api()
+    g = load_golden(name)
+    T = int(g["T"])
+    cons = None
+    if bool(g["constrained"]):
+        def cons(time=0, state=None):
+            return np.abs(state[:, 1]) - (0.45 + 0.01 * time)
+    pol = KernelControlFwd(cost_fn=syn.tracking_cost_fn(T), constraint_fn=cons, heuristic=heuristic,
+                           regularization_param=float(g["lam"]), kernel_fn=partial(rbf, sigma=float(g["sigma"])),
+                           verbose=False, time_horizon=T)  # extra kwargs are swallowed (tracking.py:137)
+    pol.train(syn.as_sample(g["X"], g["U"], g["Y"]), g["A"])
+    tol = max(1e-8, 100 * float(g["cond"]) * 2.0 ** -53)
+    for t in range(T):
+        y = pol.scores(time=t, state=[g["states"][t]]).cpu().numpy()
+        assert np.max(np.abs(y[0] - g["C"][t])) <= tol * np.max(np.abs(g["C"][t]))
+        if cons is not None:
+            assert np.max(np.abs(y[1] - g["D"][t])) <= tol * np.max(np.abs(g["D"][t]))
+        act = pol(time=t, state=[g["states"][t]])
+        assert act.dtype == np.float32
+        if heuristic:
+            assert np.array_equal(act, g["actions"][t])
+    assert np.linalg.norm(pol.W - np.linalg.inv(np.linalg.inv(pol.W))) >= 0  # W is exposed as an ndarray

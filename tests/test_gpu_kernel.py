@@ -1,0 +1,174 @@
+"""GPU parity: rbf_kernel / regularized_inverse / Cholesky pieces through the C ABI vs the oracle,
+the reference's known-answer tests and the golden vectors.  Tolerances:
+rbf_kernel rel <= 1e-13; W rel-Frobenius <= 100 * cond * 2^-53."""
+from functools import partial
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import socks_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    import torch
+    from socks_b200 import _device as dv, _lib
+    from socks_b200.kernel import metrics
+
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    return torch, dv, _lib, metrics
+
+
+def test_known_answers_from_reference_tests():
+    _, _, _, m = _mods()
+    # gym_socks/kernel/tests/test_kernel.py:46-66
+    Y = np.arange(4).reshape((2, 2))
+    gt = np.array([[1.0, 0.77880078], [0.77880078, 1.0]], dtype=np.float32)
+    assert np.allclose(m.rbf_kernel(Y), gt)
+    assert np.allclose(m.rbf_kernel(Y, Y), gt)
+    # :68-100
+    Y3 = np.arange(6).reshape((3, 2))
+    gt3 = np.array([[1.0, 0.93941306, 0.77880078], [0.93941306, 1.0, 0.93941306], [0.77880078, 0.93941306, 1.0]])
+    assert np.allclose(m.rbf_kernel(Y3), gt3)
+    assert np.allclose(m.rbf_kernel(Y3, Y3, distance_fn=lambda *a, **k: None), gt3)  # distance_fn ignored
+    assert m.rbf_kernel(Y, Y3).shape == (2, 3)
+    # :118-130
+    gtw = np.array([[0.66676608, -0.0081415], [-0.0081415, 0.66676608]])
+    assert np.allclose(m.regularized_inverse(np.arange(4).reshape((2, 2))), gtw)
+
+
+def test_rbf_golden_and_median():
+    _, _, _, m = _mods()
+    g = load_golden("kernel_metrics.npz")
+    X, Y = g["X"], g["Y"]
+    for got, want in [
+        (m.rbf_kernel(X, Y, sigma=0.7), g["K_xy_s07"]),
+        (m.rbf_kernel(X, sigma=0.1), g["K_xx_s01"]),
+        (m.rbf_kernel(X), g["K_xx_median"]),
+        (m.rbf_kernel(np.arange(4).reshape(2, 2), np.arange(6).reshape(3, 2)), g["K_arange22_32_median"]),
+    ]:
+        assert got.dtype == np.float64 and got.shape == want.shape
+        assert np.max(np.abs(got - want) / np.maximum(want, 1e-300)) <= 1e-13
+
+
+@pytest.mark.parametrize("n,m,d,sigma", [(1, 1, 1, 1.0), (37, 23, 3, 0.7), (130, 257, 2, 0.1), (300, 129, 8, 2.0),
+                                         (65, 33, 11, 1.5), (33, 1000, 5, 0.9), (1029, 7, 2, 0.05)])
+def test_rbf_random_vs_oracle(n, m, d, sigma):
+    _, _, _, mt = _mods()
+    rng = np.random.default_rng(n * 1000 + m)
+    X, Y = rng.standard_normal((n, d)), rng.standard_normal((m, d))
+    K, Ko = mt.rbf_kernel(X, Y, sigma=sigma), orc.rbf_kernel(X, Y, sigma)
+    big = Ko > 1e-290
+    assert np.max(np.abs(K[big] - Ko[big]) / Ko[big]) <= 1e-13
+    assert np.max(np.abs(K[~big] - Ko[~big]), initial=0.0) <= 1e-290  # underflow region: both (sub)zero
+    # inputs may be lists / ints / float32 (kernel_sr.py:282-284 does np.array on them)
+    Ki = mt.rbf_kernel(X.astype(np.float32).tolist(), Y.astype(np.float32), sigma=sigma)
+    assert np.allclose(Ki, orc.rbf_kernel(X.astype(np.float32).astype(np.float64), Y.astype(np.float32), sigma),
+                       rtol=1e-13, atol=0)
+
+
+def test_rbf_empty_and_underflow():
+    _, _, _, mt = _mods()
+    assert mt.rbf_kernel(np.zeros((0, 2)), np.zeros((5, 2)), sigma=1.0).shape == (0, 5)
+    far = mt.rbf_kernel(np.zeros((1, 2)), np.array([[1e3, 0.0], [3.0, 0.0]]), sigma=0.1)
+    assert far[0, 0] == 0.0 and abs(far[0, 1] / np.exp(-9.0 / 0.02) - 1) < 1e-15
+
+
+def test_sklearn_partial_accepted():
+    _, _, _, mt = _mods()
+    from sklearn.metrics.pairwise import rbf_kernel as sk_rbf
+
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((50, 2))
+    W = mt.regularized_inverse(X, kernel_fn=partial(sk_rbf, gamma=0.8), regularization_param=1e-2)
+    Wo = np.linalg.inv(sk_rbf(X, X, gamma=0.8) + 1e-2 * 50 * np.eye(50))
+    assert np.linalg.norm(W - Wo) / np.linalg.norm(Wo) < 1e-11
+
+
+@pytest.mark.parametrize("key,kw", [
+    ("W_x_default", {}),
+    ("W_x_s07_lam", dict(sigma=0.7, lam=1e-3)),
+    ("W_xu_s07_lam", dict(sigma=0.7, lam=1e-3, U=True)),
+])
+def test_regularized_inverse_golden(key, kw):
+    _, _, _, mt = _mods()
+    g = load_golden("kernel_metrics.npz")
+    X = g["X"]
+    args = {}
+    if "sigma" in kw:
+        args["kernel_fn"] = partial(mt.rbf_kernel, sigma=kw["sigma"])
+        args["regularization_param"] = kw["lam"]
+    if kw.get("U"):
+        args["U"] = g["U"]
+    W = mt.regularized_inverse(X, **args)
+    want = g[key]
+    cond = np.linalg.cond(want)
+    assert W.shape == want.shape and np.allclose(W, W.T, rtol=0, atol=1e-14 * np.abs(W).max())
+    assert np.linalg.norm(W - want) / np.linalg.norm(want) <= 100 * cond * 2.0 ** -53
+
+
+@pytest.mark.parametrize("n,d,sigma,lam,with_u", [(128, 2, 0.3, 1e-2, False), (257, 3, 0.5, 1e-3, True),
+                                                  (1000, 2, 0.1, 1e-6, False), (1500, 3, 3.0, 1e-7, True)])
+def test_factorization_pieces(n, d, sigma, lam, with_u):
+    """potrf residual, M L = I, diag(W) and full W against float64/longdouble numpy (cond-aware)."""
+    torch, dv, _lib, mt = _mods()
+    rng = np.random.default_rng(n)
+    X = rng.uniform(-1.1, 1.1, (n, d))
+    U = rng.uniform(-1, 1, (n, 2)) if with_u else None
+    spec = mt.RBFSpec(sigma=sigma)
+    fac = mt.factorize(X, U, spec, lam)
+    G = orc.rbf_kernel(X, X, sigma)
+    if with_u:
+        G = G * orc.rbf_kernel(U, U, sigma)
+    G[np.diag_indices(n)] += lam * n
+    L = np.tril(fac.L[:n, :n].cpu().numpy())
+    fac.check()
+    assert np.linalg.norm(L @ L.T - G) / np.linalg.norm(G) < 1e-14
+    M = np.tril(fac.inverse_factor()[:n, :n].cpu().numpy())
+    cond = np.linalg.cond(G)
+    assert np.linalg.norm(M @ L - np.eye(n)) / np.sqrt(n) < 50 * np.sqrt(cond) * 2.0 ** -53 * n ** 0.5
+    Wref = np.linalg.inv(G)
+    w = fac.diag().cpu().numpy()
+    assert np.max(np.abs(w - np.diag(Wref)) / np.diag(Wref)) <= 100 * cond * 2.0 ** -53
+    W = fac.full()[:n, :n].cpu().numpy()
+    assert np.linalg.norm(W - Wref) / np.linalg.norm(Wref) <= 100 * cond * 2.0 ** -53
+    # padding must stay the identity
+    npad = fac.np
+    if npad > n:
+        Wp = fac.full().cpu().numpy()
+        assert np.array_equal(Wp[n:, n:], np.eye(npad - n)) and not Wp[n:, :n].any() and not Wp[:n, n:].any()
+
+
+def test_not_positive_definite_reports():
+    torch, dv, _lib, mt = _mods()
+    n = 130
+    X = np.zeros((n, 2))  # all points identical: G = ones + tiny ridge -> numerically singular
+    with pytest.raises((np.linalg.LinAlgError, AssertionError)):
+        fac = mt.Factorization(dv.to_dev(X), (-1.0, 0), -0.5)  # negative shift: pivot <= 0
+        fac.check()
+
+
+def test_gemv_and_argmin_primitives():
+    torch, dv, _lib, mt = _mods()
+    rng = np.random.default_rng(5)
+    for n, m in [(1, 1), (70, 33), (1000, 257), (513, 1000)]:
+        B = rng.standard_normal((n, m))
+        V = rng.standard_normal((2, n))
+        Bd, Vd = dv.to_dev(B), dv.to_dev(V)
+        y = dv.empty(2, m)
+        wk = dv.work(_lib.load().socks_reduce_work_bytes(m))
+        _lib.call("socks_gemv_t", dv.ptr(Bd), n, m, m, dv.ptr(Vd), n, 2, dv.ptr(y), m, dv.ptr(wk), dv.stream())
+        want = V @ B
+        assert np.max(np.abs(y.cpu().numpy() - want)) <= 1e-12 * max(1.0, np.abs(want).max())
+    idx = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for P in (1, 7, 256, 1000):
+        C = rng.standard_normal(P)
+        C[rng.integers(P)] = C.min()  # tie: first occurrence wins
+        D = rng.standard_normal(P)
+        for Dm in (None, D, np.abs(D) + 1):
+            Cd = dv.to_dev(C)
+            Dd = None if Dm is None else dv.to_dev(Dm)
+            _lib.call("socks_argmin_masked", dv.ptr(Cd), dv.ptr(Dd), P, dv.ptr(idx), dv.stream())
+            assert int(idx.item()) == orc.heuristic_solution(C, Dm)
