@@ -65,15 +65,18 @@ def test_rbf_random_vs_oracle(n, m, d, sigma):
     assert np.max(np.abs(K[~big] - Ko[~big]), initial=0.0) <= 1e-290  # underflow region: both (sub)zero
     # inputs may be lists / ints / float32 (kernel_sr.py:282-284 does np.array on them)
     Ki = mt.rbf_kernel(X.astype(np.float32).tolist(), Y.astype(np.float32), sigma=sigma)
-    assert np.allclose(Ki, orc.rbf_kernel(X.astype(np.float32).astype(np.float64), Y.astype(np.float32), sigma),
-                       rtol=1e-13, atol=0)
+    Kio = orc.rbf_kernel(X.astype(np.float32).astype(np.float64), Y.astype(np.float32), sigma)
+    big = Kio > 1e-290
+    assert np.max(np.abs(Ki[big] - Kio[big]) / Kio[big]) <= 1e-13
+    assert np.max(np.abs(Ki[~big] - Kio[~big]), initial=0.0) <= 1e-290
 
 
 def test_rbf_empty_and_underflow():
     _, _, _, mt = _mods()
     assert mt.rbf_kernel(np.zeros((0, 2)), np.zeros((5, 2)), sigma=1.0).shape == (0, 5)
     far = mt.rbf_kernel(np.zeros((1, 2)), np.array([[1e3, 0.0], [3.0, 0.0]]), sigma=0.1)
-    assert far[0, 0] == 0.0 and abs(far[0, 1] / np.exp(-9.0 / 0.02) - 1) < 1e-15
+    want = orc.rbf_kernel(np.zeros((1, 2)), np.array([[3.0, 0.0]]), 0.1)[0, 0]  # exp(9 / (-2 * 0.1**2))
+    assert far[0, 0] == 0.0 and abs(far[0, 1] / want - 1) < 1e-15
 
 
 def test_sklearn_partial_accepted():
