@@ -103,11 +103,14 @@ int socks_sr_recursion(const double* B, int64_t n, int64_t m, int64_t ldb, const
 
 /* Fused predict (kernel_sr.py:329-342 without materialising K(X,pts)):
  *   out[t][j] = step(pts_j, sum_i vf[t+1][i] w_i k(x_i,pts_j) / sum_i w_i k(x_i,pts_j)).
- * coef: workspace of n * 20 doubles per 15 time steps (packed by the library).
- * variant: 0 = DMMA contraction (default), 1 = FMA-pipe contraction. */
+ * work: socks_sr_predict_work_bytes(n, m) bytes (packed coefficients + per-split partial sums).
+ * variant: 0 = DMMA contraction (default), 1 = FMA-pipe contraction.  The sample axis is cut into fixed
+ * 2048-sample splits summed in order, so each output column is bit-identical however the test points
+ * are chunked or sharded. */
+int64_t socks_sr_predict_work_bytes(int64_t n, int64_t m);
 int socks_sr_predict(const double* X, const double* w, const double* vf, int64_t ldvf, int64_t n, int d,
                      double scale, int divide, const double* pts, int64_t m, const double* tubes, int problem, int T,
-                     double* out, int64_t ldout, double* coef, int variant, socks_stream_t stream);
+                     double* out, int64_t ldout, double* work, int variant, socks_stream_t stream);
 
 /* ---- Maximal SR: gym_socks/algorithms/reach/kernel_sr_max.py:30-79 --------------------- */
 

@@ -31,6 +31,7 @@ SIGNATURES = {
     "socks_diag_inv": (_I, [_P, _L, _L, _P, _P, _P]),
     "socks_lauum": (_I, [_P, _L, _L, _P, _L, _P]),
     "socks_sr_recursion": (_I, [_P, _L, _L, _L, _P, _I, _P, _I, _I, _P, _L, _P, _L, _P, _P]),
+    "socks_sr_predict_work_bytes": (_L, [_L, _L]),
     "socks_sr_predict": (_I, [_P, _P, _P, _L, _L, _I, _D, _I, _P, _L, _P, _I, _I, _P, _L, _P, _I, _P]),
     "socks_srmax_pack": (_I, [_P, _L, _I, _P, _P, _L, _I, _I, _P, _L, _L, _P]),
     "socks_gemm_tn": (_I, [_P, _L, _P, _L, _P, _L, _L, _L, _L, _P]),

@@ -114,10 +114,35 @@ class KernelSR:
 
     _keep_factors = True  # `.W` stays available; set False to free L and M right after fit
 
+    predict_chunks = 4  # D2H of chunk c overlaps the kernel of chunk c+1 (only for large M)
+
     def predict(self, T):
+        """Host in, host out (`kernel_sr.py:311-344`): (m, d) points -> (time_horizon, m) float64 ndarray."""
         self._validate_data(T)
-        out = self.predict_dev(dv.to_dev(dv.as2d(T)))
-        return out.cpu().numpy()
+        pts_h = dv.as2d(T)
+        m, Th = pts_h.shape[0], int(self.time_horizon)
+        if m == 0 or Th == 0:
+            return np.empty((Th, m))
+        import torch
+
+        src = torch.from_numpy(pts_h)
+        pts = src.to(dv.device(), non_blocking=src.is_pinned())
+        host = dv.host_pool.get(Th, m)
+        out = self._cached("out", (Th, m))
+        nchunks = self.predict_chunks if m >= 65536 else 1
+        chunk = -(-(-(-m // nchunks)) // 256) * 256
+        cs = dv.copy_stream()
+        for s in range(0, m, chunk):
+            e = min(m, s + chunk)
+            self._predict_into(pts[s:e], out[:, s:e])
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(cs):
+                cs.wait_event(ev)
+                for t in range(Th):  # row segments are contiguous on both sides: plain async memcpys
+                    host[t, s:e].copy_(out[t, s:e], non_blocking=True)
+        cs.synchronize()
+        return host.numpy()
 
     def predict_dev(self, pts):
         """Device in, device out: (m, d) test points -> (time_horizon, m) safety probabilities."""
@@ -126,12 +151,25 @@ class KernelSR:
         out = dv.empty(max(Th, 1), max(m, 1))[:Th, :m]
         if m == 0 or Th == 0:
             return out
-        scale, divide = self._spec.params_for(self._Xd, pts)
-        coef = dv.work(8 * 20 * (dv.padded(self._n) + 128))
-        _lib.call("socks_sr_predict", dv.ptr(self._Xd), dv.ptr(self._w), dv.ptr(self._vf), self._n, self._n, self._d,
-                  float(scale), int(divide), dv.ptr(pts), m, dv.ptr(self._tubes), PROBLEM_CODE[self.problem], Th,
-                  dv.ptr(out), out.stride(0), dv.ptr(coef), int(self.predict_variant), dv.stream())
+        self._predict_into(pts, out)
         return out
+
+    def _cached(self, name, shape):
+        cache = self.__dict__.setdefault("_buf_cache", {})
+        t = cache.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = cache[name] = dv.empty(*shape)
+        return t
+
+    def _predict_into(self, pts, out):
+        m = pts.shape[0]
+        scale, divide = self._spec.params_for(self._Xd, pts)
+        nbytes = _lib.load().socks_sr_predict_work_bytes(self._n, m)
+        work = self._cached("work", ((nbytes + 7) // 8 + 2,))
+        _lib.call("socks_sr_predict", dv.ptr(self._Xd), dv.ptr(self._w), dv.ptr(self._vf), self._n, self._n, self._d,
+                  float(scale), int(divide), dv.ptr(pts), m, dv.ptr(self._tubes), PROBLEM_CODE[self.problem],
+                  int(self.time_horizon), dv.ptr(out), out.stride(0), dv.ptr(work), int(self.predict_variant),
+                  dv.stream())
 
     # -- attributes the reference exposes (kernel_sr.py:286-309)
     @property

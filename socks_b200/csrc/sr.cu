@@ -56,6 +56,8 @@ constexpr int SP_TS = 64;        // samples per shared-memory stage
 constexpr int SP_WARPS = 8;
 constexpr int SP_Q = 4;          // 8-point n-tiles per warp
 constexpr int SP_PTS = SP_WARPS * SP_Q * 8;  // 256 points per CTA
+constexpr int SP_SPLIT = 2048;   // samples per CTA (blockIdx.y): a FIXED split, so the summation order -- and
+                                 // hence every output bit -- does not depend on M, chunking or sharding
 
 template <int D>
 __device__ __forceinline__ void sp_load_stage(double* __restrict__ sx, double* __restrict__ sc,
@@ -70,15 +72,16 @@ __device__ __forceinline__ void sp_load_stage(double* __restrict__ sx, double* _
     }
 }
 
-// variant 0: DMMA contraction.  CTA = 8 warps x 32 points; each lane evaluates k(x_s, p) for sample
-// s = 4*ks + lane%4 and the points {8q + lane/4}, q < 4, which is exactly the B-fragment layout of
-// mma.m8n8k4 (B[k = lane%4][n = lane/4]).
+// variant 0: DMMA contraction.  CTA = 8 warps x 32 points x one 2048-sample split; each lane evaluates
+// k(x_s, p) for sample s = 4*ks + lane%4 and the points {8q + lane/4}, q < 4, which is exactly the B-fragment
+// layout of mma.m8n8k4 (B[k = lane%4][n = lane/4]).  Partial sums go to part[split][16][ldp]; the finish
+// kernel adds the splits in order, divides by the normaliser row and applies the FHT/THT step.  Splitting
+// the sample axis gives N/2048 times more CTAs than point tiles alone: no wave-quantisation tail.
 template <int D>
 __global__ void __launch_bounds__(SP_WARPS * 32)
     sr_predict_dmma_kernel(const double* __restrict__ X, const double* __restrict__ coef, int64_t n, int64_t n_pad,
-                           const double* __restrict__ pts, int64_t m, double neg_gamma,
-                           const double* __restrict__ tubes, int problem, int t0, int R, double* __restrict__ out,
-                           int64_t ldout) {
+                           const double* __restrict__ pts, int64_t m, double neg_gamma, double* __restrict__ part,
+                           int64_t ldp) {
     __shared__ __align__(16) double sx[2][SP_TS * D];
     __shared__ __align__(16) double sc[2][SP_TS * SR_CP];
     __shared__ double etbl[EXP_TBL];
@@ -100,14 +103,15 @@ __global__ void __launch_bounds__(SP_WARPS * 32)
 #pragma unroll
         for (int h = 0; h < 2; ++h) acc[q][h][0] = acc[q][h][1] = 0.0;
 
-    const int ntiles = (int)(n_pad / SP_TS);
-    sp_load_stage<D>(sx[0], sc[0], X, coef, n, 0, tid, SP_WARPS * 32);
+    const int tile0 = blockIdx.y * (SP_SPLIT / SP_TS);
+    const int tile1 = min((int)(n_pad / SP_TS), tile0 + SP_SPLIT / SP_TS);
+    sp_load_stage<D>(sx[0], sc[0], X, coef, n, (int64_t)tile0 * SP_TS, tid, SP_WARPS * 32);
     cp_async_commit();
-    for (int tile = 0; tile < ntiles; ++tile) {
-        const int cur = tile & 1;
+    for (int tile = tile0; tile < tile1; ++tile) {
+        const int cur = (tile - tile0) & 1;
         cp_async_wait<0>();
         __syncthreads();  // stage `cur` visible to all; everyone is done reading stage cur^1
-        if (tile + 1 < ntiles)
+        if (tile + 1 < tile1)
             sp_load_stage<D>(sx[cur ^ 1], sc[cur ^ 1], X, coef, n, (int64_t)(tile + 1) * SP_TS, tid, SP_WARPS * 32);
         cp_async_commit();
         const double* x_s = sx[cur];
@@ -135,23 +139,37 @@ __global__ void __launch_bounds__(SP_WARPS * 32)
         }
     }
 
-    // epilogue: row 0 of the accumulator tile is the normaliser; rows r >= 1 are time steps t0+r-1.
+    // epilogue: accumulator rows r = lq (+8) of this split -> part[split][r][j], 16-byte stores
+    double* pbase_out = part + (int64_t)blockIdx.y * 16 * ldp;
 #pragma unroll
     for (int q = 0; q < SP_Q; ++q) {
+        const int64_t j = pbase + q * 8 + 2 * lr;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const double den = __shfl_sync(0xffffffffu, acc[q][0][e], lr);
-            const int64_t j = pbase + q * 8 + 2 * lr + e;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int r = lq + 8 * h;
-                if (r >= 1 && r < R && j < m) {
-                    const int t = t0 + r - 1;
-                    out[(int64_t)t * ldout + j] =
-                        sr_step(pts + j * D, tubes + (int64_t)t * 4 * D, D, problem, acc[q][h][e] / den);
-                }
+        for (int h = 0; h < 2; ++h) {
+            double* dst = pbase_out + (int64_t)(lq + 8 * h) * ldp + j;
+            if (j + 1 < m) {
+                *reinterpret_cast<double2*>(dst) = make_double2(acc[q][h][0], acc[q][h][1]);
+            } else if (j < m) {
+                dst[0] = acc[q][h][0];
             }
         }
+    }
+}
+
+// out[t0+r-1][j] = step(pts_j, (sum_s part[s][r][j]) / (sum_s part[s][0][j])),  1 <= r < R
+__global__ void sr_predict_finish_kernel(const double* __restrict__ part, int64_t ldp, int splits, int64_t m, int R,
+                                         int t0, const double* __restrict__ pts, int d,
+                                         const double* __restrict__ tubes, int problem, double* __restrict__ out,
+                                         int64_t ldout) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    double den = 0.0;
+    for (int s = 0; s < splits; ++s) den += part[(int64_t)s * 16 * ldp + j];
+    for (int r = 1; r < R; ++r) {
+        double num = 0.0;
+        for (int s = 0; s < splits; ++s) num += part[((int64_t)s * 16 + r) * ldp + j];
+        const int t = t0 + r - 1;
+        out[(int64_t)t * ldout + j] = sr_step(pts + j * d, tubes + (int64_t)t * 4 * d, d, problem, num / den);
     }
 }
 
@@ -313,20 +331,30 @@ extern "C" int socks_sr_recursion(const double* B, int64_t n, int64_t m, int64_t
 
 template <int D>
 static void launch_predict(int variant, const double* X, const double* coef, int64_t n, int64_t n_pad,
-                           const double* pts, int64_t m, double neg_gamma, const double* tubes, int problem, int t0,
-                           int R, double* out, int64_t ldout, cudaStream_t st) {
+                           const double* pts, int64_t m, double kmul, const double* tubes, int problem, int t0,
+                           int R, double* out, int64_t ldout, double* part, int64_t ldp, int splits,
+                           cudaStream_t st) {
     if (variant == 0) {
-        sr_predict_dmma_kernel<D><<<(unsigned)ceil_div(m, SP_PTS), SP_WARPS * 32, 0, st>>>(
-            X, coef, n, n_pad, pts, m, neg_gamma, tubes, problem, t0, R, out, ldout);
+        dim3 grid((unsigned)ceil_div(m, SP_PTS), (unsigned)splits);
+        sr_predict_dmma_kernel<D><<<grid, SP_WARPS * 32, 0, st>>>(X, coef, n, n_pad, pts, m, kmul, part, ldp);
+        sr_predict_finish_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(part, ldp, splits, m, R, t0, pts, D,
+                                                                             tubes, problem, out, ldout);
     } else {
-        sr_predict_fma_kernel<D><<<(unsigned)ceil_div(m, 128), 128, 0, st>>>(X, coef, n, n_pad, pts, m, neg_gamma,
-                                                                            tubes, problem, t0, R, out, ldout);
+        sr_predict_fma_kernel<D><<<(unsigned)ceil_div(m, 128), 128, 0, st>>>(X, coef, n, n_pad, pts, m, kmul, tubes,
+                                                                            problem, t0, R, out, ldout);
     }
+}
+
+static inline int64_t predict_coef_doubles(int64_t n) { return round_up(n, SP_TS) * SR_CP + 64; }
+static inline int predict_splits(int64_t n) { return (int)ceil_div(round_up(n, SP_TS), SP_SPLIT); }
+
+extern "C" int64_t socks_sr_predict_work_bytes(int64_t n, int64_t m) {
+    return (predict_coef_doubles(n) + (int64_t)predict_splits(n) * 16 * round_up(m, 2) + 2) * 8;
 }
 
 extern "C" int socks_sr_predict(const double* X, const double* w, const double* vf, int64_t ldvf, int64_t n, int d,
                                 double scale, int divide, const double* pts, int64_t m, const double* tubes,
-                                int problem, int T, double* out, int64_t ldout, double* coef, int variant,
+                                int problem, int T, double* out, int64_t ldout, double* work, int variant,
                                 socks_stream_t stream) {
     SOCKS_CHECK_ARG(X != nullptr, 1);
     SOCKS_CHECK_ARG(w != nullptr, 2);
@@ -339,7 +367,7 @@ extern "C" int socks_sr_predict(const double* X, const double* w, const double* 
     SOCKS_CHECK_ARG(problem == SOCKS_PROBLEM_THT || problem == SOCKS_PROBLEM_FHT, 12);
     SOCKS_CHECK_ARG(T >= 1, 13);
     SOCKS_CHECK_ARG(ldout >= m, 15);
-    SOCKS_CHECK_ARG(coef != nullptr && (reinterpret_cast<uintptr_t>(coef) & 15) == 0, 16);
+    SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 15) == 0, 16);
     SOCKS_CHECK_ARG(variant == 0 || variant == 1, 17);
     if (m == 0) return SOCKS_OK;
     SOCKS_CHECK_ARG(pts != nullptr && out != nullptr, 9);
@@ -347,6 +375,10 @@ extern "C" int socks_sr_predict(const double* X, const double* w, const double* 
     const double kmul = divide ? 1.0 / scale : scale;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n_pad = round_up(n, SP_TS);
+    double* coef = work;
+    double* part = work + predict_coef_doubles(n);
+    const int64_t ldp = round_up(m, 2);
+    const int splits = predict_splits(n);
     sr_init_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(pts, m, d, tubes, T, out, ldout);
     SOCKS_CHECK_LAUNCH();
     for (int t0 = 0; t0 < T - 1; t0 += SOCKS_SR_ROWS - 1) {
@@ -354,9 +386,10 @@ extern "C" int socks_sr_predict(const double* X, const double* w, const double* 
         const int R = steps + 1;
         sr_pack_coef_kernel<<<(unsigned)ceil_div(n_pad, 256), 256, 0, st>>>(w, vf, ldvf, n, n_pad, t0, R, coef);
         SOCKS_CHECK_LAUNCH();
-#define SOCKS_PRED_CASE(DD)                                                                                       \
-    case DD:                                                                                                      \
-        launch_predict<DD>(variant, X, coef, n, n_pad, pts, m, kmul, tubes, problem, t0, R, out, ldout, st);     \
+#define SOCKS_PRED_CASE(DD)                                                                                      \
+    case DD:                                                                                                     \
+        launch_predict<DD>(variant, X, coef, n, n_pad, pts, m, kmul, tubes, problem, t0, R, out, ldout, part, ldp, \
+                           splits, st);                                                                          \
         break;
         switch (d) {
             SOCKS_PRED_CASE(1) SOCKS_PRED_CASE(2) SOCKS_PRED_CASE(3) SOCKS_PRED_CASE(4)

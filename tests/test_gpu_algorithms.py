@@ -128,6 +128,41 @@ def test_kernel_sr_medium_vs_oracle_and_properties():
     assert np.all(out[:, in_t] == 1.0)
 
 
+def test_kernel_sr_full_size_golden():
+    """BASELINE.json configs[1] at full size (N = 20 000, T = 15) against the unmodified reference
+    (oracle/make_golden_c2.py: reference fit 128 s): value functions (every 10th sample), diag(W) and the
+    safety probabilities of 2 000 of the 250 000 test points."""
+    KernelSR, _, _, _, _, rbf = _api()
+    g = load_golden("sr_c2_n20000_fht.npz")
+    n, T = int(g["n"]), int(g["T"])
+    X, U, Y = syn.integrator_sample(n, dim=2, seed=0)
+    pts = syn.uniform_points(250000, 2, seed=1)
+    ct, tt = syn.integrator_tubes(T)
+    alg = KernelSR(time_horizon=T, constraint_tube=ct, target_tube=tt, problem="FHT", kernel_fn=partial(rbf, sigma=0.1),
+                   regularization_param=float(g["lam"]))
+    alg.fit_arrays(X, Y)
+    stride = int(g["vf_stride"])
+    assert np.max(np.abs(alg.value_functions[:, ::stride] - g["value_functions_sub"])) <= TOL
+    w = alg._w.cpu().numpy()[::stride]
+    assert np.max(np.abs(w - g["w_diag_sub"]) / np.abs(g["w_diag_sub"])) <= 1e-6
+    out = alg.predict(pts)  # all 250k points through the chunked, overlapped host path
+    m_sub = int(g["m_sub"])
+    assert out.shape == (T, 250000)
+    assert np.max(np.abs(out[:, :m_sub] - g["out"])) <= TOL
+    # the chunked host path, the one-launch device path and a sharded evaluation agree bit for bit
+    assert np.array_equal(alg.predict_dev(alg_dev(pts)).cpu().numpy(), out)
+    assert np.array_equal(alg.predict(pts[100000:100000 + 4321]), out[:, 100000:100000 + 4321])
+    in_t = np.all(np.abs(pts) <= 0.5, axis=1)
+    assert np.array_equal(out[T - 1], in_t.astype(float)) and np.all(out[:, in_t] == 1.0)
+    assert np.nanmin(out) >= 0.0 and np.nanmax(out) <= 1.0 + 1e-9
+
+
+def alg_dev(a):
+    from socks_b200 import _device as dv
+
+    return dv.to_dev(a)
+
+
 @pytest.mark.parametrize("name", ["srmax_fht.npz", "srmax_tht_batch.npz"])
 def test_kernel_sr_max_golden(name):
     _, _, KernelMaximalSR, kernel_sr_max, _, rbf = _api()

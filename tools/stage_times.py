@@ -77,7 +77,7 @@ def main(n=20000, m=250000, T=15, out_path=None, hbm_gbs=6546.2):
     res["fit_recursion_gbs"] = T * 8 * n * n / t / 1e9  # T passes: 1 normaliser + T-1 steps
     res["fit_recursion_frac_hbm"] = res["fit_recursion_gbs"] / hbm_gbs
     out = dv.empty(T, m)
-    coef = dv.work(8 * 20 * (npad + 128))
+    coef = dv.work(lib.socks_sr_predict_work_bytes(n, m))
     for variant in (0, 1):
         f = lambda: _lib.call("socks_sr_predict", dv.ptr(Xd), dv.ptr(w), dv.ptr(vf), n, n, d, -gamma, 0, dv.ptr(Pd), m,
                               dv.ptr(tubes), PROBLEM_CODE["FHT"], T, dv.ptr(out), m, dv.ptr(coef), variant, st)
