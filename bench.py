@@ -183,17 +183,11 @@ def run_ours(args):
         alg._fac.release_factors()
         torch.cuda.empty_cache()
     else:
-        alg._n, alg._d, alg._Xh = n, d, X
-        alg._Xd = dv.empty(n, d)
-        alg._w = dv.empty(n)
-        alg._vf = dv.empty(T, n)
-        alg._vf_host = None
-        from socks_b200.algorithms.reach.common import pack_tubes
-
-        alg._tubes = pack_tubes(ct, tt, T, d)
+        alg.allocate_state(n, d)
     if world > 1:  # fit state broadcast over NCCL/NVLink: the only collective on the path
-        for t in (alg._Xd, alg._w, alg._vf):
-            dist.broadcast(t, src=0)
+        from socks_b200.distributed import broadcast_state
+
+        fit_info["broadcast_bytes"] = broadcast_state(alg.state_tensors(), src=0)
 
     pts_host = syn.uniform_points(m, d, seed=1 + rank)
     pts = dv.to_dev(pts_host)

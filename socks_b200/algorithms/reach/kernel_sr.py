@@ -68,9 +68,19 @@ class KernelSR:
         if S is None:
             raise ValueError("Must supply a sample.")
 
-    # -- device state shared with the multi-GPU helpers
-    def _state(self):
-        return {"X": self._Xd, "w": self._w, "vf": self._vf}
+    # -- fitted state for the multi-GPU helpers (socks_b200/distributed.py): ~ N (d + 1 + T) doubles
+    def state_tensors(self):
+        return {"X": self._Xd, "vf": self._vf, "w": self._w}
+
+    def allocate_state(self, n, d):
+        """Receiving side of a broadcast: empty device state of the right shapes (no fit on this rank)."""
+        self._validate_params(None)
+        T = int(self.time_horizon)
+        self._n, self._d, self._Xh = int(n), int(d), None
+        self._Xd, self._w, self._vf = dv.empty(n, d), dv.empty(n), dv.empty(T, n)
+        self._vf_host, self._fac = None, None
+        self._tubes = pack_tubes(self.constraint_tube, self.target_tube, T, d)
+        return self.state_tensors()
 
     def fit(self, S):
         self._validate_data(S)
@@ -174,12 +184,14 @@ class KernelSR:
     # -- attributes the reference exposes (kernel_sr.py:286-309)
     @property
     def X(self):
+        if self._Xh is None:
+            self._Xh = self._Xd.cpu().numpy()
         return self._Xh
 
     @property
     def W(self):
         """inv(G) as an ndarray; computed on first access (the algorithm itself only needs diag(W))."""
-        if self._fac.L is None and self._fac._W is None:
+        if self._fac is None or (self._fac.L is None and self._fac._W is None):
             raise AttributeError("factors were released (keep_factors=False); W is unavailable")
         return self._fac.full()[: self._n, : self._n].cpu().numpy()
 

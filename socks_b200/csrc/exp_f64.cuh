@@ -62,4 +62,48 @@ __device__ __forceinline__ double exp_tbl(double x, const double* __restrict__ t
     return __hiloint2double(__double2hiint(res) + (e << 20), __double2loint(res));
 }
 
+// Four independent exponentials with the stages interleaved by hand (4 dependency chains in flight).
+__device__ __forceinline__ void exp_tbl_x4(const double (&x)[4], double (&out)[4], const double* __restrict__ tbl) {
+    const double kMagic = 6755399441055744.0, kInv = 92.33248261689366;
+    const double kHi = 0x1.62e42fe000000p-7, kLo = 0x1.f473de6af278fp-36;
+    double t[4], kd[4], r[4], p[4], T[4];
+    int k[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = fma(x[i], kInv, kMagic);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { k[i] = __double2loint(t[i]); kd[i] = t[i] - kMagic; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) T[i] = tbl[k[i] & (EXP_TBL - 1)];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = fma(kd[i], -kHi, x[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = fma(kd[i], -kLo, r[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = fma(r[i], 1.0 / 120.0, 1.0 / 24.0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = fma(p[i], r[i], 1.0 / 6.0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = fma(p[i], r[i], 0.5);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = p[i] * r[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = fma(p[i], r[i], r[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double res = fma(T[i], p[i], T[i]);
+        int e = k[i] >> 6;
+        if (e < -1020) {
+            if (!(x[i] >= -800.0)) {
+                out[i] = (x[i] != x[i]) ? x[i] : 0.0;
+                continue;
+            }
+            e += 1000;
+            res = __hiloint2double(__double2hiint(res) + (e << 20), __double2loint(res)) * 0x1p-1000;
+        } else {
+            res = __hiloint2double(__double2hiint(res) + (e << 20), __double2loint(res));
+        }
+        out[i] = res;
+    }
+}
+
 }  // namespace socks
