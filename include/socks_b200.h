@@ -124,6 +124,16 @@ int socks_srmax_pack(const double* CUA, int64_t n, int P, const double* w, const
 int socks_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                   int64_t m, int64_t nn, int64_t K, socks_stream_t stream);
 
+/* General form of the same kernel: C = alpha * op(A) * op(B) + beta * C, all row-major.
+ *   transa == 0: A is m x K;  transa != 0: A is K x m.   transb != 0: B is nn x K ("NT");  transb == 0: B is K x nn.
+ *   (transa && transb is not provided.)  flags: bit0 A(i,k)=0 for k>i, bit1 A(i,k)=0 for k<i, bit2 B(k,j)=0 for
+ *   k<j, bit3 B(k,j)=0 for k>j, all at 128-tile granularity; lower_only: skip 128-tiles above the block diagonal;
+ *   tile_cfg: 0 auto, 1 = 128x128 CTA tiles, 2 = 64x64.  These are the SYRK/GEMM/TRMM updates of socks_potrf,
+ *   socks_trtri and socks_lauum (numpy.linalg.inv's LAPACK calls, gym_socks/kernel/metrics.py:280). */
+int socks_gemm_f64(int transa, int transb, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                   int64_t ldc, int64_t m, int64_t nn, int64_t K, double alpha, double beta, int flags,
+                   int lower_only, int tile_cfg, socks_stream_t stream);
+
 /* out[t0 + r - 1][j] = step(pts_j, max_a Cm[j][r*P + a] / Cm[j][a]) for r = 1..R-1
  * (kernel_sr_max.py:72-73).  If write_last != 0 also out[T-1][j] = 1_target(pts_j). */
 int socks_srmax_step(const double* Cm, int64_t ldc, int64_t m, int P, int R, int t0, const double* pts,

@@ -77,8 +77,8 @@ __device__ __forceinline__ void sp_load_stage(double* __restrict__ sx, double* _
 // layout of mma.m8n8k4 (B[k = lane%4][n = lane/4]).  Partial sums go to part[split][16][ldp]; the finish
 // kernel adds the splits in order, divides by the normaliser row and applies the FHT/THT step.  Splitting
 // the sample axis gives N/2048 times more CTAs than point tiles alone: no wave-quantisation tail.
-template <int D, int MINB, bool ILV>
-__global__ void __launch_bounds__(SP_WARPS * 32, MINB)
+template <int D>
+__global__ void __launch_bounds__(SP_WARPS * 32, 2)
     sr_predict_dmma_kernel(const double* __restrict__ X, const double* __restrict__ coef, int64_t n, int64_t n_pad,
                            const double* __restrict__ pts, int64_t m, double neg_gamma, double* __restrict__ part,
                            int64_t ldp) {
@@ -124,20 +124,7 @@ __global__ void __launch_bounds__(SP_WARPS * 32, MINB)
             for (int k = 0; k < D; ++k) xs[k] = x_s[s * D + k];
             const double a0 = c_s[s * SR_CP + lq];
             const double a1 = c_s[s * SR_CP + lq + 8];
-            if (!ILV) {
-#pragma unroll
-                for (int q = 0; q < SP_Q; ++q) {
-                    double d2 = 0.0;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        const double t = p[q][k] - xs[k];
-                        d2 = fma(t, t, d2);
-                    }
-                    const double kv = exp_tbl(d2 * neg_gamma, etbl);
-                    dmma884(acc[q][0][0], acc[q][0][1], a0, kv);
-                    dmma884(acc[q][1][0], acc[q][1][1], a1, kv);
-                }
-            } else {
+            {
                 double arg[SP_Q], kv[SP_Q];
 #pragma unroll
                 for (int q = 0; q < SP_Q; ++q) {
@@ -354,16 +341,9 @@ static void launch_predict(int variant, const double* X, const double* coef, int
                            const double* pts, int64_t m, double kmul, const double* tubes, int problem, int t0,
                            int R, double* out, int64_t ldout, double* part, int64_t ldp, int splits,
                            cudaStream_t st) {
-    if (variant != 1) {
+    if (variant == 0) {
         dim3 grid((unsigned)ceil_div(m, SP_PTS), (unsigned)splits);
-        if (variant == 0)
-            sr_predict_dmma_kernel<D, 3, false><<<grid, SP_WARPS * 32, 0, st>>>(X, coef, n, n_pad, pts, m, kmul, part, ldp);
-        else if (variant == 2)
-            sr_predict_dmma_kernel<D, 4, false><<<grid, SP_WARPS * 32, 0, st>>>(X, coef, n, n_pad, pts, m, kmul, part, ldp);
-        else if (variant == 3)
-            sr_predict_dmma_kernel<D, 3, true><<<grid, SP_WARPS * 32, 0, st>>>(X, coef, n, n_pad, pts, m, kmul, part, ldp);
-        else
-            sr_predict_dmma_kernel<D, 2, true><<<grid, SP_WARPS * 32, 0, st>>>(X, coef, n, n_pad, pts, m, kmul, part, ldp);
+        sr_predict_dmma_kernel<D><<<grid, SP_WARPS * 32, 0, st>>>(X, coef, n, n_pad, pts, m, kmul, part, ldp);
         sr_predict_finish_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(part, ldp, splits, m, R, t0, pts, D,
                                                                              tubes, problem, out, ldout);
     } else {
@@ -395,7 +375,7 @@ extern "C" int socks_sr_predict(const double* X, const double* w, const double* 
     SOCKS_CHECK_ARG(T >= 1, 13);
     SOCKS_CHECK_ARG(ldout >= m, 15);
     SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 15) == 0, 16);
-    SOCKS_CHECK_ARG(variant >= 0 && variant <= 4, 17);
+    SOCKS_CHECK_ARG(variant == 0 || variant == 1, 17);
     if (m == 0) return SOCKS_OK;
     SOCKS_CHECK_ARG(pts != nullptr && out != nullptr, 9);
     // the fused path multiplies by the (rounded) reciprocal: 1 ulp of the argument, far below the 1e-8 bar

@@ -103,6 +103,37 @@ extern "C" int socks_gemm_tn(const double* A, int64_t lda, const double* B, int6
     return SOCKS_OK;
 }
 
+// General entry (tests, profiling, and the building block a caller can use directly).
+extern "C" int socks_gemm_f64(int transa, int transb, const double* A, int64_t lda, const double* B, int64_t ldb,
+                              double* C, int64_t ldc, int64_t m, int64_t nn, int64_t K, double alpha, double beta,
+                              int flags, int lower_only, int tile_cfg, socks_stream_t stream) {
+    SOCKS_CHECK_ARG(!(transa && transb), 1);
+    SOCKS_CHECK_ARG(A != nullptr && (reinterpret_cast<uintptr_t>(A) & 15) == 0, 3);
+    SOCKS_CHECK_ARG(lda % 2 == 0 && lda >= (transa ? m : K), 4);
+    SOCKS_CHECK_ARG(B != nullptr && (reinterpret_cast<uintptr_t>(B) & 15) == 0, 5);
+    SOCKS_CHECK_ARG(ldb % 2 == 0 && ldb >= (transb ? K : nn), 6);
+    SOCKS_CHECK_ARG(C != nullptr && (reinterpret_cast<uintptr_t>(C) & 15) == 0, 7);
+    SOCKS_CHECK_ARG(ldc >= nn && ldc % 2 == 0, 8);
+    SOCKS_CHECK_ARG(m >= 0 && m % 128 == 0, 9);
+    SOCKS_CHECK_ARG(nn >= 0 && nn % 128 == 0, 10);
+    SOCKS_CHECK_ARG(K >= 0 && K % 16 == 0, 11);
+    SOCKS_CHECK_ARG(alpha != 0.0, 12);
+    SOCKS_CHECK_ARG(tile_cfg >= 0 && tile_cfg <= 2, 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (transa)
+        e = gemm_f64<true, false>(A, lda, B, ldb, C, ldc, m, nn, K, alpha, beta, flags, lower_only, st, tile_cfg);
+    else if (transb)
+        e = gemm_f64<false, true>(A, lda, B, ldb, C, ldc, m, nn, K, alpha, beta, flags, lower_only, st, tile_cfg);
+    else
+        e = gemm_f64<false, false>(A, lda, B, ldb, C, ldc, m, nn, K, alpha, beta, flags, lower_only, st, tile_cfg);
+    if (e != cudaSuccess) {
+        set_error("socks_gemm_f64: CUDA launch failed: %s", cudaGetErrorString(e));
+        return SOCKS_ECUDA;
+    }
+    return SOCKS_OK;
+}
+
 extern "C" int socks_srmax_step(const double* Cm, int64_t ldc, int64_t m, int P, int R, int t0, const double* pts,
                                 int d, const double* tubes, int problem, int T, double* out, int64_t ldout,
                                 int write_last, socks_stream_t stream) {

@@ -175,3 +175,45 @@ def test_gemv_and_argmin_primitives():
             Dd = None if Dm is None else dv.to_dev(Dm)
             _lib.call("socks_argmin_masked", dv.ptr(Cd), dv.ptr(Dd), P, dv.ptr(idx), dv.stream())
             assert int(idx.item()) == orc.heuristic_solution(C, Dm)
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0)])
+@pytest.mark.parametrize("cfg", [1, 2])
+def test_gemm_f64_forms(ta, tb, cfg):
+    """Every operand form / tile configuration of the DMMA GEMM against numpy, incl. alpha/beta, the
+    triangular k-range flags and lower-only output."""
+    torch, dv, _lib, mt = _mods()
+    rng = np.random.default_rng(10 * ta + tb)
+    m, n, K = 256, 384, 272
+    A = rng.standard_normal((K, m) if ta else (m, K))
+    B = rng.standard_normal((n, K) if tb else (K, n))
+    C0 = rng.standard_normal((m, n))
+    opA = A.T if ta else A
+    opB = B.T if tb else B
+    Ad, Bd = dv.to_dev(A), dv.to_dev(B)
+    for alpha, beta in [(1.0, 0.0), (-1.0, 1.0), (0.5, -2.0)]:
+        Cd = dv.to_dev(C0)
+        _lib.call("socks_gemm_f64", ta, tb, dv.ptr(Ad), A.shape[1], dv.ptr(Bd), B.shape[1], dv.ptr(Cd), n, m, n, K,
+                  alpha, beta, 0, 0, cfg, dv.stream())
+        want = alpha * (opA @ opB) + beta * C0
+        assert np.max(np.abs(Cd.cpu().numpy() - want)) <= 1e-12 * np.abs(want).max()
+    # triangular operands (square case): A lower (k <= i) times B lower in (k, j) sense (k >= j), lower output only
+    s = 384
+    L1 = np.tril(rng.standard_normal((s, s)))
+    L2 = np.tril(rng.standard_normal((s, s)))
+    if not ta and not tb:
+        Ad, Bd, Cd = dv.to_dev(L1), dv.to_dev(L2), dv.zeros(s, s)
+        _lib.call("socks_gemm_f64", 0, 0, dv.ptr(Ad), s, dv.ptr(Bd), s, dv.ptr(Cd), s, s, s, s, 1.0, 0.0, 1 | 4, 1, cfg,
+                  dv.stream())
+        got, want = Cd.cpu().numpy(), L1 @ L2
+        for bi in range(3):
+            for bj in range(bi + 1):
+                blk = (slice(128 * bi, 128 * bi + 128), slice(128 * bj, 128 * bj + 128))
+                assert np.max(np.abs(got[blk] - want[blk])) <= 1e-12 * np.abs(want).max()
+        assert not got[:128, 128:].any()  # tiles above the block diagonal untouched
+    if ta and not tb:  # lauum form: M^T M with M lower, k >= max(i, j)
+        Ad, Cd = dv.to_dev(L1), dv.zeros(s, s)
+        _lib.call("socks_gemm_f64", 1, 0, dv.ptr(Ad), s, dv.ptr(Ad), s, dv.ptr(Cd), s, s, s, s, 1.0, 0.0, 2 | 4, 1, cfg,
+                  dv.stream())
+        got, want = np.tril(Cd.cpu().numpy()), np.tril(L1.T @ L1)
+        assert np.max(np.abs(got - want)) <= 1e-12 * np.abs(want).max()

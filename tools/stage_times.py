@@ -78,12 +78,12 @@ def main(n=20000, m=250000, T=15, out_path=None, hbm_gbs=6546.2):
     res["fit_recursion_frac_hbm"] = res["fit_recursion_gbs"] / hbm_gbs
     out = dv.empty(T, m)
     coef = dv.work(lib.socks_sr_predict_work_bytes(n, m))
-    for variant in (0, 1, 2, 3, 4):
+    for variant in (0, 1):
         f = lambda: _lib.call("socks_sr_predict", dv.ptr(Xd), dv.ptr(w), dv.ptr(vf), n, n, d, -gamma, 0, dv.ptr(Pd), m,
                               dv.ptr(tubes), PROBLEM_CODE["FHT"], T, dv.ptr(out), m, dv.ptr(coef), variant, st)
         f()
         t, _ = timed(f, reps=3)
-        key = {0: "predict_dmma", 1: "predict_fma", 2: "predict_dmma_mb4", 3: "predict_dmma_ilv", 4: "predict_dmma_ilv_mb2"}[variant]
+        key = "predict_dmma" if variant == 0 else "predict_fma"
         res[key + "_s"] = t
         res[key + "_pts_per_s"] = m / t
         res[key + "_fma_pipe_tflops"] = n * m * (3 * d + 2 + EXP_FLOPS) / t / 1e12
