@@ -128,7 +128,7 @@ int socks_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, do
  *   transa == 0: A is m x K;  transa != 0: A is K x m.   transb != 0: B is nn x K ("NT");  transb == 0: B is K x nn.
  *   (transa && transb is not provided.)  flags: bit0 A(i,k)=0 for k>i, bit1 A(i,k)=0 for k<i, bit2 B(k,j)=0 for
  *   k<j, bit3 B(k,j)=0 for k>j, all at 128-tile granularity; lower_only: skip 128-tiles above the block diagonal;
- *   tile_cfg: 0 auto, 1 = 128x128 CTA tiles, 2 = 64x64.  These are the SYRK/GEMM/TRMM updates of socks_potrf,
+ *   tile_cfg: 0 = 64x64 CTA tiles x 3 CTAs/SM (default), 1 = 128x128.  These are the SYRK/GEMM/TRMM updates of socks_potrf,
  *   socks_trtri and socks_lauum (numpy.linalg.inv's LAPACK calls, gym_socks/kernel/metrics.py:280). */
 int socks_gemm_f64(int transa, int transb, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                    int64_t ldc, int64_t m, int64_t nn, int64_t K, double alpha, double beta, int flags,

@@ -12,14 +12,13 @@
 // Requirements: m, n multiples of 128; K multiple of 16; lda, ldb, ldc even; 16-byte aligned bases.
 // Triangular structure is exploited at tile level through `flags` (k-range clipping per output tile, in
 // units of 128) and `lower_only` (skip output tiles strictly above the block diagonal).
-// Two tile configurations: 128 x 128 (8 warps of 64 x 32) for GEMMs that fill the 148 SMs, and 64 x 64
-// (4 warps of 32 x 32, two CTAs per SM) for the sub-wave GEMMs near the leaves of the recursions.
+// Default tile configuration: 64 x 64 CTA tiles (4 warps of 32 x 32), 3 stages, three CTAs per SM.
 #pragma once
 #include "common.cuh"
 
 namespace socks {
 
-constexpr int GM_BK = 16, GM_STAGES = 4;
+constexpr int GM_BK = 16;
 constexpr int GM_LDK = GM_BK + 4;  // 20: row stride of a [BM][16] tile; 20 mod 16 = 4 -> conflict-free frags
 
 enum GemmFlags : int {
@@ -29,7 +28,7 @@ enum GemmFlags : int {
     GEMM_B_K_LE_N = 8,  // B(k,j) == 0 for k >  j                                  -> k_hi = 128-block end of n0
 };
 
-template <int BM, int BN, int WM, int WN>
+template <int BM, int BN, int WM, int WN, int STAGES>
 struct GemmCfg {
     static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
     static constexpr int THREADS = WARPS_M * WARPS_N * 32;
@@ -37,7 +36,7 @@ struct GemmCfg {
     static constexpr int LDA_T = BM + 4, LDB_T = BN + 4;  // strides of [16][BM] / [16][BN] tiles (= 4 mod 16)
     static constexpr int A_DBL = (BM * GM_LDK > GM_BK * LDA_T) ? BM * GM_LDK : GM_BK * LDA_T;
     static constexpr int B_DBL = (BN * GM_LDK > GM_BK * LDB_T) ? BN * GM_LDK : GM_BK * LDB_T;
-    static constexpr int SMEM_BYTES = GM_STAGES * (A_DBL + B_DBL) * 8;
+    static constexpr int SMEM_BYTES = STAGES * (A_DBL + B_DBL) * 8;
 };
 
 // ROWS x 16 doubles of a row-major "rows x K" operand (TRANS=false) or 16 x ROWS of a "K x rows" operand.
@@ -59,12 +58,13 @@ __device__ __forceinline__ void gemm_load_tile(double* __restrict__ s, const dou
     }
 }
 
-template <bool TA, bool TB, int BM, int BN, int WM, int WN, int MINB>
-__global__ void __launch_bounds__(GemmCfg<BM, BN, WM, WN>::THREADS, MINB)
+template <bool TA, bool TB, int BM, int BN, int WM, int WN, int STAGES, int MINB>
+__global__ void __launch_bounds__(GemmCfg<BM, BN, WM, WN, STAGES>::THREADS, MINB)
     gemm_f64_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
                     double* __restrict__ C, int64_t ldc, int64_t K, double alpha, double beta, int flags,
                     int lower_only) {
-    using Cfg = GemmCfg<BM, BN, WM, WN>;
+    using Cfg = GemmCfg<BM, BN, WM, WN, STAGES>;
+    constexpr int GM_STAGES = STAGES;
     constexpr int THREADS = Cfg::THREADS, MI = Cfg::MI, NI = Cfg::NI;
     extern __shared__ __align__(16) double gm_smem[];
     const int64_t m0 = (int64_t)blockIdx.y * BM;
@@ -157,12 +157,12 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, WM, WN>::THREADS, MINB)
         }
 }
 
-template <bool TA, bool TB, int BM, int BN, int WM, int WN, int MINB>
+template <bool TA, bool TB, int BM, int BN, int WM, int WN, int STAGES, int MINB>
 inline cudaError_t gemm_f64_launch(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                                    int64_t m, int64_t n, int64_t K, double alpha, double beta, int flags,
                                    int lower_only, cudaStream_t st) {
-    using Cfg = GemmCfg<BM, BN, WM, WN>;
-    auto kern = gemm_f64_kernel<TA, TB, BM, BN, WM, WN, MINB>;
+    using Cfg = GemmCfg<BM, BN, WM, WN, STAGES>;
+    auto kern = gemm_f64_kernel<TA, TB, BM, BN, WM, WN, STAGES, MINB>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -175,7 +175,11 @@ inline cudaError_t gemm_f64_launch(const double* A, int64_t lda, const double* B
 }
 
 // Host launcher: picks the tile configuration from the number of 128 x 128 output tiles.
-// tile_cfg: 0 = automatic, 1 = force 128 x 128, 2 = force 64 x 64.
+// tile_cfg: 0 = default: 64 x 64 tiles, 4 warps of 32 x 32, 3-stage pipeline, three CTAs per SM -- measured
+// 35.0-35.4 TFLOP/s (95 % of the 37.1 TFLOP/s DMMA peak) on the factorisation's large shapes, against
+// 30.8 for 1 = 128 x 128 tiles / 8 warps of 64 x 32 / one CTA per SM (profiles/r1_gemm_tile_sweep.txt):
+// with one DMMA pipe per SM sub-partition, three independent CTAs hide the fragment-load and barrier
+// latency that two resident warps per scheduler cannot.
 template <bool TA, bool TB>
 inline cudaError_t gemm_f64(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                             int64_t m, int64_t n, int64_t K, double alpha, double beta, int flags, int lower_only,
@@ -183,12 +187,12 @@ inline cudaError_t gemm_f64(const double* A, int64_t lda, const double* B, int64
     if (m == 0 || n == 0) return cudaSuccess;
     const int64_t tm = m / TILE, tn = n / TILE;
     const int64_t tiles = lower_only ? (tm * (tm + 1)) / 2 : tm * tn;
-    const bool small = (tile_cfg == 2) || (tile_cfg == 0 && tiles < 120);
-    if (small)
-        return gemm_f64_launch<TA, TB, 64, 64, 32, 32, 2>(A, lda, B, ldb, C, ldc, m, n, K, alpha, beta, flags,
-                                                          lower_only, st);
-    return gemm_f64_launch<TA, TB, 128, 128, 64, 32, 1>(A, lda, B, ldb, C, ldc, m, n, K, alpha, beta, flags,
-                                                        lower_only, st);
+    (void)tiles;
+    if (tile_cfg == 1)
+        return gemm_f64_launch<TA, TB, 128, 128, 64, 32, 4, 1>(A, lda, B, ldb, C, ldc, m, n, K, alpha, beta, flags,
+                                                               lower_only, st);
+    return gemm_f64_launch<TA, TB, 64, 64, 32, 32, 3, 3>(A, lda, B, ldb, C, ldc, m, n, K, alpha, beta, flags,
+                                                         lower_only, st);
 }
 
 }  // namespace socks

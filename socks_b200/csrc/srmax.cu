@@ -118,7 +118,7 @@ extern "C" int socks_gemm_f64(int transa, int transb, const double* A, int64_t l
     SOCKS_CHECK_ARG(nn >= 0 && nn % 128 == 0, 10);
     SOCKS_CHECK_ARG(K >= 0 && K % 16 == 0, 11);
     SOCKS_CHECK_ARG(alpha != 0.0, 12);
-    SOCKS_CHECK_ARG(tile_cfg >= 0 && tile_cfg <= 2, 16);
+    SOCKS_CHECK_ARG(tile_cfg == 0 || tile_cfg == 1, 16);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
     if (transa)

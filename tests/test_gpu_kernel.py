@@ -178,7 +178,7 @@ def test_gemv_and_argmin_primitives():
 
 
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0)])
-@pytest.mark.parametrize("cfg", [1, 2])
+@pytest.mark.parametrize("cfg", [0, 1])
 def test_gemm_f64_forms(ta, tb, cfg):
     """Every operand form / tile configuration of the DMMA GEMM against numpy, incl. alpha/beta, the
     triangular k-range flags and lower-only output."""

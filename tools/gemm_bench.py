@@ -33,12 +33,14 @@ def run(ta, tb, m, n, K, lower, cfg, flags=0, reps=3):
     return {"ta": ta, "tb": tb, "m": m, "n": n, "K": K, "lower": lower, "cfg": cfg, "ms": t * 1e3, "tflops": fl / t / 1e12}
 
 
-shapes = [(0, 1, 10112, 10112, 9984, 1)] if quick else [
+cfgs = (0, 1)
+shapes = [(0, 1, 10112, 10112, 9984, 1), (0, 0, 10112, 9984, 9984, 0), (0, 1, 2560, 2560, 2560, 1), (0, 1, 640, 640, 640, 0),
+          (0, 1, 128, 128, 128, 0)] if quick else [
     (0, 1, 10112, 10112, 9984, 1), (0, 0, 10112, 9984, 9984, 0), (1, 0, 8192, 8192, 8192, 0),
     (0, 1, 5120, 5120, 4992, 1), (0, 1, 10112, 1280, 1280, 0), (0, 1, 2560, 2560, 2560, 1),
     (0, 1, 1280, 1280, 1280, 1), (0, 1, 640, 640, 640, 0), (0, 1, 384, 256, 256, 0), (0, 1, 128, 128, 128, 0),
     (0, 0, 256, 128, 256, 0),
 ]
 for ta, tb, m, n, K, lower in shapes:
-    for cfg in ((1,) if quick else (1, 2)):
+    for cfg in cfgs:
         print(json.dumps(run(ta, tb, m, n, K, lower, cfg)), flush=True)
