@@ -103,6 +103,12 @@ def run_reference(args):
         return
     n, T, m_s = args.n, args.T, args.cpu_sample
     cores = os.cpu_count()
+    try:  # torchrun exports OMP_NUM_THREADS=1; the reference arm may use every host thread
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     vals, secs = [], []
     for i in range(args.warmup + args.steps):
         v, dt = cpu_predict_sample(n, T, m_s, seed=10 + i)
@@ -265,7 +271,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(res.nbytes)},
             "gpu_launches": 3 * args.steps,  # sr_init + sr_pack_coef + sr_predict_dmma per step
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak, "traffic": None,
+                         "frac": achieved / fp64_peak,
+                         # dram__bytes_read + dram__bytes_write of one launch at this exact shape, from the ncu
+                         # --set full capture summarised in profiles/r1_ncu_sr_predict_dmma_n20000_m250000.txt
+                         "traffic": 280.0e6 if (n, m, T) == (20000, 250000, 15) else None,
                          "kernel": "sr_predict_dmma_kernel<2>",
                          "note": "algorithmic flops = N*M*(3d+2+E+2T), E=18 (exp_f64.cuh); FMA and DMMA share the "
                                  "FP64 pipe on B200 (tools/probe_fp64.py), so one FP64 peak bounds both; peak "

@@ -171,8 +171,15 @@ class KernelSR:
             t = cache[name] = dv.empty(*shape)
         return t
 
+    max_launch_points = 1 << 20  # bounds the per-split partial-sum workspace (16 * splits * 8 B per point)
+
     def _predict_into(self, pts, out):
         m = pts.shape[0]
+        if m > self.max_launch_points:
+            for s in range(0, m, self.max_launch_points):
+                e = min(m, s + self.max_launch_points)
+                self._predict_into(pts[s:e], out[:, s:e])
+            return
         scale, divide = self._spec.params_for(self._Xd, pts)
         nbytes = _lib.load().socks_sr_predict_work_bytes(self._n, m)
         work = self._cached("work", ((nbytes + 7) // 8 + 2,))
