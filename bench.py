@@ -269,17 +269,19 @@ def run_ours(args):
                        "parallelism": f"test points sharded, {world} rank(s), fit on rank 0 + NCCL broadcast"},
             "e2e": {"value": world * m * args.steps / e2e_s, "unit": "points/s", "h2d_bytes_per_step": int(pts_host.nbytes),
                     "d2h_bytes_per_step": int(res.nbytes)},
-            "gpu_launches": 3 * args.steps,  # sr_init + sr_pack_coef + sr_predict_dmma per step
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak,
+            "gpu_launches": 4 * args.steps,  # sr_init + sr_pack_coef + sr_predict_dmma + sr_predict_finish per step
+            "roofline": {"bound": "tensor", "peak_kind": "fp64 DMMA (mma.sync.m8n8k4.f64), measured live",
+                         "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
+                         "frac": achieved / dmma_peak,
                          # dram__bytes_read + dram__bytes_write of one launch at this exact shape, from the ncu
                          # --set full capture summarised in profiles/r1_ncu_sr_predict_dmma_n20000_m250000.txt
                          "traffic": 280.0e6 if (n, m, T) == (20000, 250000, 15) else None,
                          "kernel": "sr_predict_dmma_kernel<2>",
                          "note": "algorithmic flops = N*M*(3d+2+E+2T), E=18 (exp_f64.cuh); FMA and DMMA share the "
-                                 "FP64 pipe on B200 (tools/probe_fp64.py), so one FP64 peak bounds both; peak "
-                                 "measured live by socks_probe_fp64 (MEASURED_PEAKS.json has no FP64 figure)",
-                         "fp64_dmma_peak": dmma_peak, "hbm_peak_gbs": peaks.get("hbm_gbs")},
+                                 "FP64 pipe on B200 (tools/probe_fp64.py: 36.5 / 37.1 TFLOP/s alone, 35.7 combined), so the fp64 "
+                                 "tensor peak bounds the whole kernel; measured live by socks_probe_fp64 "
+                                 "(MEASURED_PEAKS.json has HBM and bf16 only)",
+                         "fp64_fma_peak": fp64_peak, "hbm_peak_gbs": peaks.get("hbm_gbs")},
             "clocks": clocks,
             "wall_s_timed_region": wall,
         }

@@ -157,6 +157,9 @@ int socks_argmin_masked(const double* C, const double* D, int P, int* idx_dev, s
 
 /* ---- Measurement helpers (tools/, bench.py): register-resident FP64 peak probes -------- */
 int socks_probe_fp64(int mode, int iters, double* out_dev, int blocks, socks_stream_t stream);
+/* clock64() at the phase boundaries of the 128 x 128 leaf factorisation (cycles: 16 int64 on the device). */
+int socks_dev_potf2_phases(double* A, int64_t lda, double* dinv, int* info_dev, long long* cycles,
+                           socks_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,7 @@ SIGNATURES = {
     "socks_gemv_t": (_I, [_P, _L, _L, _L, _P, _L, _I, _P, _L, _P, _P]),
     "socks_fwd_weights": (_I, [_P, _L, _I, _D, _I, _P, _P, _L, _I, _P, _L, _P]),
     "socks_argmin_masked": (_I, [_P, _P, _I, _P, _P]),
+    "socks_dev_potf2_phases": (_I, [_P, _L, _P, _P, _P, _P]),
     "socks_probe_fp64": (_I, [_I, _I, _P, _I, _P]),
 }
 

@@ -17,21 +17,77 @@ namespace socks {
 
 constexpr int LF = TILE;        // leaf size 128
 constexpr int LF_LD = LF + 1;   // odd smem stride: row and column accesses are both conflict-free
-constexpr int LF_THREADS = 256;
-constexpr int LF_NB = 32;       // inner block: one warp factors a 32 x 32 diagonal block
-constexpr int LF_SC_LD = 97;    // scratch [96][33] (panel) or [32][97] (inverse assembly)
-// S (L, then inv L in place), Dinv[4][32][33], scratch 96*33, rinv[128]  (~192 KB)
+constexpr int LF_THREADS = 512;
+constexpr int LF_NB = 32;       // inner block: one warp factors a 32 x 32 diagonal block in registers
+constexpr int LF_SC_LD = 97;    // scratch [32][97] for the inverse assembly
+// S (L, then inv L in place), Dinv[4][32][33], scratch 32*97 (+ slack), rinv[128]  (~190 KB)
 constexpr int LF_SMEM = (LF * LF_LD + 4 * LF_NB * 33 + 96 * 33 + LF) * 8;
+
+// (a) Cholesky of the 32 x 32 block at (o, o) of S by ONE warp, entirely in registers: lane i owns row i,
+// pivots and multipliers travel by shuffle, the pivot is inverted with rsqrt (rinv[o+j] = 1 / L_jj).
+__device__ __forceinline__ void chol32_warp(double* __restrict__ S, int o, double* __restrict__ rinv,
+                                            int* __restrict__ info, int col_offset, int lane) {
+    double a[LF_NB];
+    double* row = S + (o + lane) * LF_LD + o;
+#pragma unroll
+    for (int k = 0; k < LF_NB; ++k) a[k] = row[k];  // strictly-upper entries of S are zero
+#pragma unroll
+    for (int j = 0; j < LF_NB; ++j) {
+        double d = __shfl_sync(0xffffffffu, a[j], j);
+        if (!(d > 0.0)) {  // non-positive or NaN pivot: report the first one, continue with 1
+            if (lane == 0) atomicCAS(info, 0, col_offset + o + j + 1);
+            d = 1.0;
+        }
+        const double ri = rsqrt(d);
+        const double l = ((lane == j) ? d : a[j]) * ri;  // lane j: sqrt(d); lanes > j: L[i][j]
+        a[j] = l;
+        if (lane == j) rinv[o + j] = ri;
+#pragma unroll
+        for (int k = j + 1; k < LF_NB; ++k) {
+            const double lk = __shfl_sync(0xffffffffu, l, k);
+            a[k] = fma(-l, lk, a[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < LF_NB; ++k)
+        if (k <= lane) row[k] = a[k];
+}
+
+// (b) D = inv(L_oo) (32 x 32 lower) by one warp: lane c owns column c (forward substitution in registers,
+// L entries are warp-uniform shared-memory broadcasts).
+__device__ __forceinline__ void inv32_warp(const double* __restrict__ S, int o, const double* __restrict__ rinv,
+                                           double* __restrict__ D, int lane) {
+    double m[LF_NB];
+#pragma unroll
+    for (int i = 0; i < LF_NB; ++i) {
+        const double* lrow = S + (o + i) * LF_LD + o;
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) {
+            if (k & 1) acc1 = fma(lrow[k], m[k], acc1);
+            else acc0 = fma(lrow[k], m[k], acc0);
+        }
+        const double ri = rinv[o + i];
+        m[i] = (i < lane) ? 0.0 : ((i == lane) ? ri : -(acc0 + acc1) * ri);
+    }
+#pragma unroll
+    for (int i = 0; i < LF_NB; ++i) D[i * 33 + lane] = m[i];
+}
 
 // Factor one 128 x 128 diagonal block in shared memory and invert the factor.
 //   A (global, lower part) <- L ;  dinv (dense 128 x 128) <- inv(L) with explicit zeros above.
-// Blocked right-looking over four 32-column panels: (a) warp 0 factors the 32 x 32 diagonal block
-// (left-looking, lane = row, rsqrt pivots), (b) all warps invert it (8 lanes per column), (c) panel
-// solve P <- P inv(D)^T, (d) trailing update; then inv(L) is assembled block row by block row.
+// Right-looking over four 32-column panels: (a) one warp factors the 32 x 32 pivot block in registers,
+// (c) one thread per row solves the panel below it against L_kk^T, (d) all threads update the trailing
+// lower triangle; then the four pivot-block inverses are formed in parallel (one warp each) and inv(L) is
+// assembled block row by block row, in place.
+template <bool TIMING>
 __global__ void __launch_bounds__(LF_THREADS, 1)
     potf2_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ dinv, int* __restrict__ info,
-                     int col_offset) {
+                     int col_offset, long long* __restrict__ cycles) {
+#define LF_TICK(slot)                                       \
+    if (TIMING && threadIdx.x == 0) cycles[slot] = clock64();
     extern __shared__ __align__(16) double lf_smem[];
+    LF_TICK(0)
     double* S = lf_smem;                     // [128][129]  block -> L (lower) -> inv(L), block row by block row
     double* Di = S + LF * LF_LD;             // [4][32][33] inverses of the diagonal 32-blocks
     double* Sc = Di + 4 * LF_NB * 33;        // scratch
@@ -43,92 +99,54 @@ __global__ void __launch_bounds__(LF_THREADS, 1)
         S[r * LF_LD + c] = (c <= r) ? A[(int64_t)r * lda + c] : 0.0;
     }
     __syncthreads();
+    LF_TICK(1)
 
     for (int kb = 0; kb < 4; ++kb) {
         const int o = kb * LF_NB;
-        double* D = Di + kb * LF_NB * 33;
-        // ---- (a) 32 x 32 Cholesky by warp 0: lane i owns row o+i
-        if (warp == 0) {
-            const double* rowi = S + (o + lane) * LF_LD + o;
-            for (int j = 0; j < LF_NB; ++j) {
-                const double* rowj = S + (o + j) * LF_LD + o;
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                int k = 0;
-                for (; k + 4 <= j; k += 4) {
-                    a0 = fma(rowi[k], rowj[k], a0);
-                    a1 = fma(rowi[k + 1], rowj[k + 1], a1);
-                    a2 = fma(rowi[k + 2], rowj[k + 2], a2);
-                    a3 = fma(rowi[k + 3], rowj[k + 3], a3);
-                }
-                for (; k < j; ++k) a0 = fma(rowi[k], rowj[k], a0);
-                const double v = rowi[j] - ((a0 + a1) + (a2 + a3));
-                double vj = __shfl_sync(0xffffffffu, v, j);
-                if (!(vj > 0.0)) {  // non-positive or NaN pivot: report the first one, continue with 1
-                    if (lane == 0) atomicCAS(info, 0, col_offset + o + j + 1);
-                    vj = 1.0;
-                }
-                const double ri = rsqrt(vj);
-                if (lane == j) {
-                    S[(o + j) * LF_LD + o + j] = vj * ri;
-                    rinv[o + j] = ri;
-                } else if (lane > j) {
-                    S[(o + lane) * LF_LD + o + j] = v * ri;
-                }
-                __syncwarp();
-            }
-        }
+        if (warp == 0) chol32_warp(S, o, rinv, info, col_offset, lane);
         __syncthreads();
-        // ---- (b) D = inv(L_kk): column c by the 8 lanes {8c' .. 8c'+7} of one warp (column-private)
-        {
-            const int c = tid >> 3, sub = tid & 7;
-            for (int i = 0; i < LF_NB; ++i) {
-                double acc = 0.0;
-                if (i > c)
-                    for (int k = c + sub; k < i; k += 8) acc = fma(S[(o + i) * LF_LD + o + k], D[k * 33 + c], acc);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-                if (sub == 0) D[i * 33 + c] = (i < c) ? 0.0 : (i == c ? rinv[o + c] : -acc * rinv[o + i]);
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-        const int rem = LF - o - LF_NB;  // rows below the diagonal block
+        LF_TICK(2 + 3 * kb)
+        const int rem = LF - o - LF_NB;  // rows below the pivot block
         if (rem > 0) {
-            // ---- (c) panel solve into scratch: X[r][c] = sum_{k <= c} P[r][k] D[c][k]
-            for (int e = tid; e < rem * LF_NB; e += LF_THREADS) {
-                const int r = e >> 5, c = e & 31;
-                const double* prow = S + (o + LF_NB + r) * LF_LD + o;
-                double a0 = 0.0, a1 = 0.0;
-                int k = 0;
-                for (; k + 2 <= c + 1; k += 2) {
-                    a0 = fma(prow[k], D[c * 33 + k], a0);
-                    a1 = fma(prow[k + 1], D[c * 33 + k + 1], a1);
+            // ---- (c) panel solve X L_kk^T = P, one thread per row, row in registers
+            if (tid < rem) {
+                double* prow = S + (o + LF_NB + tid) * LF_LD + o;
+                double x[LF_NB];
+#pragma unroll
+                for (int k = 0; k < LF_NB; ++k) x[k] = prow[k];
+#pragma unroll
+                for (int c = 0; c < LF_NB; ++c) {
+                    const double* lrow = S + (o + c) * LF_LD + o;  // warp-uniform: broadcast reads
+                    double acc0 = x[c], acc1 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < c; ++k) {
+                        if (k & 1) acc1 = fma(-x[k], lrow[k], acc1);
+                        else acc0 = fma(-x[k], lrow[k], acc0);
+                    }
+                    x[c] = (acc0 + acc1) * rinv[o + c];
                 }
-                if (k <= c) a0 = fma(prow[k], D[c * 33 + k], a0);
-                Sc[r * 33 + c] = a0 + a1;
+#pragma unroll
+                for (int k = 0; k < LF_NB; ++k) prow[k] = x[k];
             }
             __syncthreads();
-            // ---- (d) write the panel back and update the trailing lower triangle (4 x 4 micro-tiles)
-            for (int e = tid; e < rem * LF_NB; e += LF_THREADS) {
-                const int r = e >> 5, c = e & 31;
-                S[(o + LF_NB + r) * LF_LD + o + c] = Sc[r * 33 + c];
-            }
-            const int nt = rem >> 2;  // micro-tiles per side
+            LF_TICK(3 + 3 * kb)
+            // ---- (d) trailing lower triangle -= X X^T, 4 x 4 micro-tiles
+            const int nt = rem >> 2;
             for (int e = tid; e < nt * nt; e += LF_THREADS) {
                 const int ti = e / nt, tj = e % nt;
                 if (tj > ti) continue;
-                const double* xi = Sc + (ti * 4) * 33;
-                const double* xj = Sc + (tj * 4) * 33;
+                const double* xi = S + (o + LF_NB + ti * 4) * LF_LD + o;
+                const double* xj = S + (o + LF_NB + tj * 4) * LF_LD + o;
                 double acc[4][4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
                     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 4
                 for (int k = 0; k < LF_NB; ++k) {
                     double va[4], vb[4];
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) { va[a] = xi[a * 33 + k]; vb[a] = xj[a * 33 + k]; }
+                    for (int a = 0; a < 4; ++a) { va[a] = xi[a * LF_LD + k]; vb[a] = xj[a * LF_LD + k]; }
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -138,19 +156,24 @@ __global__ void __launch_bounds__(LF_THREADS, 1)
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) dst[a * LF_LD + b] -= acc[a][b];
+                    for (int b = 0; b < 4; ++b)
+                        if (ti != tj || b <= a) dst[a * LF_LD + b] -= acc[a][b];  // keep the upper triangle zero
             }
             __syncthreads();
+            LF_TICK(4 + 3 * kb)
         }
     }
 
-    // ---- L is final: write it out, then turn S into inv(L) in place.  Block row i of inv(L) only needs
-    //      block row i of L and the finished rows above it:  M_ii = D_i,  M_ij = -D_i (sum_{k=j}^{i-1} L_ik M_kj).
+    // ---- L is final.  Warps 0-3 invert the four pivot blocks; everyone writes L out.
+    if (warp < 4) inv32_warp(S, warp * LF_NB, rinv, Di + warp * LF_NB * 33, lane);
     for (int e = tid; e < LF * LF; e += LF_THREADS) {
         const int r = e >> 7, c = e & 127;
         if (c <= r) A[(int64_t)r * lda + c] = S[r * LF_LD + c];
     }
     __syncthreads();
+    LF_TICK(12)
+    // ---- turn S into inv(L) in place.  Block row i of inv(L) only needs block row i of L and the finished
+    //      rows above it:  M_ii = D_i,  M_ij = -D_i (sum_{k=j}^{i-1} L_ik M_kj).
     for (int e = tid; e < 4 * LF_NB * LF_NB; e += LF_THREADS) {
         const int b = e >> 10, r = (e >> 5) & 31, c = e & 31;
         S[(b * LF_NB + r) * LF_LD + b * LF_NB + c] = Di[b * LF_NB * 33 + r * 33 + c];  // zeros above the diagonal
@@ -161,28 +184,38 @@ __global__ void __launch_bounds__(LF_THREADS, 1)
         for (int e = tid; e < LF_NB * w; e += LF_THREADS) {
             const int r = e / w, cc = e % w;
             const double* lrow = S + (w + r) * LF_LD;
-            double a0 = 0.0, a1 = 0.0;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             int kk = cc & ~31;  // M[kk][cc] == 0 for kk < cc; start at the block boundary (explicit zeros)
-            for (; kk + 2 <= w; kk += 2) {
+            for (; kk + 4 <= w; kk += 4) {
                 a0 = fma(lrow[kk], S[kk * LF_LD + cc], a0);
                 a1 = fma(lrow[kk + 1], S[(kk + 1) * LF_LD + cc], a1);
+                a2 = fma(lrow[kk + 2], S[(kk + 2) * LF_LD + cc], a2);
+                a3 = fma(lrow[kk + 3], S[(kk + 3) * LF_LD + cc], a3);
             }
-            Sc[r * LF_SC_LD + cc] = a0 + a1;
+            Sc[r * LF_SC_LD + cc] = (a0 + a1) + (a2 + a3);
         }
         __syncthreads();
         const double* D = Di + i * LF_NB * 33;
         for (int e = tid; e < LF_NB * w; e += LF_THREADS) {
             const int r = e / w, cc = e % w;
-            double a0 = 0.0;
-            for (int q = 0; q <= r; ++q) a0 = fma(D[r * 33 + q], Sc[q * LF_SC_LD + cc], a0);
-            S[(w + r) * LF_LD + cc] = -a0;
+            double a0 = 0.0, a1 = 0.0;
+            int q = 0;
+            for (; q + 2 <= r + 1; q += 2) {
+                a0 = fma(D[r * 33 + q], Sc[q * LF_SC_LD + cc], a0);
+                a1 = fma(D[r * 33 + q + 1], Sc[(q + 1) * LF_SC_LD + cc], a1);
+            }
+            if (q <= r) a0 = fma(D[r * 33 + q], Sc[q * LF_SC_LD + cc], a0);
+            S[(w + r) * LF_LD + cc] = -(a0 + a1);
         }
         __syncthreads();
     }
+    LF_TICK(13)
     for (int e = tid; e < LF * LF; e += LF_THREADS) {
         const int r = e >> 7, c = e & 127;
         dinv[r * LF + c] = (c <= r) ? S[r * LF_LD + c] : 0.0;
     }
+    LF_TICK(14)
+#undef LF_TICK
 }
 
 // Leaf TRSM: B (rows x 128, in place) <- B * Minv^T, Minv = inv(L_kk) lower triangular (dense 128x128).
@@ -291,7 +324,7 @@ static void trsm_rec(CholCtx& cx, double* B, int64_t ldb, int64_t m, const doubl
 
 static void potrf_rec(CholCtx& cx, double* A, int64_t lda, int64_t n, double* dinv, int* info, int64_t off) {
     if (n == LF) {
-        potf2_inv_kernel<<<1, LF_THREADS, LF_SMEM, cx.st>>>(A, lda, dinv, info, (int)off);
+        potf2_inv_kernel<false><<<1, LF_THREADS, LF_SMEM, cx.st>>>(A, lda, dinv, info, (int)off, nullptr);
         cx.note(cudaGetLastError());
         return;
     }
@@ -324,7 +357,8 @@ static void trtri_rec(CholCtx& cx, const double* L, int64_t ldl, const double* d
 static int chol_configure() {
     static bool done = false;
     if (done) return SOCKS_OK;
-    SOCKS_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM));
+    SOCKS_CUDA(cudaFuncSetAttribute(potf2_inv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM));
+    SOCKS_CUDA(cudaFuncSetAttribute(potf2_inv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM));
     SOCKS_CUDA(cudaFuncSetAttribute(trsm_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
     done = true;
     return SOCKS_OK;
@@ -364,6 +398,18 @@ extern "C" int socks_potrf(double* G, int64_t n, int64_t ldg, double* dinv, int*
         set_error("socks_potrf: CUDA launch failed: %s", cudaGetErrorString(cx.err));
         return SOCKS_ECUDA;
     }
+    return SOCKS_OK;
+}
+
+// Development helper: factor ONE 128 x 128 block (A, lda) and record clock64() at the phase boundaries of the
+// leaf kernel into cycles[0..14] (device buffer of 16 int64).
+extern "C" int socks_dev_potf2_phases(double* A, int64_t lda, double* dinv, int* info_dev, long long* cycles,
+                                      socks_stream_t stream) {
+    SOCKS_CHECK_ARG(A != nullptr && dinv != nullptr && info_dev != nullptr && cycles != nullptr, 1);
+    int rc = chol_configure();
+    if (rc) return rc;
+    potf2_inv_kernel<true><<<1, LF_THREADS, LF_SMEM, (cudaStream_t)stream>>>(A, lda, dinv, info_dev, 0, cycles);
+    SOCKS_CHECK_LAUNCH();
     return SOCKS_OK;
 }
 
