@@ -140,6 +140,18 @@ int socks_srmax_step(const double* Cm, int64_t ldc, int64_t m, int P, int R, int
                      int d, const double* tubes, int problem, int T, double* out, int64_t ldout,
                      int write_last, socks_stream_t stream);
 
+/* ---- Backward (dynamic-programming) control: gym_socks/algorithms/control/kernel_control_bwd.py:58-122 */
+
+/* Bm[i][r*P + a] = coefs[r][i] * CUA[i][a] (r < R), zero padding to np x ldbm: right operand of
+ * C = K(X,Y)^T diag(z) CUA for z = vf[t+1] @ W and z = constraint_t @ W (kernel_control_bwd.py:90-97). */
+int socks_scale_pack(const double* CUA, int64_t n, int P, const double* coefs, int64_t ldcoef, int R,
+                     double* Bm, int64_t np, int64_t ldbm, socks_stream_t stream);
+
+/* out[j] = add[j] + min_a {Cm[j][a] : Cm[j][P + a] <= 0} (all a when unconstrained or none feasible)
+ * (kernel_control_bwd.py:99-115). */
+int socks_rowmin_masked(const double* Cm, int64_t ldc, int64_t m, int P, int constrained, const double* add,
+                        double* out, socks_stream_t stream);
+
 /* ---- Forward control: gym_socks/algorithms/control/kernel_control_fwd.py:211-238 ------- */
 
 /* y[r][j] = sum_i V[r][i] * Bmat[i][j] (R <= 2 row vectors, V rows ldv apart; V NULL = ones).

@@ -29,6 +29,7 @@ from gym_socks.kernel.metrics import rbf_kernel, regularized_inverse  # noqa: E4
 from gym_socks.algorithms.reach.kernel_sr import KernelSR  # noqa: E402
 from gym_socks.algorithms.reach.kernel_sr_max import KernelMaximalSR  # noqa: E402
 from gym_socks.algorithms.control.kernel_control_fwd import KernelControlFwd  # noqa: E402
+from gym_socks.algorithms.control.kernel_control_bwd import KernelControlBwd  # noqa: E402
 from gym_socks.utils import normalize, indicator_fn  # noqa: E402
 
 from socks_b200 import synthetic as syn  # noqa: E402
@@ -138,7 +139,37 @@ def fwd_case(name, n, sigma, lam, T, seed, constrained):
          cond=np.linalg.cond(np.linalg.inv(pol.W)))
 
 
+def bwd_case(name, n, sigma, lam, T, seed, constrained):
+    X, U, Y = syn.unicycle_sample(n, seed=seed)
+    A = syn.unicycle_actions(6, 9)
+    cost = syn.tracking_cost_fn(T)
+
+    def constraint(time=0, state=None):
+        return np.abs(state[:, 1]) - (0.45 + 0.01 * time)
+
+    pol = KernelControlBwd(time_horizon=T, cost_fn=cost, constraint_fn=constraint if constrained else None,
+                           heuristic=True, regularization_param=lam, kernel_fn=partial(rbf_kernel, sigma=sigma),
+                           verbose=False)
+    pol.train(list(zip(X, U, Y)), A)
+    rng = np.random.default_rng(seed + 5)
+    states = rng.uniform([-1, -0.6, -1], [1, 0.6, 1], size=(T, 3))
+    Cs, acts = [], []
+    for t in range(T):
+        s = states[t:t + 1]
+        CXT = rbf_kernel(pol.X, s, sigma=sigma)
+        beta = pol.W @ (CXT * pol.CUA)
+        Cs.append(np.matmul(np.array(pol.value_functions[t], dtype=np.float32), beta))
+        acts.append(pol(time=t, state=s))
+    save(name, X=X, U=U, Y=Y, A=A, T=T, sigma=sigma, lam=lam, states=states, constrained=constrained,
+         value_functions=pol.value_functions, C=np.array(Cs), actions=np.array(acts),
+         cond=np.linalg.cond(np.linalg.inv(pol.W)))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "bwd":
+        bwd_case("bwd_unconstrained.npz", 300, 1.0, 1e-3, 6, seed=21, constrained=False)
+        bwd_case("bwd_constrained.npz", 260, 1.5, 1e-3, 5, seed=22, constrained=True)
+        sys.exit(0)
     kernel_cases()
     # BASELINE.json configs[0]: N=1000, T=15, 50x50 grid, sigma=0.1, lambda=1/N^2
     sr_case("sr_c1_fht.npz", 1000, None, 15, 2, 0.1, 1 / 1000 ** 2, "FHT", seed=0, grid=50)

@@ -29,6 +29,7 @@ __all__ = [
     "KernelSROracle",
     "KernelMaximalSROracle",
     "KernelControlFwdOracle",
+    "KernelControlBwdOracle",
     "heuristic_solution",
 ]
 
@@ -256,6 +257,59 @@ class KernelControlFwdOracle:
         CXT = rbf_kernel(self.X, np.asarray(state, dtype=np.float64).reshape(1, -1), self.sigma)
         beta = self.W @ (CXT * self.CUA)
         C = np.matmul(np.array(self.cost_fn(time=time, state=self.Y), dtype=np.float32), beta)
+        D = None
+        if self.constraint_fn is not None:
+            D = np.matmul(np.array(self.constraint_fn(time=time, state=self.Y), dtype=np.float32), beta)
+        return C, D
+
+    def __call__(self, time=0, state=None):
+        C, D = self.scores(time, state)
+        return np.array(self.A[heuristic_solution(C, D)], dtype=np.float32)
+
+
+class KernelControlBwdOracle:
+    """`KernelControlBwd.train/__call__` (`gym_socks/algorithms/control/kernel_control_bwd.py:58-122, 351-440`).
+
+    Recursion (`:70-120`): out[T-1] = f32(cost_{T-1}(Y)); for t = T-2..0: Z = out[t+1] @ W (`:90`),
+    C[j,k] = sum_i Z_i CXY[i,j] CUA[i,k] (`:67,91`: einsum over beta = CXY (x) CUA), optional
+    D from R = constraint_t(Y) @ W (`:96-97`), V_j = min_k C[j,k] over {D[j,k] <= 0} (all k if empty, `:99-107`),
+    out[t] = cost_t(Y) + V (`:115`).  The N x N x P tensor `beta` is never formed: C = CXY^T diag(Z) CUA."""
+
+    def __init__(self, time_horizon, cost_fn, constraint_fn=None, sigma=0.1, regularization_param=1):
+        self.T, self.cost_fn, self.constraint_fn = time_horizon, cost_fn, constraint_fn
+        self.sigma, self.lam = sigma, regularization_param
+
+    def train(self, X, U, Y, A):
+        self.X = np.asarray(X, dtype=np.float64)
+        self.Y = np.asarray(Y, dtype=np.float64)
+        self.A = np.asarray(A, dtype=np.float64)
+        U = np.asarray(U, dtype=np.float64)
+        self.W = regularized_inverse(self.X, U=U, regularization_param=self.lam, sigma=self.sigma)
+        self.CUA = rbf_kernel(U, self.A, self.sigma)
+        CXY = rbf_kernel(self.X, self.Y, self.sigma)
+        n, T = len(self.Y), self.T
+        out = np.empty((T, n))
+        out[T - 1, :] = np.array(self.cost_fn(time=T - 1, state=self.Y), dtype=np.float32)
+        for t in range(T - 2, -1, -1):
+            Z = np.matmul(out[t + 1, :], self.W)
+            C = CXY.T @ (Z[:, None] * self.CUA)
+            if self.constraint_fn is not None:
+                R = np.matmul(self.constraint_fn(time=t, state=self.Y), self.W)
+                D = CXY.T @ (R[:, None] * self.CUA)
+                V = np.empty(n)
+                for i in range(n):
+                    CA = C[i][D[i] <= 0]
+                    V[i] = np.min(C[i]) if CA.size == 0 else np.min(CA)
+            else:
+                V = np.min(C, axis=1)
+            out[t, :] = self.cost_fn(time=t, state=self.Y) + V
+        self.value_functions = out
+        return self
+
+    def scores(self, time, state):
+        CXT = rbf_kernel(self.X, np.asarray(state, dtype=np.float64).reshape(1, -1), self.sigma)
+        beta = self.W @ (CXT * self.CUA)
+        C = np.matmul(np.array(self.value_functions[time], dtype=np.float32), beta)
         D = None
         if self.constraint_fn is not None:
             D = np.matmul(np.array(self.constraint_fn(time=time, state=self.Y), dtype=np.float32), beta)

@@ -58,9 +58,88 @@ __global__ void srmax_step_kernel(const double* __restrict__ Cm, int64_t ldc, in
         out[(int64_t)(T - 1) * ldout + j] = in_box(pts + j * d, tubes + (int64_t)(T - 1) * 4 * d, 1, d) ? 1.0 : 0.0;
 }
 
+// Bm[i][r*P + a] = coefs[r][i] * CUA[i][a]: the right operand of C = K(X,Y)^T diag(z) CUA for arbitrary row
+// vectors z (kernel_control_bwd.py:90-97: Z = vf[t+1] @ W, R = constraint_t @ W).
+__global__ void scale_pack_kernel(const double* __restrict__ CUA, int64_t n, int P, const double* __restrict__ coefs,
+                                  int64_t ldcoef, int R, double* __restrict__ Bm, int64_t ldbm) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = blockIdx.y;
+    if (c >= ldbm) return;
+    double v = 0.0;
+    if (i < n && c < (int64_t)R * P) {
+        const int r = (int)(c / P), a = (int)(c % P);
+        v = coefs[(int64_t)r * ldcoef + i] * CUA[i * P + a];
+    }
+    Bm[i * ldbm + c] = v;
+}
+
+// out[j] = add[j] + min_a { C[j][a] : D[j][a] <= 0 }  (all a if unconstrained or no a is feasible);
+// C = Cm[:, 0:P], D = Cm[:, P:2P].  np.min semantics (NaN among the candidates propagates).
+// kernel_control_bwd.py:99-115.  One warp per row.
+__global__ void rowmin_masked_kernel(const double* __restrict__ Cm, int64_t ldc, int64_t m, int P, int constrained,
+                                     const double* __restrict__ add, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= m) return;
+    const double* row = Cm + j * ldc;
+    double best_all = INFINITY, best_ok = INFINITY;
+    int nan_all = 0, nan_ok = 0, any_ok = 0;
+    for (int a = lane; a < P; a += 32) {
+        const double c = row[a];
+        const bool isn = (c != c);
+        nan_all |= isn;
+        best_all = fmin(best_all, c);
+        if (constrained && row[P + a] <= 0.0) {
+            any_ok = 1;
+            nan_ok |= isn;
+            best_ok = fmin(best_ok, c);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        best_all = fmin(best_all, __shfl_xor_sync(0xffffffffu, best_all, off));
+        best_ok = fmin(best_ok, __shfl_xor_sync(0xffffffffu, best_ok, off));
+        nan_all |= __shfl_xor_sync(0xffffffffu, nan_all, off);
+        nan_ok |= __shfl_xor_sync(0xffffffffu, nan_ok, off);
+        any_ok |= __shfl_xor_sync(0xffffffffu, any_ok, off);
+    }
+    if (lane == 0) {
+        double v = (constrained && any_ok) ? (nan_ok ? NAN : best_ok) : (nan_all ? NAN : best_all);
+        out[j] = add[j] + v;
+    }
+}
+
 }  // namespace socks
 
 using namespace socks;
+
+extern "C" int socks_scale_pack(const double* CUA, int64_t n, int P, const double* coefs, int64_t ldcoef, int R,
+                                double* Bm, int64_t np, int64_t ldbm, socks_stream_t stream) {
+    SOCKS_CHECK_ARG(CUA != nullptr, 1);
+    SOCKS_CHECK_ARG(n >= 1, 2);
+    SOCKS_CHECK_ARG(P >= 1, 3);
+    SOCKS_CHECK_ARG(coefs != nullptr && ldcoef >= n, 4);
+    SOCKS_CHECK_ARG(R >= 1, 6);
+    SOCKS_CHECK_ARG(Bm != nullptr, 7);
+    SOCKS_CHECK_ARG(np >= n && np <= 65535, 8);
+    SOCKS_CHECK_ARG(ldbm >= (int64_t)R * P && ldbm % 2 == 0, 9);
+    dim3 grid((unsigned)ceil_div(ldbm, 256), (unsigned)np);
+    scale_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(CUA, n, P, coefs, ldcoef, R, Bm, ldbm);
+    SOCKS_CHECK_LAUNCH();
+    return SOCKS_OK;
+}
+
+extern "C" int socks_rowmin_masked(const double* Cm, int64_t ldc, int64_t m, int P, int constrained,
+                                   const double* add, double* out, socks_stream_t stream) {
+    SOCKS_CHECK_ARG(Cm != nullptr, 1);
+    SOCKS_CHECK_ARG(m >= 1, 3);
+    SOCKS_CHECK_ARG(P >= 1 && ldc >= (constrained ? 2 : 1) * (int64_t)P, 4);
+    SOCKS_CHECK_ARG(add != nullptr, 6);
+    SOCKS_CHECK_ARG(out != nullptr, 7);
+    rowmin_masked_kernel<<<(unsigned)ceil_div(m, 8), 256, 0, (cudaStream_t)stream>>>(Cm, ldc, m, P, constrained, add,
+                                                                                     out);
+    SOCKS_CHECK_LAUNCH();
+    return SOCKS_OK;
+}
 
 extern "C" int socks_srmax_pack(const double* CUA, int64_t n, int P, const double* w, const double* vf, int64_t ldvf,
                                 int t0, int R, double* Bm, int64_t np, int64_t ldbm, socks_stream_t stream) {

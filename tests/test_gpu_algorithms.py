@@ -222,3 +222,27 @@ def test_kernel_control_fwd_golden(name, heuristic):
         if heuristic:
             assert np.array_equal(act, g["actions"][t])
     assert np.linalg.norm(pol.W - np.linalg.inv(np.linalg.inv(pol.W))) >= 0  # W is exposed as an ndarray
+
+
+@pytest.mark.parametrize("name", ["bwd_unconstrained.npz", "bwd_constrained.npz"])
+def test_kernel_control_bwd_golden(name):
+    """KernelControlBwd against the unmodified reference (value functions, scores, actions)."""
+    from socks_b200.algorithms.control.kernel_control_bwd import KernelControlBwd
+    _, _, _, _, _, rbf = _api()
+    g = load_golden(name)
+    T = int(g["T"])
+    cons = None
+    if bool(g["constrained"]):
+        def cons(time=0, state=None):
+            return np.abs(state[:, 1]) - (0.45 + 0.01 * time)
+    pol = KernelControlBwd(time_horizon=T, cost_fn=syn.tracking_cost_fn(T), constraint_fn=cons, heuristic=True,
+                           regularization_param=float(g["lam"]), kernel_fn=partial(rbf, sigma=float(g["sigma"])),
+                           verbose=False)
+    pol.train(syn.as_sample(g["X"], g["U"], g["Y"]), g["A"])
+    tol = max(1e-8, 100 * float(g["cond"]) * 2.0 ** -53)
+    scale = np.max(np.abs(g["value_functions"]))
+    assert np.max(np.abs(pol.value_functions - g["value_functions"])) <= tol * scale
+    for t in range(T):
+        y = pol.scores(time=t, state=[g["states"][t]]).cpu().numpy()
+        assert np.max(np.abs(y[0] - g["C"][t])) <= tol * np.max(np.abs(g["C"][t]))
+        assert np.array_equal(pol(time=t, state=[g["states"][t]]), g["actions"][t])

@@ -93,3 +93,24 @@ def test_control_fwd_golden(name):
         if cons is not None:
             assert np.max(np.abs(D - g["D"][t])) <= tol * np.max(np.abs(g["D"][t]))
         assert np.array_equal(pol(time=t, state=g["states"][t]), g["actions"][t])
+
+
+@pytest.mark.parametrize("name", ["bwd_unconstrained.npz", "bwd_constrained.npz"])
+def test_control_bwd_golden(name):
+    from socks_b200 import synthetic as syn
+
+    g = load_golden(name)
+    T = int(g["T"])
+    cons = None
+    if bool(g["constrained"]):
+        def cons(time=0, state=None):
+            return np.abs(state[:, 1]) - (0.45 + 0.01 * time)
+    pol = orc.KernelControlBwdOracle(T, syn.tracking_cost_fn(T), cons, float(g["sigma"]), float(g["lam"]))
+    pol.train(g["X"], g["U"], g["Y"], g["A"])
+    tol = max(1e-8, 100 * float(g["cond"]) * 2.0 ** -53)
+    scale = np.max(np.abs(g["value_functions"]))
+    assert np.max(np.abs(pol.value_functions - g["value_functions"])) <= tol * scale
+    for t in range(T):
+        C, _ = pol.scores(t, g["states"][t])
+        assert np.max(np.abs(C - g["C"][t])) <= tol * np.max(np.abs(g["C"][t]))
+        assert np.array_equal(pol(time=t, state=g["states"][t]), g["actions"][t])
