@@ -80,15 +80,15 @@ __device__ __forceinline__ void sp_load_stage(double* __restrict__ sx, double* _
 template <int D>
 __global__ void __launch_bounds__(SP_WARPS * 32, 2)
     sr_predict_dmma_kernel(const double* __restrict__ X, const double* __restrict__ coef, int64_t n, int64_t n_pad,
-                           const double* __restrict__ pts, int64_t m, double neg_gamma, double* __restrict__ part,
+                           const double* __restrict__ pts, int64_t m, ExpScaled ex, double* __restrict__ part,
                            int64_t ldp) {
     __shared__ __align__(16) double sx[2][SP_TS * D];
     __shared__ __align__(16) double sc[2][SP_TS * SR_CP];
-    __shared__ double etbl[EXP_TBL];
+    __shared__ double etbl[EXP_TBL2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lq = lane >> 2, lr = lane & 3;
     const int64_t pbase = (int64_t)blockIdx.x * SP_PTS + warp * (SP_Q * 8);
-    exp_table_init(etbl, tid, SP_WARPS * 32);  // visible after the first __syncthreads of the main loop
+    exp_table2_init(etbl, tid, SP_WARPS * 32);  // visible after the first __syncthreads of the main loop
 
     double p[SP_Q][D];
 #pragma unroll
@@ -134,9 +134,9 @@ __global__ void __launch_bounds__(SP_WARPS * 32, 2)
                         const double t = p[q][k] - xs[k];
                         d2 = fma(t, t, d2);
                     }
-                    arg[q] = d2 * neg_gamma;
+                    arg[q] = d2;
                 }
-                exp_tbl_x4(arg, kv, etbl);
+                exp_scaled_x4(arg, kv, etbl, ex);
 #pragma unroll
                 for (int q = 0; q < SP_Q; ++q) {
                     dmma884(acc[q][0][0], acc[q][0][1], a0, kv[q]);
@@ -343,7 +343,8 @@ static void launch_predict(int variant, const double* X, const double* coef, int
                            cudaStream_t st) {
     if (variant == 0) {
         dim3 grid((unsigned)ceil_div(m, SP_PTS), (unsigned)splits);
-        sr_predict_dmma_kernel<D><<<grid, SP_WARPS * 32, 0, st>>>(X, coef, n, n_pad, pts, m, kmul, part, ldp);
+        sr_predict_dmma_kernel<D><<<grid, SP_WARPS * 32, 0, st>>>(X, coef, n, n_pad, pts, m, make_exp_scaled(kmul), part,
+                                                                  ldp);
         sr_predict_finish_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(part, ldp, splits, m, R, t0, pts, D,
                                                                              tubes, problem, out, ldout);
     } else {
