@@ -28,8 +28,8 @@ if ROOT not in sys.path:
 
 SIGMA, DIM, PROBLEM = 0.1, 2, "FHT"
 # algorithmic FP64 work per (sample, test point) pair of the fused predict:
-# distance 3d+2, shipped exp (exp_f64.cuh: 8 DFMA + DADD + DMUL = 18 flop), contraction 2T
-EXP_FLOPS = 18
+# distance 3d+2, shipped exp (exp_f64.cuh exp_scaled_x4: 7 DFMA + DADD + DMUL = 16 flop), contraction 2T
+EXP_FLOPS = 16
 
 
 def pair_flops(d, T):
@@ -286,7 +286,7 @@ def run_ours(args):
                          # --set full capture summarised in profiles/r1_ncu_sr_predict_dmma_n20000_m250000.txt
                          "traffic": 280.0e6 if (n, m, T) == (20000, 250000, 15) else None,
                          "kernel": "sr_predict_dmma_kernel<2>",
-                         "note": "algorithmic flops = N*M*(3d+2+E+2T), E=18 (exp_f64.cuh); FMA and DMMA share the "
+                         "note": "algorithmic flops = N*M*(3d+2+E+2T), E=16 (exp_f64.cuh); FMA and DMMA share the "
                                  "FP64 pipe on B200 (tools/probe_fp64.py: 36.5 / 37.1 TFLOP/s alone, 35.7 combined), so the fp64 "
                                  "tensor peak bounds the whole kernel; measured live by socks_probe_fp64 "
                                  "(MEASURED_PEAKS.json has HBM and bf16 only)",

@@ -23,6 +23,21 @@ constexpr int LF_SC_LD = 97;    // scratch [32][97] for the inverse assembly
 // S (L, then inv L in place), Dinv[4][32][33], scratch 32*97 (+ slack), rinv[128]  (~190 KB)
 constexpr int LF_SMEM = (LF * LF_LD + 4 * LF_NB * 33 + 96 * 33 + LF) * 8;
 
+// 1/sqrt(d) for the pivot recurrence, branch-free so the whole unrolled factorisation stays one basic block
+// and the scheduler can interleave a column's trailing updates with the next pivot's chain: hardware seed
+// (rsqrt.approx.ftz.f64 -> MUFU.RSQ64H, relative error ~2^-22) and ONE third-order step
+// y (1 + r/2 + 3 r^2/8), r = 1 - d y^2 (error ~ r^3 < 2^-60: the result is within ~1 ulp).
+// Valid for d in the normal range; the caller treats pivots outside [1e-290, 1e290] as failures.
+__device__ __forceinline__ double rsqrt_pivot(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double t = d * y;
+    const double r = fma(-t, y, 1.0);
+    const double u = y * r;
+    const double s2 = fma(r, 0.375, 0.5);
+    return fma(u, s2, y);
+}
+
 // (a) Cholesky of the 32 x 32 block at (o, o) of S by ONE warp, entirely in registers: lane i owns row i,
 // pivots and multipliers travel by shuffle, the pivot is inverted with rsqrt (rinv[o+j] = 1 / L_jj).
 __device__ __forceinline__ void chol32_warp(double* __restrict__ S, int o, double* __restrict__ rinv,
@@ -31,17 +46,19 @@ __device__ __forceinline__ void chol32_warp(double* __restrict__ S, int o, doubl
     double* row = S + (o + lane) * LF_LD + o;
 #pragma unroll
     for (int k = 0; k < LF_NB; ++k) a[k] = row[k];  // strictly-upper entries of S are zero
+    double dnext = a[0];  // lane j's own updated diagonal, formed without waiting for the shuffle of l
+    int first_bad = -1;
 #pragma unroll
     for (int j = 0; j < LF_NB; ++j) {
-        double d = __shfl_sync(0xffffffffu, a[j], j);
-        if (!(d > 0.0)) {  // non-positive or NaN pivot: report the first one, continue with 1
-            if (lane == 0) atomicCAS(info, 0, col_offset + o + j + 1);
-            d = 1.0;
-        }
-        const double ri = rsqrt(d);
+        double d = __shfl_sync(0xffffffffu, dnext, j);
+        const bool bad = !(d > 1e-290 && d < 1e290);  // non-positive, NaN or out-of-range pivot: continue with 1
+        first_bad = (bad && first_bad < 0) ? j : first_bad;
+        d = bad ? 1.0 : d;
+        const double ri = rsqrt_pivot(d);
         const double l = ((lane == j) ? d : a[j]) * ri;  // lane j: sqrt(d); lanes > j: L[i][j]
         a[j] = l;
         if (lane == j) rinv[o + j] = ri;
+        if (j + 1 < LF_NB) dnext = fma(-l, l, a[j + 1]);  // valid in lane j+1 (its a[j+1] is the diagonal)
 #pragma unroll
         for (int k = j + 1; k < LF_NB; ++k) {
             const double lk = __shfl_sync(0xffffffffu, l, k);
@@ -51,6 +68,7 @@ __device__ __forceinline__ void chol32_warp(double* __restrict__ S, int o, doubl
 #pragma unroll
     for (int k = 0; k < LF_NB; ++k)
         if (k <= lane) row[k] = a[k];
+    if (first_bad >= 0 && lane == 0) atomicCAS(info, 0, col_offset + o + first_bad + 1);  // report the first one
 }
 
 // (b) D = inv(L_oo) (32 x 32 lower) by one warp: lane c owns column c (forward substitution in registers,
@@ -74,6 +92,44 @@ __device__ __forceinline__ void inv32_warp(const double* __restrict__ S, int o, 
     for (int i = 0; i < LF_NB; ++i) D[i * 33 + lane] = m[i];
 }
 
+// One 8 x 8 output tile of A(8 x 4*ksteps) * B on the fp64 tensor core, operands in shared memory.
+//   a(i,k) = Ap[i*lda + k];  TB: b(k,j) = Bp[j*ldb + k];  !TB: b(k,j) = Bp[k*ldb + j].
+// Returns this lane's two accumulators C[lq][2*lr], C[lq][2*lr+1].
+template <bool TB>
+__device__ __forceinline__ double2 smem_tile8(const double* __restrict__ Ap, int lda, const double* __restrict__ Bp,
+                                              int ldb, int ksteps, int lq, int lr) {
+    double c0 = 0.0, c1 = 0.0;
+#pragma unroll 4
+    for (int ks = 0; ks < ksteps; ++ks) {
+        const double a = Ap[lq * lda + ks * 4 + lr];
+        const double b = TB ? Bp[lq * ldb + ks * 4 + lr] : Bp[(ks * 4 + lr) * ldb + lq];
+        dmma884(c0, c1, a, b);
+    }
+    return make_double2(c0, c1);
+}
+
+// 16 x 16 output block = 2 x 2 tiles with four independent accumulator chains (DMMA latency is ~4x its issue
+// interval, so one 8 x 8 tile per warp leaves the pipe idle).  c[a][b] is the tile at rows 8a, cols 8b.
+template <bool TB>
+__device__ __forceinline__ void smem_tile16(const double* __restrict__ Ap, int lda, const double* __restrict__ Bp,
+                                            int ldb, int ksteps, int lq, int lr, double2 (&c)[2][2]) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) c[a][b] = make_double2(0.0, 0.0);
+#pragma unroll 2
+    for (int ks = 0; ks < ksteps; ++ks) {
+        const int k = ks * 4 + lr;
+        const double a0 = Ap[lq * lda + k], a1 = Ap[(lq + 8) * lda + k];
+        const double b0 = TB ? Bp[lq * ldb + k] : Bp[k * ldb + lq];
+        const double b1 = TB ? Bp[(lq + 8) * ldb + k] : Bp[k * ldb + lq + 8];
+        dmma884(c[0][0].x, c[0][0].y, a0, b0);
+        dmma884(c[0][1].x, c[0][1].y, a0, b1);
+        dmma884(c[1][0].x, c[1][0].y, a1, b0);
+        dmma884(c[1][1].x, c[1][1].y, a1, b1);
+    }
+}
+
 // Factor one 128 x 128 diagonal block in shared memory and invert the factor.
 //   A (global, lower part) <- L ;  dinv (dense 128 x 128) <- inv(L) with explicit zeros above.
 // Right-looking over four 32-column panels: (a) one warp factors the 32 x 32 pivot block in registers,
@@ -94,9 +150,12 @@ __global__ void __launch_bounds__(LF_THREADS, 1)
     double* rinv = Sc + 96 * 33;             // [128] 1 / L_jj
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int e = tid; e < LF * LF; e += LF_THREADS) {
-        const int r = e >> 7, c = e & 127;
-        S[r * LF_LD + c] = (c <= r) ? A[(int64_t)r * lda + c] : 0.0;
+#pragma unroll 4
+    for (int e = tid; e < LF * LF / 2; e += LF_THREADS) {  // 16-byte loads, all in flight before first use
+        const int r = e >> 6, c = (e & 63) * 2;
+        const double2 v = *reinterpret_cast<const double2*>(A + (int64_t)r * lda + c);
+        S[r * LF_LD + c] = (c <= r) ? v.x : 0.0;
+        S[r * LF_LD + c + 1] = (c + 1 <= r) ? v.y : 0.0;
     }
     __syncthreads();
     LF_TICK(1)
@@ -130,34 +189,24 @@ __global__ void __launch_bounds__(LF_THREADS, 1)
             }
             __syncthreads();
             LF_TICK(3 + 3 * kb)
-            // ---- (d) trailing lower triangle -= X X^T, 4 x 4 micro-tiles
-            const int nt = rem >> 2;
-            for (int e = tid; e < nt * nt; e += LF_THREADS) {
-                const int ti = e / nt, tj = e % nt;
-                if (tj > ti) continue;
-                const double* xi = S + (o + LF_NB + ti * 4) * LF_LD + o;
-                const double* xj = S + (o + LF_NB + tj * 4) * LF_LD + o;
-                double acc[4][4];
+            // ---- (d) trailing lower triangle -= X X^T: 16 x 16 DMMA blocks, one warp per block (K = 32)
+            {
+                const int nt = rem >> 4, lq = lane >> 2, lr = lane & 3;
+                const double* Xp = S + (o + LF_NB) * LF_LD + o;
+                for (int e = warp; e < nt * nt; e += LF_THREADS / 32) {
+                    const int ti = e / nt, tj = e % nt;
+                    if (tj > ti) continue;
+                    double2 c[2][2];
+                    smem_tile16<true>(Xp + ti * 16 * LF_LD, LF_LD, Xp + tj * 16 * LF_LD, LF_LD, LF_NB / 4, lq, lr, c);
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                    for (int a2 = 0; a2 < 2; ++a2)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-#pragma unroll 4
-                for (int k = 0; k < LF_NB; ++k) {
-                    double va[4], vb[4];
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) { va[a] = xi[a * LF_LD + k]; vb[a] = xj[a * LF_LD + k]; }
-#pragma unroll
-                    for (int a = 0; a < 4; ++a)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) acc[a][b] = fma(va[a], vb[b], acc[a][b]);
+                        for (int b2 = 0; b2 < 2; ++b2) {
+                            double* dst = S + (o + LF_NB + ti * 16 + a2 * 8 + lq) * LF_LD + o + LF_NB + tj * 16 + b2 * 8 + 2 * lr;
+                            dst[0] -= c[a2][b2].x;
+                            dst[1] -= c[a2][b2].y;
+                        }
                 }
-                double* dst = S + (o + LF_NB + ti * 4) * LF_LD + o + LF_NB + tj * 4;
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (ti != tj || b <= a) dst[a * LF_LD + b] -= acc[a][b];  // keep the upper triangle zero
             }
             __syncthreads();
             LF_TICK(4 + 3 * kb)
@@ -181,31 +230,40 @@ __global__ void __launch_bounds__(LF_THREADS, 1)
     __syncthreads();
     for (int i = 1; i < 4; ++i) {
         const int w = i * LF_NB;  // columns 0 .. w-1
-        for (int e = tid; e < LF_NB * w; e += LF_THREADS) {
-            const int r = e / w, cc = e % w;
-            const double* lrow = S + (w + r) * LF_LD;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int kk = cc & ~31;  // M[kk][cc] == 0 for kk < cc; start at the block boundary (explicit zeros)
-            for (; kk + 4 <= w; kk += 4) {
-                a0 = fma(lrow[kk], S[kk * LF_LD + cc], a0);
-                a1 = fma(lrow[kk + 1], S[(kk + 1) * LF_LD + cc], a1);
-                a2 = fma(lrow[kk + 2], S[(kk + 2) * LF_LD + cc], a2);
-                a3 = fma(lrow[kk + 3], S[(kk + 3) * LF_LD + cc], a3);
-            }
-            Sc[r * LF_SC_LD + cc] = (a0 + a1) + (a2 + a3);
+        const int lq = lane >> 2, lr = lane & 3;
+        // stage 1: T (32 x w) = L_i,: (32 x w) * M (w x w lower), 16 x 16 DMMA blocks; k starts at the column's
+        // 32-block (explicit zeros above the diagonal inside it)
+        const int ntc16 = w >> 4;
+        for (int e = warp; e < 2 * ntc16; e += LF_THREADS / 32) {
+            const int tr = e / ntc16, tc = e % ntc16;
+            const int ks0 = (tc * 16) & ~31;
+            double2 c[2][2];
+            smem_tile16<false>(S + (w + tr * 16) * LF_LD + ks0, LF_LD, S + ks0 * LF_LD + tc * 16, LF_LD, (w - ks0) >> 2,
+                               lq, lr, c);
+#pragma unroll
+            for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+                for (int b2 = 0; b2 < 2; ++b2) {
+                    double* dst = Sc + (tr * 16 + a2 * 8 + lq) * LF_SC_LD + tc * 16 + b2 * 8 + 2 * lr;
+                    dst[0] = c[a2][b2].x;
+                    dst[1] = c[a2][b2].y;
+                }
         }
         __syncthreads();
+        // stage 2: M_i,: = -D_i * T  (D_i lower with explicit zeros above: k runs to the end of the row block)
         const double* D = Di + i * LF_NB * 33;
-        for (int e = tid; e < LF_NB * w; e += LF_THREADS) {
-            const int r = e / w, cc = e % w;
-            double a0 = 0.0, a1 = 0.0;
-            int q = 0;
-            for (; q + 2 <= r + 1; q += 2) {
-                a0 = fma(D[r * 33 + q], Sc[q * LF_SC_LD + cc], a0);
-                a1 = fma(D[r * 33 + q + 1], Sc[(q + 1) * LF_SC_LD + cc], a1);
-            }
-            if (q <= r) a0 = fma(D[r * 33 + q], Sc[q * LF_SC_LD + cc], a0);
-            S[(w + r) * LF_LD + cc] = -(a0 + a1);
+        for (int e = warp; e < 2 * ntc16; e += LF_THREADS / 32) {
+            const int tr = e / ntc16, tc = e % ntc16;
+            double2 c[2][2];
+            smem_tile16<false>(D + tr * 16 * 33, 33, Sc + tc * 16, LF_SC_LD, (tr * 16 + 16) >> 2, lq, lr, c);
+#pragma unroll
+            for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+                for (int b2 = 0; b2 < 2; ++b2) {
+                    double* dst = S + (w + tr * 16 + a2 * 8 + lq) * LF_LD + tc * 16 + b2 * 8 + 2 * lr;
+                    dst[0] = -c[a2][b2].x;
+                    dst[1] = -c[a2][b2].y;
+                }
         }
         __syncthreads();
     }
