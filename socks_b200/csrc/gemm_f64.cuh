@@ -67,7 +67,9 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, WM, WN, STAGES>::THREADS, MINB
     constexpr int GM_STAGES = STAGES;
     constexpr int THREADS = Cfg::THREADS, MI = Cfg::MI, NI = Cfg::NI;
     extern __shared__ __align__(16) double gm_smem[];
-    const int64_t m0 = (int64_t)blockIdx.y * BM;
+    // k_hi grows with m0 for a lower-triangular A: launch the long tiles first (no tail of heavy CTAs)
+    const int by = (flags & GEMM_A_K_LE_M) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    const int64_t m0 = (int64_t)by * BM;
     const int64_t n0 = (int64_t)blockIdx.x * BN;
     if (lower_only && (n0 / TILE) > (m0 / TILE)) return;  // 128-tile strictly above the block diagonal
 

@@ -76,6 +76,13 @@ def main(n=20000, m=250000, T=15, out_path=None, hbm_gbs=6546.2):
     res["fit_recursion_s"] = t
     res["fit_recursion_gbs"] = T * 8 * n * n / t / 1e9  # T passes: 1 normaliser + T-1 steps
     res["fit_recursion_frac_hbm"] = res["fit_recursion_gbs"] / hbm_gbs
+    # steady-state cost of one GEMV pass alone (15 back-to-back passes, no step kernels in between)
+    yv = dv.empty(1, n)
+    f = lambda: _lib.call("socks_gemv_t", dv.ptr(B), n, n, ldb, dv.ptr(vf), n, 1, dv.ptr(yv), n, dv.ptr(rwk), st)
+    f()
+    t, _ = timed(f, reps=15)
+    res["gemv_pass_s"] = t
+    res["gemv_pass_gbs"] = 8 * n * n / t / 1e9
     out = dv.empty(T, m)
     coef = dv.work(lib.socks_sr_predict_work_bytes(n, m))
     for variant in (0, 1):
