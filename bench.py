@@ -295,6 +295,8 @@ def run_ours(args):
             "wall_s_timed_region": wall,
         }
         line.update(fit_info)
+        if world == 1 and not args.no_extras:
+            line["kernel_maximal_sr"] = maximal_sr_extra(n, m, T, d, ct, tt, X, U, Y, pts)
         if world == 1:
             wh, vfh = alg._w.cpu().numpy(), alg._vf.cpu().numpy()
             v, dt = cpu_predict_sample(n, T, args.cpu_sample, w=wh, vf=vfh, X=X)
@@ -307,6 +309,42 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def maximal_sr_extra(n, m, T, d, ct, tt, X, U, Y, pts, P=100):
+    """BASELINE.json configs[1] names KernelMaximalSR at the same sizes: report it beside the headline (one fit and one
+    predict over the same M resident test points, P = 100 admissible actions as benchmarks/kernel_sr_max/baseline.py:33)."""
+    import torch
+    from functools import partial
+
+    from socks_b200 import _device as dv
+    from socks_b200.algorithms.reach.kernel_sr_max import KernelMaximalSR
+    from socks_b200.kernel.metrics import rbf_kernel
+
+    A = np.linspace(-1, 1, P).reshape(-1, 1)
+    alg = KernelMaximalSR(time_horizon=T, constraint_tube=ct, target_tube=tt, problem=PROBLEM,
+                          kernel_fn=partial(rbf_kernel, sigma=SIGMA), regularization_param=1.0)
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3, r
+
+    t_fit, _ = timed(lambda: alg.fit_arrays(X, U, Y, A))
+    alg.predict_dev(pts[:16384])
+    t_pred, out = timed(lambda: alg.predict_dev(pts))
+    npad = dv.padded(n)
+    cols = -(-T * P // 128) * 128
+    res = {"P": P, "fit_s": t_fit, "predict_s": t_pred, "points_per_s": m / t_pred,
+           "predict_gemm_tflops": 2.0 * npad * m * cols / t_pred / 1e12,
+           "note": "predict = Gram chunks + one DMMA GEMM K(X,pts)^T [diag(coef_r) CUA]_r per chunk + fused max/step"}
+    del alg, out
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -317,6 +355,7 @@ def main():
     ap.add_argument("--m", type=int, default=250000)
     ap.add_argument("--T", type=int, default=15)
     ap.add_argument("--cpu-sample", type=int, default=4000)
+    ap.add_argument("--no-extras", action="store_true", help="skip the KernelMaximalSR side measurement")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --m test points per GPU (default, the driver's contract); strong: --m in total")
     args = ap.parse_args()

@@ -114,10 +114,12 @@ int socks_sr_predict(const double* X, const double* w, const double* vf, int64_t
 
 /* ---- Maximal SR: gym_socks/algorithms/reach/kernel_sr_max.py:30-79 --------------------- */
 
-/* Bm[i][c] = coef_r[i] * CUA[i][a] for c = r*P + a, r < R; zero for i >= n or c >= R*P.
- * coef row 0 = w, rows r >= 1 = vf[t0 + r] * w.  Bm: np x ldbm (the GEMM's right operand). */
+/* Bm[i][c] = coef_r[i] * CUA[i][a] for c = (r - first_row)*P + a, first_row <= r < first_row + R; zero for
+ * i >= n or c >= R*P.  coef row 0 = w (the normaliser, independent of t), rows r >= 1 = vf[t0 + r] * w.
+ * Bm: np x ldbm (the GEMM's right operand). */
 int socks_srmax_pack(const double* CUA, int64_t n, int P, const double* w, const double* vf,
-                     int64_t ldvf, int t0, int R, double* Bm, int64_t np, int64_t ldbm, socks_stream_t stream);
+                     int64_t ldvf, int t0, int first_row, int R, double* Bm, int64_t np, int64_t ldbm,
+                     socks_stream_t stream);
 
 /* C (m x nn) = A^T B with A = Kmat (K x m, row-major: the Gram chunk K(X, pts)), B = Bm (K x nn);
  * m, nn multiples of 128, K multiple of 16.  DMMA GEMM (kernel_sr_max.py:65-70 as a contraction). */
@@ -134,9 +136,11 @@ int socks_gemm_f64(int transa, int transb, const double* A, int64_t lda, const d
                    int64_t ldc, int64_t m, int64_t nn, int64_t K, double alpha, double beta, int flags,
                    int lower_only, int tile_cfg, socks_stream_t stream);
 
-/* out[t0 + r - 1][j] = step(pts_j, max_a Cm[j][r*P + a] / Cm[j][a]) for r = 1..R-1
- * (kernel_sr_max.py:72-73).  If write_last != 0 also out[T-1][j] = 1_target(pts_j). */
-int socks_srmax_step(const double* Cm, int64_t ldc, int64_t m, int P, int R, int t0, const double* pts,
+/* out[t0 + r - 1][j] = step(pts_j, max_a num_r[j][a] / den[j][a]) for r = 1..R-1 (kernel_sr_max.py:72-73).
+ * Den == NULL: Cm = [den | num_1 .. num_{R-1}] (column blocks of P);  Den != NULL: Cm = [num_1 .. num_{R-1}] and
+ * Den (m x ldden) is the normaliser computed once.  If write_last != 0 also out[T-1][j] = 1_target(pts_j). */
+int socks_srmax_step(const double* Cm, int64_t ldc, const double* Den, int64_t ldden, int64_t m, int P, int R,
+                     int t0, const double* pts,
                      int d, const double* tubes, int problem, int T, double* out, int64_t ldout,
                      int write_last, socks_stream_t stream);
 

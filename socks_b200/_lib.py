@@ -33,10 +33,10 @@ SIGNATURES = {
     "socks_sr_recursion": (_I, [_P, _L, _L, _L, _P, _I, _P, _I, _I, _P, _L, _P, _L, _P, _P]),
     "socks_sr_predict_work_bytes": (_L, [_L, _L]),
     "socks_sr_predict": (_I, [_P, _P, _P, _L, _L, _I, _D, _I, _P, _L, _P, _I, _I, _P, _L, _P, _I, _P]),
-    "socks_srmax_pack": (_I, [_P, _L, _I, _P, _P, _L, _I, _I, _P, _L, _L, _P]),
+    "socks_srmax_pack": (_I, [_P, _L, _I, _P, _P, _L, _I, _I, _I, _P, _L, _L, _P]),
     "socks_gemm_tn": (_I, [_P, _L, _P, _L, _P, _L, _L, _L, _L, _P]),
     "socks_gemm_f64": (_I, [_I, _I, _P, _L, _P, _L, _P, _L, _L, _L, _L, _D, _D, _I, _I, _I, _P]),
-    "socks_srmax_step": (_I, [_P, _L, _L, _I, _I, _I, _P, _I, _P, _I, _I, _P, _L, _I, _P]),
+    "socks_srmax_step": (_I, [_P, _L, _P, _L, _L, _I, _I, _I, _P, _I, _P, _I, _I, _P, _L, _I, _P]),
     "socks_scale_pack": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _L, _P]),
     "socks_rowmin_masked": (_I, [_P, _L, _L, _I, _I, _P, _P, _P]),
     "socks_gemv_t": (_I, [_P, _L, _L, _L, _P, _L, _I, _P, _L, _P, _P]),

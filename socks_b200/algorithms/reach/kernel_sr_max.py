@@ -97,20 +97,24 @@ class KernelMaximalSR:
         gram_dev(Xd, Yd, self._spec.params_for(Xd, Yd), out=Kmat, ld=npad)
         logger.debug("Computing value functions.")
         vf = dv.empty(max(T, 1), n)
-        ldbm = -(-2 * P // 128) * 128
+        ldbm = -(-P // 128) * 128
         Bm = dv.empty(npad, ldbm)
         Cm = dv.empty(npad, ldbm)
+        Den = dv.empty(npad, ldbm)
         st = dv.stream()
         prob = PROBLEM_CODE[self.problem]
         # vf[T-1] = 1_target(Y) first (kernel_sr_max.py:59): the first pack below reads it
-        _lib.call("socks_srmax_step", dv.ptr(Cm), ldbm, n, P, 1, 0, dv.ptr(Yd), d, dv.ptr(self._tubes), prob, T,
+        _lib.call("socks_srmax_step", dv.ptr(Cm), ldbm, 0, 0, n, P, 1, 0, dv.ptr(Yd), d, dv.ptr(self._tubes), prob, T,
                   dv.ptr(vf), n, 1, st)
+        if T > 1:  # the normaliser sum_i w_i C_ij CUA_ik does not depend on t: one GEMM for all steps
+            _lib.call("socks_srmax_pack", dv.ptr(CUA), n, P, dv.ptr(w), 0, n, 0, 0, 1, dv.ptr(Bm), npad, ldbm, st)
+            _lib.call("socks_gemm_tn", dv.ptr(Kmat), npad, dv.ptr(Bm), ldbm, dv.ptr(Den), ldbm, npad, ldbm, npad, st)
         for t in range(T - 2, -1, -1):
-            # rows: r = 0 -> w (normaliser), r = 1 -> vf[t+1] * w          (kernel_sr_max.py:65-72)
-            _lib.call("socks_srmax_pack", dv.ptr(CUA), n, P, dv.ptr(w), dv.ptr(vf), n, t, 2, dv.ptr(Bm), npad, ldbm, st)
+            # numerator row: vf[t+1] * w                                   (kernel_sr_max.py:65-72)
+            _lib.call("socks_srmax_pack", dv.ptr(CUA), n, P, dv.ptr(w), dv.ptr(vf), n, t, 1, 1, dv.ptr(Bm), npad, ldbm, st)
             _lib.call("socks_gemm_tn", dv.ptr(Kmat), npad, dv.ptr(Bm), ldbm, dv.ptr(Cm), ldbm, npad, ldbm, npad, st)
-            _lib.call("socks_srmax_step", dv.ptr(Cm), ldbm, n, P, 2, t, dv.ptr(Yd), d, dv.ptr(self._tubes), prob, T,
-                      dv.ptr(vf), n, 0, st)
+            _lib.call("socks_srmax_step", dv.ptr(Cm), ldbm, dv.ptr(Den), ldbm, n, P, 2, t, dv.ptr(Yd), d,
+                      dv.ptr(self._tubes), prob, T, dv.ptr(vf), n, 0, st)
         self._vf = vf[:T]
         self._vf_host = None
         return self
@@ -134,7 +138,7 @@ class KernelMaximalSR:
         R = Th
         ldbm = -(-R * P // 128) * 128
         Bm = dv.empty(npad, ldbm)
-        _lib.call("socks_srmax_pack", dv.ptr(self._CUA), n, P, dv.ptr(self._w), dv.ptr(self._vf), n, 0, R, dv.ptr(Bm),
+        _lib.call("socks_srmax_pack", dv.ptr(self._CUA), n, P, dv.ptr(self._w), dv.ptr(self._vf), n, 0, 0, R, dv.ptr(Bm),
                   npad, ldbm, st)
         mc = min(self.predict_chunk, -(-m // 128) * 128)
         Kmat = dv.zeros(npad, mc)
@@ -146,8 +150,8 @@ class KernelMaximalSR:
             p = pts[s:s + cnt]
             gram_dev(self._Xd, p, kparams, out=Kmat, ld=mc)
             _lib.call("socks_gemm_tn", dv.ptr(Kmat), mc, dv.ptr(Bm), ldbm, dv.ptr(Cm), ldbm, mc, ldbm, npad, st)
-            _lib.call("socks_srmax_step", dv.ptr(Cm), ldbm, cnt, P, R, 0, dv.ptr(p), d, dv.ptr(self._tubes), prob, Th,
-                      dv.ptr(out[:, s:]), out.stride(0), 1, st)
+            _lib.call("socks_srmax_step", dv.ptr(Cm), ldbm, 0, 0, cnt, P, R, 0, dv.ptr(p), d, dv.ptr(self._tubes), prob,
+                      Th, dv.ptr(out[:, s:]), out.stride(0), 1, st)
         return out
 
     @property

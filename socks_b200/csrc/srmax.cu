@@ -14,14 +14,14 @@
 namespace socks {
 
 __global__ void srmax_pack_kernel(const double* __restrict__ CUA, int64_t n, int P, const double* __restrict__ w,
-                                  const double* __restrict__ vf, int64_t ldvf, int t0, int R, double* __restrict__ Bm,
-                                  int64_t np, int64_t ldbm) {
+                                  const double* __restrict__ vf, int64_t ldvf, int t0, int first_row, int R,
+                                  double* __restrict__ Bm, int64_t np, int64_t ldbm) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t i = blockIdx.y;
     if (c >= ldbm) return;
     double v = 0.0;
     if (i < n && c < (int64_t)R * P) {
-        const int r = (int)(c / P), a = (int)(c % P);
+        const int r = first_row + (int)(c / P), a = (int)(c % P);
         const double coef = (r == 0) ? w[i] : vf[(int64_t)(t0 + r) * ldvf + i] * w[i];
         v = coef * CUA[i * P + a];
     }
@@ -29,18 +29,21 @@ __global__ void srmax_pack_kernel(const double* __restrict__ CUA, int64_t n, int
 }
 
 // one warp per point: VX_r = max_a num_r[a] / den[a] (np.max semantics: NaN propagates), then the step.
-__global__ void srmax_step_kernel(const double* __restrict__ Cm, int64_t ldc, int64_t m, int P, int R, int t0,
-                                  const double* __restrict__ pts, int d, const double* __restrict__ tubes, int problem,
-                                  int T, double* __restrict__ out, int64_t ldout, int write_last) {
+__global__ void srmax_step_kernel(const double* __restrict__ Cm, int64_t ldc, const double* __restrict__ Den,
+                                  int64_t ldden, int64_t m, int P, int R, int t0, const double* __restrict__ pts, int d,
+                                  const double* __restrict__ tubes, int problem, int T, double* __restrict__ out,
+                                  int64_t ldout, int write_last) {
     const int lane = threadIdx.x & 31;
     const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (j >= m) return;
-    const double* row = Cm + j * ldc;
+    // Den == NULL: Cm holds [den | num_1 .. num_{R-1}];  else Cm holds [num_1 .. num_{R-1}] and Den the normaliser
+    const double* den = Den ? Den + j * ldden : Cm + j * ldc;
+    const double* row = Den ? Cm + j * ldc - P : Cm + j * ldc;
     for (int r = 1; r < R; ++r) {
         double best = -INFINITY;
         bool nan = false;
         for (int a = lane; a < P; a += 32) {
-            const double v = row[(int64_t)r * P + a] / row[a];
+            const double v = row[(int64_t)r * P + a] / den[a];
             nan = nan || (v != v);
             best = fmax(best, v);
         }
@@ -142,22 +145,24 @@ extern "C" int socks_rowmin_masked(const double* Cm, int64_t ldc, int64_t m, int
 }
 
 extern "C" int socks_srmax_pack(const double* CUA, int64_t n, int P, const double* w, const double* vf, int64_t ldvf,
-                                int t0, int R, double* Bm, int64_t np, int64_t ldbm, socks_stream_t stream) {
+                                int t0, int first_row, int R, double* Bm, int64_t np, int64_t ldbm,
+                                socks_stream_t stream) {
     SOCKS_CHECK_ARG(CUA != nullptr, 1);
     SOCKS_CHECK_ARG(n >= 1, 2);
     SOCKS_CHECK_ARG(P >= 1, 3);
     SOCKS_CHECK_ARG(w != nullptr, 4);
-    SOCKS_CHECK_ARG(R >= 1 && (R == 1 || vf != nullptr), 8);
-    SOCKS_CHECK_ARG(Bm != nullptr, 9);
-    SOCKS_CHECK_ARG(np >= n && np <= 65535 * 16, 10);
-    SOCKS_CHECK_ARG(ldbm >= (int64_t)R * P && ldbm % 2 == 0, 11);
+    SOCKS_CHECK_ARG(first_row >= 0, 8);
+    SOCKS_CHECK_ARG(R >= 1 && (first_row + R == 1 || vf != nullptr), 9);
+    SOCKS_CHECK_ARG(Bm != nullptr, 10);
+    SOCKS_CHECK_ARG(np >= n && np <= 65535 * 16, 11);
+    SOCKS_CHECK_ARG(ldbm >= (int64_t)R * P && ldbm % 2 == 0, 12);
     cudaStream_t st = (cudaStream_t)stream;
     for (int64_t r0 = 0; r0 < np; r0 += 65535) {
         const int64_t rows = (np - r0 < 65535) ? (np - r0) : 65535;
         dim3 grid((unsigned)ceil_div(ldbm, 256), (unsigned)rows);
         // shift the row window: kernel indexes rows by blockIdx.y, so offset the row-indexed pointers
         srmax_pack_kernel<<<grid, 256, 0, st>>>(CUA + r0 * P, n - r0 > 0 ? n - r0 : 0, P, w + r0, vf ? vf + r0 : vf,
-                                                ldvf, t0, R, Bm + r0 * ldbm, np - r0, ldbm);
+                                                ldvf, t0, first_row, R, Bm + r0 * ldbm, np - r0, ldbm);
     }
     SOCKS_CHECK_LAUNCH();
     return SOCKS_OK;
@@ -213,21 +218,22 @@ extern "C" int socks_gemm_f64(int transa, int transb, const double* A, int64_t l
     return SOCKS_OK;
 }
 
-extern "C" int socks_srmax_step(const double* Cm, int64_t ldc, int64_t m, int P, int R, int t0, const double* pts,
-                                int d, const double* tubes, int problem, int T, double* out, int64_t ldout,
-                                int write_last, socks_stream_t stream) {
+extern "C" int socks_srmax_step(const double* Cm, int64_t ldc, const double* Den, int64_t ldden, int64_t m, int P,
+                                int R, int t0, const double* pts, int d, const double* tubes, int problem, int T,
+                                double* out, int64_t ldout, int write_last, socks_stream_t stream) {
     SOCKS_CHECK_ARG(Cm != nullptr, 1);
-    SOCKS_CHECK_ARG(m >= 1, 3);
-    SOCKS_CHECK_ARG(P >= 1, 4);
-    SOCKS_CHECK_ARG(R >= 1 && ldc >= (int64_t)R * P, 5);
-    SOCKS_CHECK_ARG(pts != nullptr, 7);
-    SOCKS_CHECK_ARG(d >= 1 && d <= SOCKS_MAX_DIM, 8);
-    SOCKS_CHECK_ARG(tubes != nullptr, 9);
-    SOCKS_CHECK_ARG(problem == SOCKS_PROBLEM_THT || problem == SOCKS_PROBLEM_FHT, 10);
-    SOCKS_CHECK_ARG(T >= 1 && t0 >= 0 && t0 + R - 1 <= T - 1, 11);
-    SOCKS_CHECK_ARG(out != nullptr && ldout >= m, 12);
-    srmax_step_kernel<<<(unsigned)ceil_div(m, 8), 256, 0, (cudaStream_t)stream>>>(Cm, ldc, m, P, R, t0, pts, d, tubes,
-                                                                                  problem, T, out, ldout, write_last);
+    SOCKS_CHECK_ARG(Den == nullptr || ldden >= P, 4);
+    SOCKS_CHECK_ARG(m >= 1, 5);
+    SOCKS_CHECK_ARG(P >= 1, 6);
+    SOCKS_CHECK_ARG(R >= 1 && ldc >= (int64_t)(Den ? R - 1 : R) * P, 7);
+    SOCKS_CHECK_ARG(pts != nullptr, 9);
+    SOCKS_CHECK_ARG(d >= 1 && d <= SOCKS_MAX_DIM, 10);
+    SOCKS_CHECK_ARG(tubes != nullptr, 11);
+    SOCKS_CHECK_ARG(problem == SOCKS_PROBLEM_THT || problem == SOCKS_PROBLEM_FHT, 12);
+    SOCKS_CHECK_ARG(T >= 1 && t0 >= 0 && t0 + R - 1 <= T - 1, 13);
+    SOCKS_CHECK_ARG(out != nullptr && ldout >= m, 14);
+    srmax_step_kernel<<<(unsigned)ceil_div(m, 8), 256, 0, (cudaStream_t)stream>>>(
+        Cm, ldc, Den, ldden, m, P, R, t0, pts, d, tubes, problem, T, out, ldout, write_last);
     SOCKS_CHECK_LAUNCH();
     return SOCKS_OK;
 }
