@@ -240,6 +240,38 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// Runtime-d fallback (8 < d <= SOCKS_MAX_DIM): one point per thread, coordinates through L1, samples and
+// coefficients straight from global memory (warp-uniform addresses).  Correctness path for high-dimensional
+// states; the benchmarked dimensions (d <= 8) use the templated kernels above.
+__global__ void __launch_bounds__(128)
+    sr_predict_generic_kernel(const double* __restrict__ X, const double* __restrict__ coef, int64_t n, int d,
+                              const double* __restrict__ pts, int64_t m, double kmul, const double* __restrict__ tubes,
+                              int problem, int t0, int R, double* __restrict__ out, int64_t ldout) {
+    const int64_t j = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (j >= m) return;
+    const double* p = pts + j * d;
+    double acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        double d2 = 0.0;
+        for (int k = 0; k < d; ++k) {
+            const double t = p[k] - __ldg(X + i * d + k);
+            d2 = fma(t, t, d2);
+        }
+        const double kv = exp(d2 * kmul);
+        const double* c = coef + i * SR_CP;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc[r] = fma(__ldg(c + r), kv, acc[r]);
+    }
+#pragma unroll
+    for (int r = 1; r < 16; ++r)
+        if (r < R) {
+            const int t = t0 + r - 1;
+            out[(int64_t)t * ldout + j] = sr_step(p, tubes + (int64_t)t * 4 * d, d, problem, acc[r] / acc[0]);
+        }
+}
+
 // q[r][i] = z[r][i] * exp(-gamma |X_i - s|^2)     (kernel_control_fwd.py:220-222: CXT * ...)
 __global__ void fwd_weights_kernel(const double* __restrict__ X, int64_t n, int d, double neg_gamma,
                                    const double* __restrict__ state, const double* __restrict__ z, int64_t ldz, int R,
@@ -368,7 +400,7 @@ extern "C" int socks_sr_predict(const double* X, const double* w, const double* 
     SOCKS_CHECK_ARG(w != nullptr, 2);
     SOCKS_CHECK_ARG(vf != nullptr && ldvf >= n, 3);
     SOCKS_CHECK_ARG(n >= 1, 5);
-    SOCKS_CHECK_ARG(d >= 1 && d <= 8, 6);
+    SOCKS_CHECK_ARG(d >= 1 && d <= SOCKS_MAX_DIM, 6);
     SOCKS_CHECK_ARG(scale == scale && (!divide || scale != 0.0), 7);
     SOCKS_CHECK_ARG(m >= 0, 10);
     SOCKS_CHECK_ARG(tubes != nullptr, 11);
@@ -402,6 +434,9 @@ extern "C" int socks_sr_predict(const double* X, const double* w, const double* 
         switch (d) {
             SOCKS_PRED_CASE(1) SOCKS_PRED_CASE(2) SOCKS_PRED_CASE(3) SOCKS_PRED_CASE(4)
             SOCKS_PRED_CASE(5) SOCKS_PRED_CASE(6) SOCKS_PRED_CASE(7) SOCKS_PRED_CASE(8)
+            default:
+                sr_predict_generic_kernel<<<(unsigned)ceil_div(m, 128), 128, 0, st>>>(X, coef, n, d, pts, m, kmul, tubes,
+                                                                                     problem, t0, R, out, ldout);
         }
 #undef SOCKS_PRED_CASE
         SOCKS_CHECK_LAUNCH();

@@ -25,6 +25,7 @@ CASES = [
     (1000, 333, 7, 6, "FHT", 1.0, 1.0),
     (2049, 300, 2, 31, "FHT", 0.1, 1e-4),   # crosses the 2048-sample split and needs three predict launches
     (2200, 257, 8, 3, "THT", 1.2, 1e-3),
+    (150, 90, 11, 4, "FHT", 1.5, 1e-2),    # d > 8: runtime-dimension kernels
 ]
 
 
