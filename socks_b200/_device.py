@@ -1,5 +1,5 @@
 """Device plumbing: torch is used ONLY to own device memory and streams (no torch math on the path)."""
-import sys
+import weakref
 
 import numpy as np
 import torch
@@ -62,31 +62,52 @@ def even(n):
     return int(n) + (int(n) & 1)
 
 
+class _Lease:
+    """Owner object of one result array: numpy keeps it (as `.base`) for as long as the array or any view of it
+    is alive, so a dead weak reference to the lease means the caller has dropped the result."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self.__array_interface__ = {"shape": tuple(tensor.shape), "typestr": "<f8",
+                                    "data": (tensor.data_ptr(), False), "version": 3}
+
+
 class HostPool:
     """Pinned host result buffers, reused only when the caller has dropped the previous result.
 
-    `predict()` returns `tensor.numpy()`, whose `.base` keeps the pinned tensor alive; a pooled tensor whose
-    refcount shows no outside holder is free to be overwritten, otherwise a new one is allocated.  This keeps
-    the reference's "fresh ndarray per call" semantics without paying a 30 MB page-faulting allocation and a
-    pageable device-to-host copy on every call."""
+    `predict()` hands out `numpy.asarray(lease)`: a zero-copy ndarray on the pinned buffer whose `.base` is a
+    lease object.  A buffer is free again once its lease has been garbage collected (every array and view the
+    caller held is gone); otherwise a new buffer is allocated.  This keeps the reference's "fresh ndarray per
+    call" semantics without a 30 MB page-faulting allocation and a pageable device-to-host copy per call."""
 
     def __init__(self, max_per_shape=3, max_shapes=8):
         self._bufs, self._max, self._max_shapes = {}, max_per_shape, max_shapes
 
     def get(self, rows, cols):
+        """-> (pinned tensor, finish) where finish() returns the ndarray to hand to the caller."""
         key = (int(rows), int(cols))
         lst = self._bufs.get(key)
         if lst is None:
             if len(self._bufs) >= self._max_shapes:
                 self._bufs.pop(next(iter(self._bufs)))
             lst = self._bufs[key] = []
-        for i in range(len(lst)):
-            if sys.getrefcount(lst[i]) <= 2:  # the list's reference + getrefcount's argument
-                return lst[i]
-        t = torch.empty(key, dtype=F64, pin_memory=True)
-        if len(lst) < self._max:
-            lst.append(t)
-        return t
+        entry = None
+        for e in lst:
+            if e["lease"] is None or e["lease"]() is None:
+                entry = e
+                break
+        if entry is None:
+            entry = {"tensor": torch.empty(key, dtype=F64, pin_memory=True), "lease": None}
+            if len(lst) < self._max:
+                lst.append(entry)
+        tensor = entry["tensor"]
+
+        def finish():
+            lease = _Lease(tensor)
+            entry["lease"] = weakref.ref(lease)
+            return np.asarray(lease)
+
+        return tensor, finish
 
 
 host_pool = HostPool()

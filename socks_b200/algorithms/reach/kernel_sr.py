@@ -137,7 +137,7 @@ class KernelSR:
 
         src = torch.from_numpy(pts_h)
         pts = src.to(dv.device(), non_blocking=src.is_pinned())
-        host = dv.host_pool.get(Th, m)
+        host, finish = dv.host_pool.get(Th, m)
         out = self._cached("out", (Th, m))
         nchunks = self.predict_chunks if m >= 65536 else 1
         chunk = -(-(-(-m // nchunks)) // 256) * 256
@@ -152,7 +152,7 @@ class KernelSR:
                 for t in range(Th):  # row segments are contiguous on both sides: plain async memcpys
                     host[t, s:e].copy_(out[t, s:e], non_blocking=True)
         cs.synchronize()
-        return host.numpy()
+        return finish()
 
     def predict_dev(self, pts):
         """Device in, device out: (m, d) test points -> (time_horizon, m) safety probabilities."""

@@ -57,6 +57,26 @@ def test_kernel_sr_golden(name, variant):
         assert np.array_equal(out2, out)
 
 
+def test_predict_results_are_not_aliased():
+    """predict() reuses pinned result buffers only after the caller dropped the previous result."""
+    KernelSR, _, _, _, _, rbf = _api()
+    X, U, Y = syn.integrator_sample(300, seed=41)
+    ct, tt = syn.integrator_tubes(4)
+    alg = KernelSR(time_horizon=4, constraint_tube=ct, target_tube=tt, problem="FHT", kernel_fn=partial(rbf, sigma=0.2))
+    alg.fit(syn.as_sample(X, U, Y))
+    p1, p2 = syn.uniform_points(500, seed=42), syn.uniform_points(500, seed=43)
+    a = alg.predict(p1)
+    a_copy = a.copy()
+    b = alg.predict(p2)              # same shape while `a` is still referenced: must not overwrite it
+    assert np.array_equal(a, a_copy) and not np.array_equal(a, b)
+    view = b[1:]                     # a view keeps the buffer leased as well
+    b_copy = b.copy()
+    del b
+    for _ in range(4):
+        c = alg.predict(p1)
+    assert np.array_equal(view, b_copy[1:]) and np.array_equal(c, a_copy)
+
+
 def test_kernel_sr_sklearn_kernel_and_defaults():
     """The reference's benchmarks pass sklearn's rbf_kernel(gamma=1/(2 sigma^2)) (benchmarks/kernel_sr/
     baseline.py:134-144); defaults sigma=0.1, lambda=1, THT (kernel_sr.py:226-230)."""

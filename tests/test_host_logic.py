@@ -108,3 +108,38 @@ def test_synthetic_is_seeded_and_closed_form():
     Xg, Ug, Yg = syn.integrator_sample(1000, dim=2, seed=0)
     assert np.array_equal(Xg, g["X"]) and np.array_equal(Yg, g["Y"])
     assert np.array_equal(syn.grid_points(50, 2), g["pts"])
+
+
+def test_host_pool_never_reuses_a_live_result(monkeypatch):
+    """The pinned result pool of predict(): a buffer is reused only after every array/view handed out is gone."""
+    import gc
+
+    import torch
+
+    from socks_b200 import _device as dv
+
+    orig = torch.empty
+
+    def unpinned_empty(*a, **k):  # no CUDA here: drop pin_memory
+        k.pop("pin_memory", None)
+        return orig(*a, **k)
+
+    monkeypatch.setattr(torch, "empty", unpinned_empty)
+    pool = dv.HostPool()
+    t1, f1 = pool.get(3, 4)
+    t1.fill_(1.0)
+    a = f1()
+    t2, f2 = pool.get(3, 4)
+    assert t2 is not t1
+    t2.fill_(2.0)
+    b = f2()
+    assert a[0, 0] == 1.0 and b[0, 0] == 2.0
+    view = a[1:]
+    del a
+    gc.collect()
+    t3, _ = pool.get(3, 4)
+    assert t3 is not t1 and t3 is not t2  # the view still leases buffer 1
+    del view
+    gc.collect()
+    t4, _ = pool.get(3, 4)
+    assert t4 is t1
