@@ -142,9 +142,10 @@ class KernelSR:
         nchunks = self.predict_chunks if m >= 65536 else 1
         chunk = -(-(-(-m // nchunks)) // 256) * 256
         cs = dv.copy_stream()
+        kparams = self._spec.params_for(self._Xd, pts)  # once for the whole call (sigma=None: median over K(X,T))
         for s in range(0, m, chunk):
             e = min(m, s + chunk)
-            self._predict_into(pts[s:e], out[:, s:e])
+            self._predict_into(pts[s:e], out[:, s:e], kparams)
             ev = torch.cuda.Event()
             ev.record()
             with torch.cuda.stream(cs):
@@ -173,14 +174,16 @@ class KernelSR:
 
     max_launch_points = 1 << 20  # bounds the per-split partial-sum workspace (16 * splits * 8 B per point)
 
-    def _predict_into(self, pts, out):
+    def _predict_into(self, pts, out, kparams=None):
         m = pts.shape[0]
+        if kparams is None:
+            kparams = self._spec.params_for(self._Xd, pts)
         if m > self.max_launch_points:
             for s in range(0, m, self.max_launch_points):
                 e = min(m, s + self.max_launch_points)
-                self._predict_into(pts[s:e], out[:, s:e])
+                self._predict_into(pts[s:e], out[:, s:e], kparams)
             return
-        scale, divide = self._spec.params_for(self._Xd, pts)
+        scale, divide = kparams
         nbytes = _lib.load().socks_sr_predict_work_bytes(self._n, m)
         work = self._cached("work", ((nbytes + 7) // 8 + 2,))
         _lib.call("socks_sr_predict", dv.ptr(self._Xd), dv.ptr(self._w), dv.ptr(self._vf), self._n, self._n, self._d,

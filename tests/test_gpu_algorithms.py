@@ -57,6 +57,21 @@ def test_kernel_sr_golden(name, variant):
         assert np.array_equal(out2, out)
 
 
+def test_kernel_sr_median_heuristic_bandwidth():
+    """kernel_fn=partial(rbf_kernel) with sigma=None: every kernel evaluation uses the median of ITS squared-distance
+    matrix (metrics.py:130-131), including K(X, T) over the whole test set."""
+    KernelSR, _, _, _, _, rbf = _api()
+    X, U, Y = syn.integrator_sample(200, seed=51)
+    pts = syn.uniform_points(150, seed=52)
+    ct, tt = syn.integrator_tubes(4)
+    alg = KernelSR(time_horizon=4, constraint_tube=ct, target_tube=tt, problem="THT", kernel_fn=partial(rbf),
+                   regularization_param=1e-2)
+    alg.fit(syn.as_sample(X, U, Y))
+    o = orc.KernelSROracle(4, ct, tt, "THT", None, 1e-2).fit(X, U, Y)
+    assert np.max(np.abs(alg.value_functions - o.value_functions)) <= TOL
+    assert np.max(np.abs(alg.predict(pts) - o.predict(pts))) <= TOL
+
+
 def test_predict_results_are_not_aliased():
     """predict() reuses pinned result buffers only after the caller dropped the previous result."""
     KernelSR, _, _, _, _, rbf = _api()
