@@ -37,6 +37,9 @@ extern "C" {
 #define SOCKS_MAX_DIM 32     /* largest state/action dimension accepted by the Gram kernels */
 #define SOCKS_SR_ROWS 16     /* coefficient rows (1 normaliser + 15 time steps) per predict launch */
 
+#define SOCKS_KERNEL_RBF 0   /* exp(|x-y|^2 (*|/) scale), gym_socks/kernel/metrics.py:69-138  */
+#define SOCKS_KERNEL_ABEL 1  /* exp(|x-y|   (*|/) scale), gym_socks/kernel/metrics.py:174-206 */
+
 #define SOCKS_PROBLEM_THT 0  /* gym_socks/algorithms/reach/common.py:42-69 */
 #define SOCKS_PROBLEM_FHT 1  /* gym_socks/algorithms/reach/common.py:8-39  */
 
@@ -54,16 +57,26 @@ int64_t socks_padded_dim(int64_t n);
 int socks_gram_rbf(const double* X, int64_t n, const double* Y, int64_t m, int d, double scale, int divide,
                    const double* rowscale, double* K, int64_t ldk, socks_stream_t stream);
 
-/* D[i*ldd + j] = |X_i - Y_j|^2 (direct differences, metrics.py:127-128); used for the
- * sigma=None median heuristic (metrics.py:130-131). */
+/* Same with the kernel family chosen by `kind` (SOCKS_KERNEL_RBF | SOCKS_KERNEL_ABEL); the Abel kernel
+ * exp(-|x-y| / sigma) (metrics.py:174-206) is what SeparatingKernelClassifier uses (scale = -sigma, divide = 1). */
+int socks_gram_kernel(int kind, const double* X, int64_t n, const double* Y, int64_t m, int d, double scale,
+                      int divide, const double* rowscale, double* K, int64_t ldk, socks_stream_t stream);
+
+/* D[i*ldd + j] = |X_i - Y_j|^2 (direct differences, metrics.py:127-128 and euclidean_distance :26-66 with
+ * squared=True); used for the sigma=None median heuristic (metrics.py:130-131).  socks_dist: the square root
+ * (euclidean_distance with squared=False; the Abel kernel's median heuristic, metrics.py:199-200). */
 int socks_sqdist(const double* X, int64_t n, const double* Y, int64_t m, int d, double* D,
                  int64_t ldd, socks_stream_t stream);
+int socks_dist(const double* X, int64_t n, const double* Y, int64_t m, int d, double* D,
+               int64_t ldd, socks_stream_t stream);
 
 /* G = K(Z,Z) + diag_add * I written into the LOWER 128-tiles of the padded np x np buffer
  * (identity in the padding).  Z = X, or [X | U] concatenated for the product Gram
  * K(X,X) * K(U,U) of metrics.py:268-276.  diag_add = lambda * N (metrics.py:278-280). */
 int socks_gram_sym(const double* Z, int64_t n, int d, double scale, int divide, double diag_add, double* G,
                    int64_t ldg, socks_stream_t stream);
+int socks_gram_sym_kernel(int kind, const double* Z, int64_t n, int d, double scale, int divide, double diag_add,
+                          double* G, int64_t ldg, socks_stream_t stream);
 
 /* ---- Regularised solve: gym_socks/kernel/metrics.py:278-280 (inv(K + lambda N I)) ------ */
 
@@ -84,6 +97,11 @@ int socks_trtri(const double* L, int64_t n, int64_t ldl, const double* dinv, dou
 /* w[i] = sum_k M[k][i]^2 = diag(inv(G))[i]  (the only part of W the SR algorithms use:
  * np.einsum("ii,ij->ij", W, CXY), kernel_sr.py:45).  work: socks_reduce_work_bytes(np). */
 int socks_diag_inv(const double* M, int64_t n, int64_t ldm, double* w, double* work, socks_stream_t stream);
+
+/* y[j] = sum_{i<n} Z[i][j]^2 (general n x m matrix).  With Z = inv(L) K(X,T) this is the diagonal of
+ * K^T W K that SeparatingKernelClassifier thresholds (gym_socks/algorithms/reach/separating_kernel.py:88,109).
+ * work: socks_reduce_work_bytes(m). */
+int socks_colsumsq(const double* Z, int64_t n, int64_t m, int64_t ldz, double* y, double* work, socks_stream_t stream);
 
 /* W = M^T M = inv(G), full symmetric np x np (what regularized_inverse returns). */
 int socks_lauum(const double* M, int64_t n, int64_t ldm, double* W, int64_t ldw, socks_stream_t stream);

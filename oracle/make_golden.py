@@ -165,7 +165,29 @@ def bwd_case(name, n, sigma, lam, T, seed, constrained):
          cond=np.linalg.cond(np.linalg.inv(pol.W)))
 
 
+def separating_case(name, n, m, sigma, lam, seed):
+    from gym_socks.kernel.metrics import abel_kernel, euclidean_distance
+    from gym_socks.algorithms.reach.separating_kernel import SeparatingKernelClassifier
+
+    rng = np.random.default_rng(seed)
+    ang = rng.uniform(0, 2 * np.pi, n)
+    rad = 0.6 + 0.05 * rng.standard_normal(n)
+    X = np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=1)  # a ring: the support to be learned
+    T = rng.uniform(-1, 1, (m, 2))
+    clf = SeparatingKernelClassifier(kernel_fn=partial(abel_kernel, sigma=sigma), regularization_param=lam)
+    clf.fit(X)
+    K = abel_kernel(clf.X, T, sigma=sigma)
+    C = np.diagonal((1 / len(X)) * K.T @ clf.W @ K)
+    save(name, X=X, T=T, sigma=sigma, lam=lam, tau=clf.tau, C=C, labels=clf.predict(T),
+         K_abel=abel_kernel(X[:40], T[:30], sigma=sigma), K_abel_median=abel_kernel(X[:40]),
+         D=euclidean_distance(X[:40], T[:30]), D2=euclidean_distance(X[:40], T[:30], squared=True),
+         cond=np.linalg.cond(np.linalg.inv(clf.W)))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sep":
+        separating_case("separating_ring.npz", 300, 400, 0.25, 1e-3, seed=31)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "bwd":
         bwd_case("bwd_unconstrained.npz", 300, 1.0, 1e-3, 6, seed=21, constrained=False)
         bwd_case("bwd_constrained.npz", 260, 1.5, 1e-3, 5, seed=22, constrained=True)

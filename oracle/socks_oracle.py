@@ -31,6 +31,8 @@ __all__ = [
     "KernelControlFwdOracle",
     "KernelControlBwdOracle",
     "heuristic_solution",
+    "abel_kernel",
+    "SeparatingKernelOracle",
 ]
 
 
@@ -318,3 +320,45 @@ class KernelControlBwdOracle:
     def __call__(self, time=0, state=None):
         C, D = self.scores(time, state)
         return np.array(self.A[heuristic_solution(C, D)], dtype=np.float32)
+
+
+# --------------------------------------------------------------------------- abel kernel / separating classifier
+def abel_kernel(X, Y=None, sigma=None):
+    """exp(-|x - y| / sigma); sigma=None uses the median of the (unsquared) distances
+    (`gym_socks/kernel/metrics.py:174-206`, distances from `euclidean_distance` `:26-66`)."""
+    if Y is None:
+        Y = X
+    K = np.sqrt(sq_dist(X, Y))
+    if sigma is None:
+        sigma = np.median(K)
+    else:
+        assert sigma > 0
+    K /= -sigma
+    np.exp(K, K)
+    return K
+
+
+class SeparatingKernelOracle:
+    """`SeparatingKernelClassifier.fit/predict` (`gym_socks/algorithms/reach/separating_kernel.py:67-111`):
+    W = inv(K + lambda N I) with the Abel kernel, tau = 1 - min diag(K^T W K / n), predict diag(K_T^T W K_T / n) >= 1 - tau."""
+
+    def __init__(self, sigma=0.1, regularization_param=1):
+        self.sigma, self.lam = sigma, regularization_param
+
+    def fit(self, X):
+        X = np.asarray(X, dtype=np.float64)
+        self.X = X
+        n = len(X)
+        K = abel_kernel(X, X, self.sigma)
+        G = K.copy()
+        G[np.diag_indices(n)] += self.lam * n
+        self.W = np.linalg.inv(G)
+        self.tau = 1 - np.min(np.diagonal((1 / n) * K.T @ self.W @ K))
+        return self
+
+    def scores(self, T):
+        K = abel_kernel(self.X, np.asarray(T, dtype=np.float64), self.sigma)
+        return np.einsum("ij,ij->j", K, self.W @ K) / len(self.X)
+
+    def predict(self, T):
+        return self.scores(T) >= 1 - self.tau

@@ -21,6 +21,10 @@ SIGNATURES = {
     "socks_last_error": (c_char_p, []),
     "socks_padded_dim": (_L, [_L]),
     "socks_gram_rbf": (_I, [_P, _L, _P, _L, _I, _D, _I, _P, _P, _L, _P]),
+    "socks_gram_kernel": (_I, [_I, _P, _L, _P, _L, _I, _D, _I, _P, _P, _L, _P]),
+    "socks_dist": (_I, [_P, _L, _P, _L, _I, _P, _L, _P]),
+    "socks_gram_sym_kernel": (_I, [_I, _P, _L, _I, _D, _I, _D, _P, _L, _P]),
+    "socks_colsumsq": (_I, [_P, _L, _L, _L, _P, _P, _P]),
     "socks_sqdist": (_I, [_P, _L, _P, _L, _I, _P, _L, _P]),
     "socks_gram_sym": (_I, [_P, _L, _I, _D, _I, _D, _P, _L, _P]),
     "socks_potrf_work_bytes": (_L, [_L]),

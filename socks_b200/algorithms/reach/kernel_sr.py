@@ -52,6 +52,9 @@ class KernelSR:
     # -- validation: same order and exception types as kernel_sr.py:224-264
     def _validate_params(self, S):
         self._spec = resolve_kernel(self.kernel_fn, default_sigma=0.1)
+        if self._spec.kind != 0:
+            raise NotImplementedError("KernelSR's fused predict kernel evaluates the RBF kernel; abel_kernel is "
+                                      "supported by rbf-free paths only (SeparatingKernelClassifier)")
         if self.regularization_param is None:
             self.regularization_param = 1
         if self.time_horizon is None:
@@ -109,7 +112,7 @@ class KernelSR:
         self._tubes = pack_tubes(self.constraint_tube, self.target_tube, T, d)
         logger.debug("Computing covariance matrix.")
         ldb = dv.even(n)
-        B = gram_dev(Xd, Yd, self._spec.params_for(Xd, Yd), rowscale=w, ld=ldb)  # un-normalised beta, kernel_sr.py:45
+        B = gram_dev(Xd, Yd, self._spec.params_for(Xd, Yd), kind=self._spec.kind, rowscale=w, ld=ldb)  # un-normalised beta, kernel_sr.py:45
         logger.debug("Computing value functions.")
         vf = dv.empty(max(T, 1), n)
         lib = _lib.load()

@@ -504,6 +504,24 @@ extern "C" int socks_diag_inv(const double* M, int64_t n, int64_t ldm, double* w
     return SOCKS_OK;
 }
 
+// y[j] = sum_{i < n} Z[i][j]^2 for a general (non-triangular) n x m matrix.
+extern "C" int socks_colsumsq(const double* Zm, int64_t n, int64_t m, int64_t ldz, double* y, double* work,
+                              socks_stream_t stream) {
+    SOCKS_CHECK_ARG(Zm != nullptr, 1);
+    SOCKS_CHECK_ARG(n >= 1, 2);
+    SOCKS_CHECK_ARG(m >= 1, 3);
+    SOCKS_CHECK_ARG(ldz >= m, 4);
+    SOCKS_CHECK_ARG(y != nullptr, 5);
+    SOCKS_CHECK_ARG(work != nullptr, 6);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int splits = colreduce_launch<true>(Zm, n, m, ldz, nullptr, 0, 1, work, /*tri=*/0, st);
+    SOCKS_CHECK_LAUNCH();
+    colreduce_finish_kernel<<<dim3((unsigned)ceil_div(m, 256), 1), 256, 0, st>>>(work, colreduce_ldpart(m), splits, m,
+                                                                                y, m);
+    SOCKS_CHECK_LAUNCH();
+    return SOCKS_OK;
+}
+
 extern "C" int socks_lauum(const double* M, int64_t n, int64_t ldm, double* W, int64_t ldw, socks_stream_t stream) {
     int rc = check_square(M, n, ldm, 1);
     if (rc) return rc;

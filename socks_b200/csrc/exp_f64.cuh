@@ -237,11 +237,21 @@ __device__ __forceinline__ void exp_scaled_x4(const double (&d2)[4], double (&ou
     for (int i = 0; i < 4; ++i) p[i] = fma(p[i], r[i], P.c1);
 #pragma unroll
     for (int i = 0; i < 4; ++i) p[i] = p[i] * r[i];
+    // results near or below the normal range (x < ~-707) need the two-step scaling: test once for all four
+    const int kmin = min(min(k[0], k[1]), min(k[2], k[3]));
+    if ((kmin >> 8) >= -1020) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double res = fma(T[i], p[i], T[i]);
+            out[i] = __hiloint2double(__double2hiint(res) + ((k[i] >> 8) << 20), __double2loint(res));
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         double res = fma(T[i], p[i], T[i]);
         int e = k[i] >> 8;
-        if (e < -1020) {  // near or below the normal range: rare
+        if (e < -1020) {
             const double x = d2[i] * P.kmul;
             if (!(x >= -800.0)) {
                 out[i] = (x != x) ? x : 0.0;

@@ -42,7 +42,7 @@ __device__ __forceinline__ double rbf_arg(double d2, const KScale& ks) {
 }
 inline KScale make_kscale(double scale, int divide) { return KScale{scale, divide ? 1.0 / scale : 0.0, divide}; }
 
-// MODE 0: rowscale * exp(-gamma d2); MODE 1: d2
+// MODE 0: rowscale * exp(arg(d2)) (RBF); 1: d2; 2: rowscale * exp(arg(sqrt(d2))) (Abel, metrics.py:194-204); 3: sqrt(d2)
 template <int D, int MODE>
 __global__ void __launch_bounds__(GR_TX* GR_TY)
     gram_cross_kernel(const double* __restrict__ X, int64_t n, const double* __restrict__ Y, int64_t m,
@@ -69,7 +69,11 @@ __global__ void __launch_bounds__(GR_TX* GR_TY)
         if (i >= n) break;
         double v0 = sqdist_reg<D>(x[r], y[0]);
         double v1 = sqdist_reg<D>(x[r], y[1]);
-        if (MODE == 0) {
+        if (MODE == 2 || MODE == 3) {
+            v0 = sqrt(v0);
+            v1 = sqrt(v1);
+        }
+        if (MODE == 0 || MODE == 2) {
             double s = rowscale ? __ldg(rowscale + i) : 1.0;
             v0 = exp(rbf_arg(v0, ks));
             v1 = exp(rbf_arg(v1, ks));
@@ -98,7 +102,8 @@ __global__ void gram_cross_generic_kernel(const double* __restrict__ X, int64_t 
         double t = __dsub_rn(__ldg(Y + j * d + k), __ldg(X + i * d + k));
         acc = __dadd_rn(acc, __dmul_rn(t, t));
     }
-    if (MODE == 0) {
+    if (MODE == 2 || MODE == 3) acc = sqrt(acc);
+    if (MODE == 0 || MODE == 2) {
         acc = exp(rbf_arg(acc, ks));
         if (rowscale) acc *= __ldg(rowscale + i);
     }
@@ -106,7 +111,7 @@ __global__ void gram_cross_generic_kernel(const double* __restrict__ X, int64_t 
 }
 
 // Lower 128-tiles of the padded G = K(Z,Z) + diag_add I; identity in the padding.
-template <int D>
+template <int D, bool ABEL>
 __global__ void __launch_bounds__(GR_TX* GR_TY)
     gram_sym_kernel(const double* __restrict__ Z, int64_t n, KScale ks, double diag_add,
                     double* __restrict__ G, int64_t ldg) {
@@ -136,7 +141,8 @@ __global__ void __launch_bounds__(GR_TX* GR_TY)
         for (int c = 0; c < 2; ++c) {
             int64_t j = j0 + c;
             if (i < n && j < n) {
-                v[c] = exp(rbf_arg(sqdist_reg<D>(x[r], y[c]), ks));
+                const double d2 = sqdist_reg<D>(x[r], y[c]);
+                v[c] = exp(rbf_arg(ABEL ? sqrt(d2) : d2, ks));
                 if (i == j) v[c] += diag_add;
             } else {
                 v[c] = (i == j) ? 1.0 : 0.0;
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(GR_TX* GR_TY)
     }
 }
 
-__global__ void gram_sym_generic_kernel(const double* __restrict__ Z, int64_t n, int d, KScale ks,
+__global__ void gram_sym_generic_kernel(const double* __restrict__ Z, int64_t n, int d, KScale ks, int abel,
                                         double diag_add, double* __restrict__ G, int64_t ldg, int64_t np) {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t i = blockIdx.y;
@@ -158,7 +164,7 @@ __global__ void gram_sym_generic_kernel(const double* __restrict__ Z, int64_t n,
             double t = __dsub_rn(__ldg(Z + j * d + k), __ldg(Z + i * d + k));
             acc = __dadd_rn(acc, __dmul_rn(t, t));
         }
-        v = exp(rbf_arg(acc, ks)) + (i == j ? diag_add : 0.0);
+        v = exp(rbf_arg(abel ? sqrt(acc) : acc, ks)) + (i == j ? diag_add : 0.0);
     } else {
         v = (i == j) ? 1.0 : 0.0;
     }
@@ -197,17 +203,31 @@ static int launch_cross(const double* X, int64_t n, const double* Y, int64_t m, 
 
 using namespace socks;
 
-extern "C" int socks_gram_rbf(const double* X, int64_t n, const double* Y, int64_t m, int d, double scale, int divide,
-                              const double* rowscale, double* K, int64_t ldk, socks_stream_t stream) {
-    SOCKS_CHECK_ARG(n >= 0, 2);
-    SOCKS_CHECK_ARG(m >= 0, 4);
-    SOCKS_CHECK_ARG(d >= 1 && d <= SOCKS_MAX_DIM, 5);
-    SOCKS_CHECK_ARG(scale == scale && (!divide || scale != 0.0), 6);
-    SOCKS_CHECK_ARG(ldk >= m, 10);
-    SOCKS_CHECK_ARG((n == 0 || m == 0) || (X && Y && K), 1);
-    launch_cross<0>(X, n, Y, m, d, make_kscale(scale, divide), rowscale, K, ldk, (cudaStream_t)stream);
+static int gram_kernel_impl(int kind, const double* X, int64_t n, const double* Y, int64_t m, int d, double scale,
+                            int divide, const double* rowscale, double* K, int64_t ldk, socks_stream_t stream) {
+    SOCKS_CHECK_ARG(kind == SOCKS_KERNEL_RBF || kind == SOCKS_KERNEL_ABEL, 1);
+    SOCKS_CHECK_ARG(n >= 0, 3);
+    SOCKS_CHECK_ARG(m >= 0, 5);
+    SOCKS_CHECK_ARG(d >= 1 && d <= SOCKS_MAX_DIM, 6);
+    SOCKS_CHECK_ARG(scale == scale && (!divide || scale != 0.0), 7);
+    SOCKS_CHECK_ARG(ldk >= m, 11);
+    SOCKS_CHECK_ARG((n == 0 || m == 0) || (X && Y && K), 2);
+    const KScale ks = make_kscale(scale, divide);
+    if (kind == SOCKS_KERNEL_RBF) launch_cross<0>(X, n, Y, m, d, ks, rowscale, K, ldk, (cudaStream_t)stream);
+    else launch_cross<2>(X, n, Y, m, d, ks, rowscale, K, ldk, (cudaStream_t)stream);
     SOCKS_CHECK_LAUNCH();
     return SOCKS_OK;
+}
+
+extern "C" int socks_gram_kernel(int kind, const double* X, int64_t n, const double* Y, int64_t m, int d, double scale,
+                                 int divide, const double* rowscale, double* K, int64_t ldk, socks_stream_t stream) {
+    return gram_kernel_impl(kind, X, n, Y, m, d, scale, divide, rowscale, K, ldk, stream);
+}
+
+extern "C" int socks_gram_rbf(const double* X, int64_t n, const double* Y, int64_t m, int d, double scale, int divide,
+                              const double* rowscale, double* K, int64_t ldk, socks_stream_t stream) {
+    int rc = gram_kernel_impl(SOCKS_KERNEL_RBF, X, n, Y, m, d, scale, divide, rowscale, K, ldk, stream);
+    return rc < -1 ? rc + 1 : rc;  // argument positions of this entry point are shifted by one
 }
 
 extern "C" int socks_sqdist(const double* X, int64_t n, const double* Y, int64_t m, int d, double* D, int64_t ldd,
@@ -222,31 +242,59 @@ extern "C" int socks_sqdist(const double* X, int64_t n, const double* Y, int64_t
     return SOCKS_OK;
 }
 
-extern "C" int socks_gram_sym(const double* Z, int64_t n, int d, double scale, int divide, double diag_add, double* G,
-                              int64_t ldg, socks_stream_t stream) {
-    SOCKS_CHECK_ARG(Z != nullptr, 1);
-    SOCKS_CHECK_ARG(n >= 1, 2);
-    SOCKS_CHECK_ARG(d >= 1 && d <= SOCKS_MAX_DIM, 3);
+extern "C" int socks_dist(const double* X, int64_t n, const double* Y, int64_t m, int d, double* D, int64_t ldd,
+                          socks_stream_t stream) {
+    SOCKS_CHECK_ARG(n >= 0, 2);
+    SOCKS_CHECK_ARG(m >= 0, 4);
+    SOCKS_CHECK_ARG(d >= 1 && d <= SOCKS_MAX_DIM, 5);
+    SOCKS_CHECK_ARG(ldd >= m, 7);
+    SOCKS_CHECK_ARG((n == 0 || m == 0) || (X && Y && D), 1);
+    launch_cross<3>(X, n, Y, m, d, make_kscale(0.0, 0), nullptr, D, ldd, (cudaStream_t)stream);
+    SOCKS_CHECK_LAUNCH();
+    return SOCKS_OK;
+}
+
+static int gram_sym_impl(int kind, const double* Z, int64_t n, int d, double scale, int divide, double diag_add,
+                         double* G, int64_t ldg, socks_stream_t stream) {
+    SOCKS_CHECK_ARG(kind == SOCKS_KERNEL_RBF || kind == SOCKS_KERNEL_ABEL, 1);
+    SOCKS_CHECK_ARG(Z != nullptr, 2);
+    SOCKS_CHECK_ARG(n >= 1, 3);
+    SOCKS_CHECK_ARG(d >= 1 && d <= SOCKS_MAX_DIM, 4);
     const int64_t np = socks_padded_dim(n);
-    SOCKS_CHECK_ARG(scale == scale && (!divide || scale != 0.0), 4);
-    SOCKS_CHECK_ARG(G != nullptr && (reinterpret_cast<uintptr_t>(G) & 15) == 0, 7);
-    SOCKS_CHECK_ARG(ldg >= np && ldg % 2 == 0, 8);
+    SOCKS_CHECK_ARG(scale == scale && (!divide || scale != 0.0), 5);
+    SOCKS_CHECK_ARG(G != nullptr && (reinterpret_cast<uintptr_t>(G) & 15) == 0, 8);
+    SOCKS_CHECK_ARG(ldg >= np && ldg % 2 == 0, 9);
     const KScale ks = make_kscale(scale, divide);
+    const bool abel = (kind == SOCKS_KERNEL_ABEL);
     cudaStream_t st = (cudaStream_t)stream;
     if (d <= 8 && np / GR_ROWS <= 65535) {
         dim3 block(GR_TX, GR_TY), grid((unsigned)(np / GR_COLS), (unsigned)(np / GR_ROWS));
-#define SOCKS_SYM_CASE(DD) \
-    case DD: gram_sym_kernel<DD><<<grid, block, 0, st>>>(Z, n, ks, diag_add, G, ldg); break;
+#define SOCKS_SYM_CASE(DD)                                                                       \
+    case DD:                                                                                     \
+        if (abel) gram_sym_kernel<DD, true><<<grid, block, 0, st>>>(Z, n, ks, diag_add, G, ldg); \
+        else gram_sym_kernel<DD, false><<<grid, block, 0, st>>>(Z, n, ks, diag_add, G, ldg);     \
+        break;
         switch (d) {
             SOCKS_SYM_CASE(1) SOCKS_SYM_CASE(2) SOCKS_SYM_CASE(3) SOCKS_SYM_CASE(4)
             SOCKS_SYM_CASE(5) SOCKS_SYM_CASE(6) SOCKS_SYM_CASE(7) SOCKS_SYM_CASE(8)
         }
 #undef SOCKS_SYM_CASE
     } else {
-        SOCKS_CHECK_ARG(np <= 65535, 2);
+        SOCKS_CHECK_ARG(np <= 65535, 3);
         dim3 block(256), grid((unsigned)ceil_div(np, 256), (unsigned)np);
-        gram_sym_generic_kernel<<<grid, block, 0, st>>>(Z, n, d, ks, diag_add, G, ldg, np);
+        gram_sym_generic_kernel<<<grid, block, 0, st>>>(Z, n, d, ks, abel ? 1 : 0, diag_add, G, ldg, np);
     }
     SOCKS_CHECK_LAUNCH();
     return SOCKS_OK;
+}
+
+extern "C" int socks_gram_sym_kernel(int kind, const double* Z, int64_t n, int d, double scale, int divide,
+                                     double diag_add, double* G, int64_t ldg, socks_stream_t stream) {
+    return gram_sym_impl(kind, Z, n, d, scale, divide, diag_add, G, ldg, stream);
+}
+
+extern "C" int socks_gram_sym(const double* Z, int64_t n, int d, double scale, int divide, double diag_add, double* G,
+                              int64_t ldg, socks_stream_t stream) {
+    int rc = gram_sym_impl(SOCKS_KERNEL_RBF, Z, n, d, scale, divide, diag_add, G, ldg, stream);
+    return rc < -1 ? rc + 1 : rc;
 }

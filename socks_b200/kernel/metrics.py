@@ -16,7 +16,10 @@ import torch
 from socks_b200 import _device as dv
 from socks_b200 import _lib
 
-__all__ = ["rbf_kernel", "regularized_inverse", "RBFSpec", "resolve_kernel", "Factorization"]
+__all__ = ["rbf_kernel", "abel_kernel", "euclidean_distance", "regularized_inverse", "RBFSpec", "resolve_kernel",
+           "Factorization"]
+
+KIND_RBF, KIND_ABEL = 0, 1  # SOCKS_KERNEL_RBF / SOCKS_KERNEL_ABEL
 
 
 # ----------------------------------------------------------------------------- kernel_fn protocol
@@ -28,8 +31,8 @@ class RBFSpec:
     `gamma`-style (sklearn semantics): gamma used as is; gamma=None -> 1 / n_features.
     """
 
-    def __init__(self, sigma=None, gamma=None, style="sigma"):
-        self.sigma, self.gamma, self.style = sigma, gamma, style
+    def __init__(self, sigma=None, gamma=None, style="sigma", kind=KIND_RBF):
+        self.sigma, self.gamma, self.style, self.kind = sigma, gamma, style, kind
         if style == "sigma" and sigma is not None:
             assert sigma > 0, "sigma must be a strictly positive real value."
 
@@ -40,6 +43,9 @@ class RBFSpec:
         if self.style == "gamma":
             g = float(self.gamma) if self.gamma is not None else 1.0 / Xd.shape[1]
             return (-g, 0)
+        if self.kind == KIND_ABEL:  # exp(dist / -sigma), sigma=None -> median of the distances (metrics.py:199-204)
+            sigma = float(self.sigma) if self.sigma is not None else _median_sqdist(Xd, Yd, squared=False)
+            return (-sigma, 1)
         sigma = float(self.sigma) if self.sigma is not None else _median_sqdist(Xd, Yd)
         return (-2 * (sigma ** 2), 1)
 
@@ -54,7 +60,7 @@ class RBFSpec:
 
 
 def _is_rbf_function(fn):
-    return callable(fn) and getattr(fn, "__name__", "") == "rbf_kernel"
+    return callable(fn) and getattr(fn, "__name__", "") in ("rbf_kernel", "abel_kernel")
 
 
 def resolve_kernel(kernel_fn, default_sigma):
@@ -77,18 +83,21 @@ def resolve_kernel(kernel_fn, default_sigma):
     module = getattr(fn, "__module__", "") or ""
     kw.pop("distance_fn", None)  # accepted and ignored by the reference (metrics.py:114-117)
     if module.startswith("sklearn"):
+        if fn.__name__ != "rbf_kernel":
+            raise TypeError("only sklearn's rbf_kernel is supported among the sklearn pairwise kernels")
         extra = set(kw) - {"gamma"}
         if extra:
             raise TypeError(f"unsupported keyword(s) for sklearn rbf_kernel: {sorted(extra)}")
         return RBFSpec(gamma=kw.get("gamma"), style="gamma")
     extra = set(kw) - {"sigma"}
     if extra:
-        raise TypeError(f"unsupported keyword(s) for rbf_kernel: {sorted(extra)}")
-    return RBFSpec(sigma=kw.get("sigma"), style="sigma")
+        raise TypeError(f"unsupported keyword(s) for {fn.__name__}: {sorted(extra)}")
+    kind = KIND_ABEL if fn.__name__ == "abel_kernel" else KIND_RBF
+    return RBFSpec(sigma=kw.get("sigma"), style="sigma", kind=kind)
 
 
 # ----------------------------------------------------------------------------- device primitives
-def gram_dev(Xd, Yd, kparams, rowscale=None, out=None, ld=None):
+def gram_dev(Xd, Yd, kparams, rowscale=None, out=None, ld=None, kind=KIND_RBF):
     """K = rowscale[:, None] * k(X_i, Y_j) on the device, kparams = (scale, divide); returns an (n, ld) tensor
     whose first m columns hold K (ld = m rounded up to even so rows stay 16-byte aligned)."""
     n, d = Xd.shape
@@ -97,23 +106,23 @@ def gram_dev(Xd, Yd, kparams, rowscale=None, out=None, ld=None):
         ld = dv.even(m)
     if out is None:
         out = dv.empty(n, ld)
-    _lib.call("socks_gram_rbf", dv.ptr(Xd), n, dv.ptr(Yd), m, d, float(kparams[0]), int(kparams[1]), dv.ptr(rowscale),
-              dv.ptr(out), ld, dv.stream())
+    _lib.call("socks_gram_kernel", int(kind), dv.ptr(Xd), n, dv.ptr(Yd), m, d, float(kparams[0]), int(kparams[1]),
+              dv.ptr(rowscale), dv.ptr(out), ld, dv.stream())
     return out
 
 
-def sqdist_dev(Xd, Yd):
+def sqdist_dev(Xd, Yd, squared=True):
     n, d = Xd.shape
     m = Yd.shape[0]
     out = dv.empty(n, m)
-    _lib.call("socks_sqdist", dv.ptr(Xd), n, dv.ptr(Yd), m, d, dv.ptr(out), m, dv.stream())
+    _lib.call("socks_sqdist" if squared else "socks_dist", dv.ptr(Xd), n, dv.ptr(Yd), m, d, dv.ptr(out), m, dv.stream())
     return out
 
 
-def _median_sqdist(Xd, Yd):
-    """np.median of the squared-distance matrix (metrics.py:130-131): mean of the two middle order
+def _median_sqdist(Xd, Yd, squared=True):
+    """np.median of the (squared) distance matrix (metrics.py:130-131, :199-200): mean of the two middle order
     statistics for an even count.  Distances come from the CUDA kernel; torch.kthvalue only selects."""
-    D = sqdist_dev(Xd, Yd).reshape(-1)
+    D = sqdist_dev(Xd, Yd, squared).reshape(-1)
     cnt = D.numel()
     hi = torch.kthvalue(D, cnt // 2 + 1).values
     if cnt % 2:
@@ -129,14 +138,14 @@ class Factorization:
     triangular inverse; `diag()` is diag(inv(G)) (all the SR algorithms read, kernel_sr.py:45),
     `full()` is inv(G) itself."""
 
-    def __init__(self, Zd, kparams, diag_add):
+    def __init__(self, Zd, kparams, diag_add, kind=KIND_RBF):
         n, d = Zd.shape
         self.n, self.np = n, dv.padded(n)
         npad = self.np
         st = dv.stream()
         self.L = dv.empty(npad, npad)
-        _lib.call("socks_gram_sym", dv.ptr(Zd), n, d, float(kparams[0]), int(kparams[1]), float(diag_add),
-                  dv.ptr(self.L), npad, st)
+        _lib.call("socks_gram_sym_kernel", int(kind), dv.ptr(Zd), n, d, float(kparams[0]), int(kparams[1]),
+                  float(diag_add), dv.ptr(self.L), npad, st)
         self.dinv = dv.work(_lib.load().socks_potrf_work_bytes(n))
         self.info = torch.zeros(1, dtype=torch.int32, device=Zd.device)
         _lib.call("socks_potrf", dv.ptr(self.L), n, npad, dv.ptr(self.dinv), dv.ptr(self.info), st)
@@ -205,6 +214,36 @@ def rbf_kernel(X, Y=None, sigma=None, distance_fn=None):
     return K[:, :m].cpu().numpy()
 
 
+def abel_kernel(X, Y=None, sigma=None, distance_fn=None):
+    """Abel kernel exp(-|x - y| / sigma), `gym_socks/kernel/metrics.py:174-206` (sigma=None: median of the
+    distances, `:199-200`).  A user-supplied `distance_fn` cannot run on the GPU and raises TypeError."""
+    if distance_fn is not None and getattr(distance_fn, "__name__", "") != "euclidean_distance":
+        raise TypeError("abel_kernel on the GPU only supports the Euclidean distance (no CPU fallback)")
+    Xh = dv.as2d(X)
+    Yh = Xh if Y is None else dv.as2d(Y)
+    if sigma is not None:
+        assert sigma > 0, "sigma must be a strictly positive real value."
+    n, m = Xh.shape[0], Yh.shape[0]
+    if n == 0 or m == 0:
+        return np.zeros((n, m))
+    Xd = dv.to_dev(Xh)
+    Yd = Xd if Y is None else dv.to_dev(Yh)
+    spec = RBFSpec(sigma=sigma, kind=KIND_ABEL)
+    return gram_dev(Xd, Yd, spec.params_for(Xd, Yd), kind=KIND_ABEL)[:, :m].cpu().numpy()
+
+
+def euclidean_distance(X, Y=None, squared=False):
+    """Pairwise (squared) Euclidean distance by direct differences, `gym_socks/kernel/metrics.py:26-66`."""
+    Xh = dv.as2d(X)
+    Yh = Xh if Y is None else dv.as2d(Y)
+    n, m = Xh.shape[0], Yh.shape[0]
+    if n == 0 or m == 0:
+        return np.zeros((n, m))
+    Xd = dv.to_dev(Xh)
+    Yd = Xd if Y is None else dv.to_dev(Yh)
+    return sqdist_dev(Xd, Yd, squared=bool(squared)).cpu().numpy()
+
+
 def regularized_inverse(X, Y=None, U=None, V=None, regularization_param=None, kernel_fn=None):
     """Regularised inverse `inv(K + lambda N I)`, `gym_socks/kernel/metrics.py:209-280`.
 
@@ -251,6 +290,9 @@ def factorize(Xh, Uh, spec, regularization_param):
     kp = spec.params_for(Xd, Xd)
     if Uh is None:
         Zd = Xd
+    elif spec.kind != KIND_RBF:
+        raise NotImplementedError("the product Gram K(X,X) * K(U,U) is fused as one kernel on [X | U], which only "
+                                  "holds for the RBF kernel; no algorithm of the reference uses it with abel_kernel")
     else:
         Ud = dv.to_dev(Uh)
         ku = spec.params_for(Ud, Ud)
@@ -259,4 +301,4 @@ def factorize(Xh, Uh, spec, regularization_param):
         else:  # data-dependent bandwidths differ: rescale U so one scale applies
             gx, gu = spec.gamma_for(Xd, Xd), spec.gamma_for(Ud, Ud)
             Zd = dv.to_dev(np.concatenate([Xh, Uh * np.sqrt(gu / gx)], axis=1))
-    return Factorization(Zd, kp, regularization_param * n)
+    return Factorization(Zd, kp, regularization_param * n, kind=spec.kind)

@@ -45,7 +45,7 @@ def test_argument_validation_codes():
     lib = _lib.load()
     # d out of range -> argument 5 of socks_gram_rbf
     assert lib.socks_gram_rbf(None, 4, None, 4, 0, -1.0, 0, None, None, 4, None) == -5
-    assert b"socks_gram_rbf" in lib.socks_last_error()
+    assert b"invalid argument" in lib.socks_last_error()
     # ldk < m -> argument 10
     assert lib.socks_gram_rbf(None, 4, None, 4, 2, -1.0, 0, None, None, 2, None) == -10
     # bad problem code -> argument 12 of socks_sr_predict

@@ -281,3 +281,28 @@ def test_kernel_control_bwd_golden(name):
         y = pol.scores(time=t, state=[g["states"][t]]).cpu().numpy()
         assert np.max(np.abs(y[0] - g["C"][t])) <= tol * np.max(np.abs(g["C"][t]))
         assert np.array_equal(pol(time=t, state=[g["states"][t]]), g["actions"][t])
+
+
+def test_abel_kernel_and_separating_classifier_golden():
+    """abel_kernel / euclidean_distance / SeparatingKernelClassifier vs the unmodified reference."""
+    from socks_b200.algorithms.reach.separating_kernel import SeparatingKernelClassifier
+    from socks_b200.kernel.metrics import abel_kernel, euclidean_distance
+
+    g = load_golden("separating_ring.npz")
+    X, T, sigma, lam = g["X"], g["T"], float(g["sigma"]), float(g["lam"])
+    K = abel_kernel(X[:40], T[:30], sigma=sigma)
+    assert np.max(np.abs(K - g["K_abel"]) / g["K_abel"]) <= 1e-13
+    assert np.max(np.abs(abel_kernel(X[:40]) - g["K_abel_median"]) / g["K_abel_median"]) <= 1e-13
+    assert np.max(np.abs(euclidean_distance(X[:40], T[:30]) - g["D"])) <= 1e-15
+    assert np.array_equal(euclidean_distance(X[:40], T[:30], squared=True), g["D2"])
+    clf = SeparatingKernelClassifier(kernel_fn=partial(abel_kernel, sigma=sigma), regularization_param=lam)
+    clf.fit(X)
+    tol = max(1e-10, 100 * float(g["cond"]) * 2.0 ** -53)
+    assert abs(clf.tau - float(g["tau"])) <= tol
+    C = clf.scores(T)
+    assert np.max(np.abs(C - g["C"])) <= tol
+    labels = clf.predict(T)
+    decided = np.abs(g["C"] - (1 - float(g["tau"]))) > 10 * tol  # points not sitting on the threshold
+    assert np.array_equal(labels[decided], g["labels"][decided])
+    clf.predict_chunk = 128  # several chunks with a ragged tail
+    assert np.max(np.abs(clf.scores(T) - C)) <= 1e-13

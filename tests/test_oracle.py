@@ -114,3 +114,15 @@ def test_control_bwd_golden(name):
         C, _ = pol.scores(t, g["states"][t])
         assert np.max(np.abs(C - g["C"][t])) <= tol * np.max(np.abs(g["C"][t]))
         assert np.array_equal(pol(time=t, state=g["states"][t]), g["actions"][t])
+
+
+def test_abel_and_separating_golden():
+    g = load_golden("separating_ring.npz")
+    X, T = g["X"], g["T"]
+    assert np.array_equal(orc.abel_kernel(X[:40], T[:30], float(g["sigma"])), g["K_abel"])
+    assert np.array_equal(orc.abel_kernel(X[:40]), g["K_abel_median"])
+    clf = orc.SeparatingKernelOracle(float(g["sigma"]), float(g["lam"])).fit(X)
+    tol = 100 * float(g["cond"]) * 2.0 ** -53
+    assert abs(clf.tau - float(g["tau"])) <= tol
+    assert np.max(np.abs(clf.scores(T) - g["C"])) <= tol
+    assert np.array_equal(clf.predict(T), g["labels"])
