@@ -26,7 +26,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-SIGMA, DIM, PROBLEM = 0.1, 2, "FHT"
+SIGMA, PROBLEM = 0.1, "FHT"
+DIM = 2  # state dimension of the headline workload; --d overrides it (BASELINE.json configs[4] uses d = 4)
 # algorithmic FP64 work per (sample, test point) pair of the fused predict:
 # distance 3d+2, shipped exp (exp_f64.cuh exp_scaled_x4: 7 DFMA + DADD + DMUL = 16 flop), contraction 2T
 EXP_FLOPS = 16
@@ -124,7 +125,7 @@ def run_reference(args):
         "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"KernelSR predict, 2-D integrator, N={n}, T={T}, M={args.m}/GPU, sigma=0.1, FHT",
+        "config": {"workload": f"KernelSR predict, {DIM}-D integrator, N={n}, T={T}, M={args.m}/GPU, sigma=0.1, FHT",
                    "sample_points_per_step": m_s},
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -271,7 +272,7 @@ def run_ours(args):
             "value": m_total * args.steps / dev_s, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"KernelSR predict, 2-D integrator, N={n}, T={T}, M={args.m}"
+            "config": {"workload": f"KernelSR predict, {d}-D integrator, N={n}, T={T}, M={args.m}"
                                    f"{'/GPU' if args.scaling == 'weak' else ' in total'}, sigma=0.1, FHT, "
                                    f"lambda=1/N^2 (BASELINE.json configs[1])",
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step event pair)",
@@ -284,7 +285,7 @@ def run_ours(args):
                          "frac": achieved / dmma_peak,
                          # dram__bytes_read + dram__bytes_write of one launch at this exact shape, from the ncu
                          # --set full capture summarised in profiles/r1_ncu_sr_predict_dmma_n20000_m250000.txt
-                         "traffic": 280.0e6 if (n, m, T) == (20000, 250000, 15) else None,
+                         "traffic": 279.1e6 if (n, m, T, d) == (20000, 250000, 15, 2) else None,
                          "kernel": "sr_predict_dmma_kernel<2>",
                          "note": "algorithmic flops = N*M*(3d+2+E+2T), E=16 (exp_f64.cuh); FMA and DMMA share the "
                                  "FP64 pipe on B200 (tools/probe_fp64.py: 36.5 / 37.1 TFLOP/s alone, 35.7 combined), so the fp64 "
@@ -295,7 +296,7 @@ def run_ours(args):
             "wall_s_timed_region": wall,
         }
         line.update(fit_info)
-        if world == 1 and not args.no_extras:
+        if world == 1 and not args.no_extras and d == 2:
             line["kernel_maximal_sr"] = maximal_sr_extra(n, m, T, d, ct, tt, X, U, Y, pts)
         if world == 1:
             wh, vfh = alg._w.cpu().numpy(), alg._vf.cpu().numpy()
@@ -358,7 +359,9 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the KernelMaximalSR side measurement")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --m test points per GPU (default, the driver's contract); strong: --m in total")
+    ap.add_argument("--d", type=int, default=DIM, help="state dimension (chain of integrators)")
     args = ap.parse_args()
+    globals()["DIM"] = args.d
     if args.impl == "reference":
         run_reference(args)
     else:
