@@ -352,14 +352,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=20000)
-    ap.add_argument("--m", type=int, default=250000)
-    ap.add_argument("--T", type=int, default=15)
+    ap.add_argument("--n", "--samples", dest="n", type=int, default=20000)
+    ap.add_argument("--m", "--points", dest="m", type=int, default=250000)
+    ap.add_argument("--T", "--horizon", dest="T", type=int, default=15)
     ap.add_argument("--cpu-sample", type=int, default=4000)
     ap.add_argument("--no-extras", action="store_true", help="skip the KernelMaximalSR side measurement")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --m test points per GPU (default, the driver's contract); strong: --m in total")
-    ap.add_argument("--d", type=int, default=DIM, help="state dimension (chain of integrators)")
+    ap.add_argument("--d", "--dim", dest="d", type=int, default=DIM, help="state dimension (chain of integrators)")
     args = ap.parse_args()
     globals()["DIM"] = args.d
     if args.impl == "reference":
