@@ -77,8 +77,8 @@ __device__ __forceinline__ void sp_load_stage(double* __restrict__ sx, double* _
 // layout of mma.m8n8k4 (B[k = lane%4][n = lane/4]).  Partial sums go to part[split][16][ldp]; the finish
 // kernel adds the splits in order, divides by the normaliser row and applies the FHT/THT step.  Splitting
 // the sample axis gives N/2048 times more CTAs than point tiles alone: no wave-quantisation tail.
-template <int D>
-__global__ void __launch_bounds__(SP_WARPS * 32, 2)
+template <int D, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
     sr_predict_dmma_kernel(const double* __restrict__ X, const double* __restrict__ coef, int64_t n, int64_t n_pad,
                            const double* __restrict__ pts, int64_t m, ExpScaled ex, double* __restrict__ part,
                            int64_t ldp) {
@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(SP_WARPS * 32, 2)
     __shared__ double etbl[EXP_TBL2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lq = lane >> 2, lr = lane & 3;
-    const int64_t pbase = (int64_t)blockIdx.x * SP_PTS + warp * (SP_Q * 8);
-    exp_table2_init(etbl, tid, SP_WARPS * 32);  // visible after the first __syncthreads of the main loop
+    const int64_t pbase = (int64_t)blockIdx.x * (WARPS * SP_Q * 8) + warp * (SP_Q * 8);
+    exp_table2_init(etbl, tid, WARPS * 32);  // visible after the first __syncthreads of the main loop
 
     double p[SP_Q][D];
 #pragma unroll
@@ -105,14 +105,14 @@ __global__ void __launch_bounds__(SP_WARPS * 32, 2)
 
     const int tile0 = blockIdx.y * (SP_SPLIT / SP_TS);
     const int tile1 = min((int)(n_pad / SP_TS), tile0 + SP_SPLIT / SP_TS);
-    sp_load_stage<D>(sx[0], sc[0], X, coef, n, (int64_t)tile0 * SP_TS, tid, SP_WARPS * 32);
+    sp_load_stage<D>(sx[0], sc[0], X, coef, n, (int64_t)tile0 * SP_TS, tid, WARPS * 32);
     cp_async_commit();
     for (int tile = tile0; tile < tile1; ++tile) {
         const int cur = (tile - tile0) & 1;
         cp_async_wait<0>();
         __syncthreads();  // stage `cur` visible to all; everyone is done reading stage cur^1
         if (tile + 1 < tile1)
-            sp_load_stage<D>(sx[cur ^ 1], sc[cur ^ 1], X, coef, n, (int64_t)(tile + 1) * SP_TS, tid, SP_WARPS * 32);
+            sp_load_stage<D>(sx[cur ^ 1], sc[cur ^ 1], X, coef, n, (int64_t)(tile + 1) * SP_TS, tid, WARPS * 32);
         cp_async_commit();
         const double* x_s = sx[cur];
         const double* c_s = sc[cur];
@@ -374,9 +374,12 @@ static void launch_predict(int variant, const double* X, const double* coef, int
                            int R, double* out, int64_t ldout, double* part, int64_t ldp, int splits,
                            cudaStream_t st) {
     if (variant == 0) {
-        dim3 grid((unsigned)ceil_div(m, SP_PTS), (unsigned)splits);
-        sr_predict_dmma_kernel<D><<<grid, SP_WARPS * 32, 0, st>>>(X, coef, n, n_pad, pts, m, make_exp_scaled(kmul), part,
-                                                                  ldp);
+        // 8 warps x 32 points per CTA, three CTAs per SM (<= 85 registers): best of the CTA-shape sweep in
+        // profiles/r1_predict_cfg_sweep.txt (all shapes within 4 %: the kernel is FP64-pipe bound)
+        const ExpScaled ex = make_exp_scaled(kmul);
+        sr_predict_dmma_kernel<D, SP_WARPS, 3>
+            <<<dim3((unsigned)ceil_div(m, SP_PTS), (unsigned)splits), SP_WARPS * 32, 0, st>>>(X, coef, n, n_pad, pts, m,
+                                                                                             ex, part, ldp);
         sr_predict_finish_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(part, ldp, splits, m, R, t0, pts, D,
                                                                              tubes, problem, out, ldout);
     } else {
