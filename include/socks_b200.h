@@ -94,6 +94,13 @@ int socks_potrf(double* G, int64_t n, int64_t ldg, double* dinv, int* info_dev, 
 int socks_trtri(const double* L, int64_t n, int64_t ldl, const double* dinv, double* M, int64_t ldm,
                 double* work, socks_stream_t stream);
 
+/* Factor and invert in ONE recursion (what the algorithms use): on return M = inv(L) (as socks_trtri) and, if
+ * keep_l != 0, G holds L (as socks_potrf); with keep_l == 0 only the diagonal 128-blocks of G hold L and the rest
+ * of G is scratch.  The panel solves run as single triangular GEMMs against the already inverted diagonal
+ * blocks (L21 = A21 inv(L11)^T), so there are no leaf TRSM kernels.  work: socks_trtri_work_bytes(n). */
+int socks_potrf_inv(double* G, int64_t n, int64_t ldg, double* M, int64_t ldm, double* work, int* info_dev,
+                    int keep_l, socks_stream_t stream);
+
 /* w[i] = sum_k M[k][i]^2 = diag(inv(G))[i]  (the only part of W the SR algorithms use:
  * np.einsum("ii,ij->ij", W, CXY), kernel_sr.py:45).  work: socks_reduce_work_bytes(np). */
 int socks_diag_inv(const double* M, int64_t n, int64_t ldm, double* w, double* work, socks_stream_t stream);

@@ -204,7 +204,7 @@ class KernelSR:
     @property
     def W(self):
         """inv(G) as an ndarray; computed on first access (the algorithm itself only needs diag(W))."""
-        if self._fac is None or (self._fac.L is None and self._fac._W is None):
+        if self._fac is None or (self._fac._M is None and self._fac._W is None):
             raise AttributeError("factors were released (keep_factors=False); W is unavailable")
         return self._fac.full()[: self._n, : self._n].cpu().numpy()
 

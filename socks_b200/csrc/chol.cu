@@ -10,6 +10,8 @@
 //   trsm(B,L) = trsm(B1,L11); B2 -= B1 L21^T; trsm(B2,L22)      leaf: B <- B inv(L_kk)^T (GEMM)
 //   trtri     = M11 = inv(L11), M22 = inv(L22), M21 = -(M22 L21) M11
 // Roofline: N^3/3 flops each for potrf, trtri and lauum; FP64 DMMA (tensor pipe) bound.
+#include <algorithm>
+
 #include "gemm_f64.cuh"
 #include "reduce.cuh"
 
@@ -138,8 +140,8 @@ __device__ __forceinline__ void smem_tile16(const double* __restrict__ Ap, int l
 // assembled block row by block row, in place.
 template <bool TIMING>
 __global__ void __launch_bounds__(LF_THREADS, 1)
-    potf2_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ dinv, int* __restrict__ info,
-                     int col_offset, long long* __restrict__ cycles) {
+    potf2_inv_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ dinv, int64_t ldd,
+                     int* __restrict__ info, int col_offset, long long* __restrict__ cycles) {
 #define LF_TICK(slot)                                       \
     if (TIMING && threadIdx.x == 0) cycles[slot] = clock64();
     extern __shared__ __align__(16) double lf_smem[];
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1)
     LF_TICK(13)
     for (int e = tid; e < LF * LF; e += LF_THREADS) {
         const int r = e >> 7, c = e & 127;
-        dinv[r * LF + c] = (c <= r) ? S[r * LF_LD + c] : 0.0;
+        dinv[(int64_t)r * ldd + c] = (c <= r) ? S[r * LF_LD + c] : 0.0;
     }
     LF_TICK(14)
 #undef LF_TICK
@@ -332,10 +334,11 @@ __global__ void __launch_bounds__(256, 1)
 }
 
 __global__ void copy_block_kernel(const double* __restrict__ src, int64_t lds, double* __restrict__ dst, int64_t ldd,
-                                  int rows, int cols) {
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < rows * cols; e += gridDim.x * blockDim.x) {
-        int r = e / cols, c = e % cols;
-        dst[(int64_t)r * ldd + c] = src[(int64_t)r * lds + c];
+                                  int64_t rows, int64_t cols) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < rows * cols;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / cols, c = e % cols;
+        dst[r * ldd + c] = src[r * lds + c];
     }
 }
 
@@ -382,7 +385,7 @@ static void trsm_rec(CholCtx& cx, double* B, int64_t ldb, int64_t m, const doubl
 
 static void potrf_rec(CholCtx& cx, double* A, int64_t lda, int64_t n, double* dinv, int* info, int64_t off) {
     if (n == LF) {
-        potf2_inv_kernel<false><<<1, LF_THREADS, LF_SMEM, cx.st>>>(A, lda, dinv, info, (int)off, nullptr);
+        potf2_inv_kernel<false><<<1, LF_THREADS, LF_SMEM, cx.st>>>(A, lda, dinv, LF, info, (int)off, nullptr);
         cx.note(cudaGetLastError());
         return;
     }
@@ -410,6 +413,38 @@ static void trtri_rec(CholCtx& cx, const double* L, int64_t ldl, const double* d
                                    GEMM_A_K_LE_M, 0, cx.st));
     cx.note(gemm_f64<false, false>(work, n1, M, ldm, M + n1 * ldm, ldm, n2, n1, n1, -1.0, 0.0, GEMM_B_K_GE_N, 0,
                                    cx.st));
+}
+
+// Factor AND invert in one recursion:  A -> L (lower, optional),  M <- inv(L).
+//   (L11, M11) = rec(A11);  L21 = A21 M11^T (one triangular GEMM: the TRSM against an already inverted factor);
+//   A22 -= L21 L21^T;  (L22, M22) = rec(A22);  M21 = -(M22 L21) M11.
+// L21 lives in M's (2,1) block until M21 overwrites it, so the panel solve needs no leaf TRSM kernels, no
+// recursive splitting of the solve and no copies: every flop outside the 128 x 128 leaves is a large GEMM.
+static void potrf_inv_rec(CholCtx& cx, double* A, int64_t lda, double* M, int64_t ldm, int64_t n, double* work,
+                          int* info, int64_t off, bool keep_l) {
+    if (n == LF) {
+        potf2_inv_kernel<false><<<1, LF_THREADS, LF_SMEM, cx.st>>>(A, lda, M, ldm, info, (int)off, nullptr);
+        cx.note(cudaGetLastError());
+        return;
+    }
+    const int64_t n1 = split_point(n), n2 = n - n1;
+    double* A21 = A + n1 * lda;
+    double* A22 = A21 + n1;
+    double* M21 = M + n1 * ldm;  // holds L21 until the last step
+    double* M22 = M21 + n1;
+    potrf_inv_rec(cx, A, lda, M, ldm, n1, work, info, off, keep_l);
+    // L21 = A21 * M11^T:  B(k, j) = M11[j][k], zero for k > j
+    cx.note(gemm_f64<false, true>(A21, lda, M, ldm, M21, ldm, n2, n1, n1, 1.0, 0.0, GEMM_B_K_LE_N, 0, cx.st));
+    cx.note(gemm_f64<false, true>(M21, ldm, M21, ldm, A22, lda, n2, n2, n1, -1.0, 1.0, 0, 1, cx.st));
+    if (keep_l) {
+        copy_block_kernel<<<(unsigned)std::min<int64_t>(4096, ceil_div(n2 * n1, 256)), 256, 0, cx.st>>>(M21, ldm, A21, lda,
+                                                                                                      n2, n1);
+        cx.note(cudaGetLastError());
+    }
+    potrf_inv_rec(cx, A22, lda, M22, ldm, n2, work, info, off + n1, keep_l);
+    // T (n2 x n1, ld n1) = M22 * L21 ;  M21 = -T * M11
+    cx.note(gemm_f64<false, false>(M22, ldm, M21, ldm, work, n1, n2, n1, n2, 1.0, 0.0, GEMM_A_K_LE_M, 0, cx.st));
+    cx.note(gemm_f64<false, false>(work, n1, M, ldm, M21, ldm, n2, n1, n1, -1.0, 0.0, GEMM_B_K_GE_N, 0, cx.st));
 }
 
 static int chol_configure() {
@@ -466,7 +501,7 @@ extern "C" int socks_dev_potf2_phases(double* A, int64_t lda, double* dinv, int*
     SOCKS_CHECK_ARG(A != nullptr && dinv != nullptr && info_dev != nullptr && cycles != nullptr, 1);
     int rc = chol_configure();
     if (rc) return rc;
-    potf2_inv_kernel<true><<<1, LF_THREADS, LF_SMEM, (cudaStream_t)stream>>>(A, lda, dinv, info_dev, 0, cycles);
+    potf2_inv_kernel<true><<<1, LF_THREADS, LF_SMEM, (cudaStream_t)stream>>>(A, lda, dinv, LF, info_dev, 0, cycles);
     SOCKS_CHECK_LAUNCH();
     return SOCKS_OK;
 }
@@ -482,6 +517,23 @@ extern "C" int socks_trtri(const double* L, int64_t n, int64_t ldl, const double
     trtri_rec(cx, L, ldl, dinv, M, ldm, socks_padded_dim(n), work);
     if (cx.err != cudaSuccess) {
         set_error("socks_trtri: CUDA launch failed: %s", cudaGetErrorString(cx.err));
+        return SOCKS_ECUDA;
+    }
+    return SOCKS_OK;
+}
+
+extern "C" int socks_potrf_inv(double* G, int64_t n, int64_t ldg, double* M, int64_t ldm, double* work, int* info_dev,
+                               int keep_l, socks_stream_t stream) {
+    int rc = check_square(G, n, ldg, 1);
+    if (rc) return rc;
+    if ((rc = check_square(M, n, ldm, 4))) return rc;
+    SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 15) == 0, 6);
+    SOCKS_CHECK_ARG(info_dev != nullptr, 7);
+    if ((rc = chol_configure())) return rc;
+    CholCtx cx{(cudaStream_t)stream};
+    potrf_inv_rec(cx, G, ldg, M, ldm, socks_padded_dim(n), work, info_dev, 0, keep_l != 0);
+    if (cx.err != cudaSuccess) {
+        set_error("socks_potrf_inv: CUDA launch failed: %s", cudaGetErrorString(cx.err));
         return SOCKS_ECUDA;
     }
     return SOCKS_OK;

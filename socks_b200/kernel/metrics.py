@@ -134,22 +134,32 @@ def _median_sqdist(Xd, Yd, squared=True):
 class Factorization:
     """G = K(Z,Z) + lambda N I = L L^T on the device, with the pieces of inv(G) the path needs.
 
-    metrics.py:278-280 (`inv(K + regularization_param * num_rows * I)`) computed as Cholesky +
-    triangular inverse; `diag()` is diag(inv(G)) (all the SR algorithms read, kernel_sr.py:45),
-    `full()` is inv(G) itself."""
+    metrics.py:278-280 (`inv(K + regularization_param * num_rows * I)`) computed as Cholesky + triangular
+    inverse in one recursion (socks_potrf_inv); `diag()` is diag(inv(G)) (all the SR algorithms read,
+    kernel_sr.py:45), `full()` is inv(G) itself.  `keep_l=True` also leaves the complete factor L in `self.L`;
+    `two_pass=True` uses the separate socks_potrf + socks_trtri entry points instead of the fused recursion."""
 
-    def __init__(self, Zd, kparams, diag_add, kind=KIND_RBF):
+    def __init__(self, Zd, kparams, diag_add, kind=KIND_RBF, keep_l=False, two_pass=False):
         n, d = Zd.shape
         self.n, self.np = n, dv.padded(n)
         npad = self.np
         st = dv.stream()
+        lib = _lib.load()
         self.L = dv.empty(npad, npad)
         _lib.call("socks_gram_sym_kernel", int(kind), dv.ptr(Zd), n, d, float(kparams[0]), int(kparams[1]),
                   float(diag_add), dv.ptr(self.L), npad, st)
-        self.dinv = dv.work(_lib.load().socks_potrf_work_bytes(n))
         self.info = torch.zeros(1, dtype=torch.int32, device=Zd.device)
-        _lib.call("socks_potrf", dv.ptr(self.L), n, npad, dv.ptr(self.dinv), dv.ptr(self.info), st)
-        self._M = None
+        self._M = dv.empty(npad, npad)
+        wk = dv.work(lib.socks_trtri_work_bytes(n))
+        if two_pass:
+            dinv = dv.work(lib.socks_potrf_work_bytes(n))
+            _lib.call("socks_potrf", dv.ptr(self.L), n, npad, dv.ptr(dinv), dv.ptr(self.info), st)
+            _lib.call("socks_trtri", dv.ptr(self.L), n, npad, dv.ptr(dinv), dv.ptr(self._M), npad, dv.ptr(wk), st)
+        else:
+            _lib.call("socks_potrf_inv", dv.ptr(self.L), n, npad, dv.ptr(self._M), npad, dv.ptr(wk), dv.ptr(self.info),
+                      1 if keep_l else 0, st)
+            if not keep_l:
+                self.L = None  # only scratch is left in it
         self._w = None
         self._W = None
 
@@ -163,11 +173,7 @@ class Factorization:
 
     def inverse_factor(self):
         if self._M is None:
-            lib = _lib.load()
-            self._M = dv.empty(self.np, self.np)
-            wk = dv.work(lib.socks_trtri_work_bytes(self.n))
-            _lib.call("socks_trtri", dv.ptr(self.L), self.n, self.np, dv.ptr(self.dinv), dv.ptr(self._M), self.np,
-                      dv.ptr(wk), dv.stream())
+            raise RuntimeError("the inverse factor was released")
         return self._M
 
     def diag(self):
@@ -278,7 +284,7 @@ def regularized_inverse(X, Y=None, U=None, V=None, regularization_param=None, ke
     return W[:n, :n].cpu().numpy()
 
 
-def factorize(Xh, Uh, spec, regularization_param):
+def factorize(Xh, Uh, spec, regularization_param, keep_l=False, two_pass=False):
     """Host arrays -> device Factorization of K(X,X) [* K(U,U)] + lambda N I.
 
     The product of two RBF kernels with the same bandwidth is the RBF kernel of the concatenated
@@ -301,4 +307,4 @@ def factorize(Xh, Uh, spec, regularization_param):
         else:  # data-dependent bandwidths differ: rescale U so one scale applies
             gx, gu = spec.gamma_for(Xd, Xd), spec.gamma_for(Ud, Ud)
             Zd = dv.to_dev(np.concatenate([Xh, Uh * np.sqrt(gu / gx)], axis=1))
-    return Factorization(Zd, kp, regularization_param * n, kind=spec.kind)
+    return Factorization(Zd, kp, regularization_param * n, kind=spec.kind, keep_l=keep_l, two_pass=two_pass)

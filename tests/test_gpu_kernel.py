@@ -114,14 +114,16 @@ def test_regularized_inverse_golden(key, kw):
 
 @pytest.mark.parametrize("n,d,sigma,lam,with_u", [(128, 2, 0.3, 1e-2, False), (257, 3, 0.5, 1e-3, True),
                                                   (1000, 2, 0.1, 1e-6, False), (1500, 3, 3.0, 1e-7, True)])
-def test_factorization_pieces(n, d, sigma, lam, with_u):
-    """potrf residual, M L = I, diag(W) and full W against float64/longdouble numpy (cond-aware)."""
+@pytest.mark.parametrize("two_pass", [False, True])
+def test_factorization_pieces(n, d, sigma, lam, with_u, two_pass):
+    """potrf residual, M L = I, diag(W) and full W against float64 numpy (cond-aware), through the fused
+    socks_potrf_inv recursion and through the separate socks_potrf + socks_trtri entry points."""
     torch, dv, _lib, mt = _mods()
     rng = np.random.default_rng(n)
     X = rng.uniform(-1.1, 1.1, (n, d))
     U = rng.uniform(-1, 1, (n, 2)) if with_u else None
     spec = mt.RBFSpec(sigma=sigma)
-    fac = mt.factorize(X, U, spec, lam)
+    fac = mt.factorize(X, U, spec, lam, keep_l=True, two_pass=two_pass)
     G = orc.rbf_kernel(X, X, sigma)
     if with_u:
         G = G * orc.rbf_kernel(U, U, sigma)
