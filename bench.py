@@ -29,8 +29,8 @@ if ROOT not in sys.path:
 SIGMA, PROBLEM = 0.1, "FHT"
 DIM = 2  # state dimension of the headline workload; --d overrides it (BASELINE.json configs[4] uses d = 4)
 # algorithmic FP64 work per (sample, test point) pair of the fused predict:
-# distance 3d+2, shipped exp (exp_f64.cuh exp_scaled_x4: 7 DFMA + DADD + DMUL = 16 flop), contraction 2T
-EXP_FLOPS = 16
+# distance 3d+2, shipped exp (exp_f64.cuh exp_scaled_x4: 5 DFMA + DADD + DMUL = 12 flop), contraction 2T
+EXP_FLOPS = 12
 
 
 def pair_flops(d, T):
@@ -287,7 +287,7 @@ def run_ours(args):
                          # --set full capture summarised in profiles/r1_ncu_sr_predict_dmma_n20000_m250000.txt
                          "traffic": 279.1e6 if (n, m, T, d) == (20000, 250000, 15, 2) else None,
                          "kernel": "sr_predict_dmma_kernel<2>",
-                         "note": "algorithmic flops = N*M*(3d+2+E+2T), E=16 (exp_f64.cuh); FMA and DMMA share the "
+                         "note": "algorithmic flops = N*M*(3d+2+E+2T), E=12 (exp_f64.cuh); FMA and DMMA share the "
                                  "FP64 pipe on B200 (tools/probe_fp64.py: 36.5 / 37.1 TFLOP/s alone, 35.7 combined), so the fp64 "
                                  "tensor peak bounds the whole kernel; measured live by socks_probe_fp64 "
                                  "(MEASURED_PEAKS.json has HBM and bf16 only)",
