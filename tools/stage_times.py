@@ -61,7 +61,9 @@ def main(n=20000, m=250000, T=15, out_path=None, hbm_gbs=6546.2):
     t, _ = timed(lambda: _lib.call("socks_potrf_inv", dv.ptr(L2), n, npad, dv.ptr(M2), npad, dv.ptr(wk), dv.ptr(info2), 0, st))
     res["potrf_inv_s"] = t
     res["potrf_inv_tflops"] = 2 * npad ** 3 / 3 / t / 1e12
-    res["potrf_inv_vs_two_pass_maxdiff"] = float((torch.tril(M2[:n, :n]) - torch.tril(M[:n, :n])).abs().max())
+    blk = slice(n - 2048, n)  # last rows of inv(L): compare the two routes (rounding differs, ~cond * eps)
+    res["potrf_inv_vs_two_pass_reldiff"] = float((torch.tril(M2[blk, blk]) - torch.tril(M[blk, blk])).abs().max()
+                                                 / torch.tril(M[blk, blk]).abs().max())
     del L2, M2
     w = dv.empty(n)
     rwk = dv.work(lib.socks_reduce_work_bytes(npad) + 8 * (npad + 2))
@@ -80,6 +82,9 @@ def main(n=20000, m=250000, T=15, out_path=None, hbm_gbs=6546.2):
     res["gram_cross_fp64_tflops"] = n * n * (3 * d + 2 + EXP_FLOPS) / t / 1e12
     tubes = pack_tubes(ct, tt, T, d)
     vf = dv.empty(T, n)
+    rec = lambda: _lib.call("socks_sr_recursion", dv.ptr(B), n, n, ldb, dv.ptr(Yd), d, dv.ptr(tubes),
+                            PROBLEM_CODE["FHT"], T, dv.ptr(vf), n, dv.ptr(vf), n, dv.ptr(rwk), st)
+    rec()  # first launch of each kernel pays CUDA's lazy module loading (~1.3 ms here): keep it out of the timing
     t, _ = timed(lambda: _lib.call("socks_sr_recursion", dv.ptr(B), n, n, ldb, dv.ptr(Yd), d, dv.ptr(tubes),
                                    PROBLEM_CODE["FHT"], T, dv.ptr(vf), n, dv.ptr(vf), n, dv.ptr(rwk), st))
     res["fit_recursion_s"] = t
