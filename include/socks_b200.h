@@ -94,6 +94,11 @@ int socks_potrf(double* G, int64_t n, int64_t ldg, double* dinv, int* info_dev, 
 int socks_trtri(const double* L, int64_t n, int64_t ldl, const double* dinv, double* M, int64_t ldm,
                 double* work, socks_stream_t stream);
 
+/* Gout (padded np x np, lower 128-tiles) = Gin (n x n) + diag_add * I with identity padding: entry for callers that
+ * bring their own Gram matrix (ConditionalEmbedding.fit, gym_socks/algorithms/kernel.py:43-66). */
+int socks_pad_spd(const double* Gin, int64_t n, int64_t ldin, double diag_add, double* Gout, int64_t ldout,
+                  socks_stream_t stream);
+
 /* Factor and invert in ONE recursion (what the algorithms use): on return M = inv(L) (as socks_trtri) and, if
  * keep_l != 0, G holds L (as socks_potrf); with keep_l == 0 only the diagonal 128-blocks of G hold L and the rest
  * of G is scratch.  The panel solves run as single triangular GEMMs against the already inverted diagonal

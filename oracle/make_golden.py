@@ -184,7 +184,32 @@ def separating_case(name, n, m, sigma, lam, seed):
          cond=np.linalg.cond(np.linalg.inv(clf.W)))
 
 
+def embedding_case(name, seed):
+    from gym_socks.algorithms.kernel import ConditionalEmbedding
+    from gym_socks.kernel.probability import maximum_mean_discrepancy, witness_function
+
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-1, 1, (150, 2))
+    y1 = np.sin(3 * X[:, 0]) + X[:, 1] ** 2
+    y2 = np.stack([y1, np.cos(2 * X[:, 1])], axis=1)
+    Xt = rng.uniform(-1, 1, (70, 2))
+    G = rbf_kernel(X, sigma=0.4)
+    K = rbf_kernel(X, Xt, sigma=0.4)
+    ce = ConditionalEmbedding(regularization_param=1e-4).fit(G)
+    P = rng.normal(0.0, 1.0, (120, 2))
+    Q = rng.normal(0.3, 1.2, (90, 2))
+    t = rng.uniform(-2, 2, (40, 2))
+    kf = partial(rbf_kernel, sigma=0.8)
+    save(name, X=X, y1=y1, y2=y2, Xt=Xt, G=G, K=K, lam=1e-4, pred1=ce.predict(y1, K), pred2=ce.predict(y2, K),
+         cond=np.linalg.cond(ce._W), P=P, Q=Q, t=t,
+         mmd_unbiased=maximum_mean_discrepancy(P, Q, kernel_fn=kf), mmd_biased_sq=maximum_mean_discrepancy(P, Q, kernel_fn=kf, biased=True, squared=True),
+         mmd_default=maximum_mean_discrepancy(P, Q, squared=True), witness=witness_function(P, Q, t, kernel_fn=kf))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "emb":
+        embedding_case("embedding_mmd.npz", seed=41)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sep":
         separating_case("separating_ring.npz", 300, 400, 0.25, 1e-3, seed=31)
         sys.exit(0)

@@ -33,6 +33,9 @@ __all__ = [
     "heuristic_solution",
     "abel_kernel",
     "SeparatingKernelOracle",
+    "maximum_mean_discrepancy",
+    "witness_function",
+    "conditional_embedding_predict",
 ]
 
 
@@ -362,3 +365,27 @@ class SeparatingKernelOracle:
 
     def predict(self, T):
         return self.scores(T) >= 1 - self.tau
+
+
+# --------------------------------------------------------------------------- kernel/probability.py, algorithms/kernel.py
+def maximum_mean_discrepancy(X, Y, sigma=1.0, biased=False, squared=False):
+    """`gym_socks/kernel/probability.py:9-73` with the rbf kernel."""
+    m, n = len(X), len(Y)
+    GX, GY, GXY = rbf_kernel(X, X, sigma), rbf_kernel(Y, Y, sigma), rbf_kernel(X, Y, sigma)
+    if biased:
+        mmd = GX.sum() / m ** 2 + GY.sum() / n ** 2 - 2 * GXY.sum() / (m * n)
+    else:
+        mmd = ((GX.sum() - np.trace(GX)) / (m * (m - 1)) + (GY.sum() - np.trace(GY)) / (n * (n - 1))
+               - 2 * GXY.sum() / (m * n))
+    return mmd if squared else np.sqrt(mmd)
+
+
+def witness_function(X, Y, t, sigma=1.0):
+    """`gym_socks/kernel/probability.py:76-93`."""
+    return rbf_kernel(X, t, sigma).sum(axis=0) / len(X) - rbf_kernel(Y, t, sigma).sum(axis=0) / len(Y)
+
+
+def conditional_embedding_predict(G, lam, y, K):
+    """`ConditionalEmbedding.fit/predict` (`gym_socks/algorithms/kernel.py:43-81`): (y^T solve(G + lam M I, K))^T."""
+    W = G + lam * len(G) * np.eye(len(G))
+    return (np.asarray(y).T @ np.linalg.solve(W, K)).T

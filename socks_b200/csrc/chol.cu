@@ -357,6 +357,19 @@ __global__ void symmetrize_kernel(double* __restrict__ W, int64_t ldw) {
     }
 }
 
+// Gout (np x np, padded) = Gin (n x n, arbitrary ld) + diag_add * I, identity in the padding; only lower
+// 128-tiles are written (what the factorisation reads).  For callers that bring their own Gram matrix
+// (gym_socks/algorithms/kernel.py:43-66 ConditionalEmbedding.fit).
+__global__ void pad_spd_kernel(const double* __restrict__ Gin, int64_t n, int64_t ldin, double diag_add,
+                               double* __restrict__ Gout, int64_t ldout, int64_t np) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = blockIdx.y;
+    if (j >= np || j / TILE > i / TILE) return;
+    double v = (i == j) ? 1.0 : 0.0;
+    if (i < n && j < n) v = Gin[i * ldin + j] + (i == j ? diag_add : 0.0);
+    Gout[i * ldout + j] = v;
+}
+
 struct CholCtx {
     cudaStream_t st;
     cudaError_t err = cudaSuccess;
@@ -519,6 +532,20 @@ extern "C" int socks_trtri(const double* L, int64_t n, int64_t ldl, const double
         set_error("socks_trtri: CUDA launch failed: %s", cudaGetErrorString(cx.err));
         return SOCKS_ECUDA;
     }
+    return SOCKS_OK;
+}
+
+extern "C" int socks_pad_spd(const double* Gin, int64_t n, int64_t ldin, double diag_add, double* Gout, int64_t ldout,
+                             socks_stream_t stream) {
+    SOCKS_CHECK_ARG(Gin != nullptr, 1);
+    SOCKS_CHECK_ARG(n >= 1 && socks_padded_dim(n) <= 65535, 2);
+    SOCKS_CHECK_ARG(ldin >= n, 3);
+    int rc = check_square(Gout, n, ldout, 5);
+    if (rc) return rc > 0 ? rc : (rc == -6 ? -2 : rc);
+    const int64_t np = socks_padded_dim(n);
+    pad_spd_kernel<<<dim3((unsigned)ceil_div(np, 256), (unsigned)np), 256, 0, (cudaStream_t)stream>>>(
+        Gin, n, ldin, diag_add, Gout, ldout, np);
+    SOCKS_CHECK_LAUNCH();
     return SOCKS_OK;
 }
 

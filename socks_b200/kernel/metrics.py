@@ -163,6 +163,22 @@ class Factorization:
         self._w = None
         self._W = None
 
+    @classmethod
+    def from_matrix(cls, Gd, diag_add):
+        """Factor a caller-supplied symmetric positive definite matrix (device, n x n) + diag_add * I."""
+        self = cls.__new__(cls)
+        n = Gd.shape[0]
+        self.n, self.np = n, dv.padded(n)
+        npad, st, lib = self.np, dv.stream(), _lib.load()
+        G = dv.empty(npad, npad)
+        _lib.call("socks_pad_spd", dv.ptr(Gd), n, Gd.stride(0), float(diag_add), dv.ptr(G), npad, st)
+        self.info = torch.zeros(1, dtype=torch.int32, device=Gd.device)
+        self._M = dv.empty(npad, npad)
+        wk = dv.work(lib.socks_trtri_work_bytes(n))
+        _lib.call("socks_potrf_inv", dv.ptr(G), n, npad, dv.ptr(self._M), npad, dv.ptr(wk), dv.ptr(self.info), 0, st)
+        self.L, self._w, self._W = None, None, None
+        return self
+
     def check(self):
         info = int(self.info.item())
         if info != 0:

@@ -306,3 +306,23 @@ def test_abel_kernel_and_separating_classifier_golden():
     assert np.array_equal(labels[decided], g["labels"][decided])
     clf.predict_chunk = 128  # several chunks with a ragged tail
     assert np.max(np.abs(clf.scores(T) - C)) <= 1e-13
+
+
+def test_conditional_embedding_and_mmd_golden():
+    """ConditionalEmbedding, maximum_mean_discrepancy, witness_function vs the unmodified reference."""
+    from socks_b200.algorithms.kernel import ConditionalEmbedding
+    from socks_b200.kernel.metrics import rbf_kernel
+    from socks_b200.kernel.probability import maximum_mean_discrepancy, witness_function
+
+    g = load_golden("embedding_mmd.npz")
+    tol = max(1e-10, 100 * float(g["cond"]) * 2.0 ** -53)
+    ce = ConditionalEmbedding(regularization_param=float(g["lam"])).fit(g["G"])
+    for y, want in ((g["y1"], g["pred1"]), (g["y2"], g["pred2"])):
+        got = ce.predict(y, g["K"])
+        assert got.shape == want.shape and np.max(np.abs(got - want)) <= tol * np.max(np.abs(want))
+    assert ce.score(g["pred1"], g["K"], g["y1"]) <= tol * np.max(np.abs(g["pred1"]))
+    kf = partial(rbf_kernel, sigma=0.8)
+    assert abs(maximum_mean_discrepancy(g["P"], g["Q"], kernel_fn=kf) - float(g["mmd_unbiased"])) <= 1e-12
+    assert abs(maximum_mean_discrepancy(g["P"], g["Q"], kernel_fn=kf, biased=True, squared=True) - float(g["mmd_biased_sq"])) <= 1e-13
+    assert abs(maximum_mean_discrepancy(g["P"], g["Q"], squared=True) - float(g["mmd_default"])) <= 1e-13
+    assert np.max(np.abs(witness_function(g["P"], g["Q"], g["t"], kernel_fn=kf) - g["witness"])) <= 1e-13

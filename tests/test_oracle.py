@@ -126,3 +126,15 @@ def test_abel_and_separating_golden():
     assert abs(clf.tau - float(g["tau"])) <= tol
     assert np.max(np.abs(clf.scores(T) - g["C"])) <= tol
     assert np.array_equal(clf.predict(T), g["labels"])
+
+
+def test_embedding_and_mmd_golden():
+    g = load_golden("embedding_mmd.npz")
+    tol = 100 * float(g["cond"]) * 2.0 ** -53
+    for y, want in ((g["y1"], g["pred1"]), (g["y2"], g["pred2"])):
+        got = orc.conditional_embedding_predict(g["G"], float(g["lam"]), y, g["K"])
+        assert got.shape == want.shape and np.max(np.abs(got - want)) <= tol * np.max(np.abs(want))
+    assert abs(orc.maximum_mean_discrepancy(g["P"], g["Q"], 0.8) - float(g["mmd_unbiased"])) <= 1e-13
+    assert abs(orc.maximum_mean_discrepancy(g["P"], g["Q"], 0.8, biased=True, squared=True) - float(g["mmd_biased_sq"])) <= 1e-14
+    assert abs(orc.maximum_mean_discrepancy(g["P"], g["Q"], 1.0, squared=True) - float(g["mmd_default"])) <= 1e-14
+    assert np.max(np.abs(orc.witness_function(g["P"], g["Q"], g["t"], 0.8) - g["witness"])) <= 1e-14
