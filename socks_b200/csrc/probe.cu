@@ -32,10 +32,26 @@ __global__ void __launch_bounds__(256) probe_fp64_kernel(int mode, int iters, do
                 dmma884(c0[u], c1[u], m, b);
             }
         }
-    } else {
+    } else if (mode == 3) {
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) a[u] = exp(-a[u]) + 0.5;
+        }
+    } else if (mode == 4) {  // 8 DFMA chains with three DISTINCT register operands each (operand-bandwidth probe)
+        double bb[8], cc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { bb[u] = m + u * 1e-9 * seed; cc[u] = b * (u + 1) * seed; }
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = fma(a[u], bb[u], cc[u]);
+        }
+    } else {  // mode 5: chains cross-feeding each other: a[u] = fma(a[u], a[(u+1)%8], a[(u+3)%8]) (all operands vary)
+        for (int it = 0; it < iters; ++it) {
+            double n8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) n8[u] = fma(a[u], a[(u + 1) & 7], a[(u + 3) & 7]) * 0.25;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = n8[u];
         }
     }
     double s = 0.0;
@@ -47,7 +63,7 @@ __global__ void __launch_bounds__(256) probe_fp64_kernel(int mode, int iters, do
 }  // namespace socks
 
 extern "C" int socks_probe_fp64(int mode, int iters, double* out_dev, int blocks, socks_stream_t stream) {
-    SOCKS_CHECK_ARG(mode >= 0 && mode <= 3, 1);
+    SOCKS_CHECK_ARG(mode >= 0 && mode <= 5, 1);
     SOCKS_CHECK_ARG(iters >= 1, 2);
     SOCKS_CHECK_ARG(out_dev != nullptr, 3);
     SOCKS_CHECK_ARG(blocks >= 1, 4);

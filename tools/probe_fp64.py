@@ -33,13 +33,17 @@ def probe(mode, iters=20000, blocks=148 * 8):
     if mode == 2:
         return {"mixed_fma_tflops": threads * iters * 4 * 2 / best / 1e12,
                 "mixed_dmma_tflops": warps * iters * 4 * 512 / best / 1e12}
-    return {"exp_per_s": threads * iters * 4 / best}
+    if mode == 3:
+        return {"exp_per_s": threads * iters * 4 / best}
+    if mode == 4:
+        return {"fp64_fma_distinct_operands_tflops": threads * iters * 8 * 2 / best / 1e12}
+    return {"fp64_fma_mul_crossfed_instr_per_s": threads * iters * 16 / best}
 
 
 def measure():
     res = {}
-    for mode in range(4):
-        res.update(probe(mode, iters=20000 if mode < 3 else 4000))
+    for mode in range(6):
+        res.update(probe(mode, iters=4000 if mode == 3 else 20000))
     return res
 
 
