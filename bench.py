@@ -131,7 +131,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def run_ours(args):
@@ -305,7 +305,7 @@ def run_ours(args):
                 "value": v, "unit": "points/s", "cores": os.cpu_count(), "kind": "port",
                 "sample": f"oracle predict of {args.cpu_sample} of the {m} test points at N={n}, T={T} on the host "
                           f"cores ({dt:.1f} s), fitted state taken from the GPU fit"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -346,6 +346,23 @@ def maximal_sr_extra(n, m, T, d, ct, tt, X, U, Y, pts, P=100):
     return res
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything except the final JSON line goes to stderr (NCCL and torchrun print banners on fd 1)."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -362,6 +379,7 @@ def main():
     ap.add_argument("--d", "--dim", dest="d", type=int, default=DIM, help="state dimension (chain of integrators)")
     args = ap.parse_args()
     globals()["DIM"] = args.d
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
