@@ -65,6 +65,20 @@ class KernelMaximalSR:
         if S is None:
             raise ValueError("Must supply a sample.")
 
+    # -- fitted state for the multi-GPU helpers (socks_b200/distributed.py): N (d + 1 + T + P) doubles
+    def state_tensors(self):
+        return {"CUA": self._CUA, "X": self._Xd, "vf": self._vf, "w": self._w}
+
+    def allocate_state(self, n, d, P):
+        """Receiving side of a broadcast: empty device state of the right shapes (no fit on this rank)."""
+        self._validate_params()
+        T = int(self.time_horizon)
+        self._n, self._d, self._P, self._Xh, self._fac = int(n), int(d), int(P), None, None
+        self._Xd, self._w, self._vf, self._CUA = dv.empty(n, d), dv.empty(n), dv.empty(T, n), dv.empty(n, P)
+        self._vf_host = None
+        self._tubes = pack_tubes(self.constraint_tube, self.target_tube, T, d)
+        return self.state_tensors()
+
     def fit(self, S, A):
         self._validate_params(S, A)
         self._validate_data(S)
@@ -156,10 +170,14 @@ class KernelMaximalSR:
 
     @property
     def X(self):
+        if self._Xh is None:
+            self._Xh = self._Xd.cpu().numpy()
         return self._Xh
 
     @property
     def W(self):
+        if self._fac is None:
+            raise AttributeError("this rank received the fitted state by broadcast; W lives on the fitting rank")
         return self._fac.full()[: self._n, : self._n].cpu().numpy()
 
     @property
