@@ -29,3 +29,26 @@ def test_non_zero_ranks_of_the_reference_arm_stay_silent():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_one_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "3", "--samples", "2000",
+                          "--points", "20000", "--cpu-sample", "200", "--no-extras"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] >= 3
+    assert line["gpu_launches"] == 8 and line["dtype"] == "f64" and line["data"] == "synthetic"
+    r = line["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    e = line["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 20000 * 2 * 8 and e["d2h_bytes_per_step"] == 15 * 20000 * 8
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
+    assert "sm_mhz" in line["clocks"] and "reasons" in line["clocks"]
+    assert line["fit_s"] > 0 and line["gram_solve_s"] > 0
