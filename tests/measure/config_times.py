@@ -1,12 +1,12 @@
 """Timings of the other BASELINE.json configs through the public API (CUDA events / wall clock), with the
-algorithmic work of SURVEY §8(d').  Usage (on a B200): python tools/config_times.py [c1 c2max c3 c4 c5] [out.json]"""
+algorithmic work of SURVEY §8(d').  Usage (on a B200): python tests/measure/config_times.py [c1 c2max c3 c4 c5] [out.json]"""
 import json
 import os
 import sys
 import time
 from functools import partial
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 

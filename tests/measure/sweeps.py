@@ -5,14 +5,14 @@ defaults (d=2, N=1000, M=1000, T=10, sigma=0.1, lambda=1, THT, sklearn rbf_kerne
 `benchmarks/*/plot_*_vs_time.py:19`).  Timed region as in the reference: tube construction + fit + predict, one
 warm-up discarded, median of 5 repeats; host arrays in, host array out.  The CPU column is the oracle port.
 
-Usage (on a B200): python tools/sweeps.py [out.json] [--no-cpu]"""
+Usage (on a B200): python tests/measure/sweeps.py [out.json] [--no-cpu]"""
 import json
 import os
 import sys
 import time
 from functools import partial
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from sklearn.metrics.pairwise import rbf_kernel as sk_rbf
