@@ -115,6 +115,12 @@ int socks_diag_inv(const double* M, int64_t n, int64_t ldm, double* w, double* w
  * work: socks_reduce_work_bytes(m). */
 int socks_colsumsq(const double* Z, int64_t n, int64_t m, int64_t ldz, double* y, double* work, socks_stream_t stream);
 
+/* X = inv(G) B = M^T (M B), in place on B (np x nrhs, nrhs a multiple of 128, zero rows in the padding):
+ * `np.linalg.solve(G + lambda M I, K)` of ConditionalEmbedding.predict (gym_socks/algorithms/kernel.py:81) and the
+ * `W @ c` products of the control algorithms, without forming W.  work: np * nrhs doubles. */
+int socks_potrs(const double* M, int64_t n, int64_t ldm, double* B, int64_t nrhs, int64_t ldb, double* work,
+                socks_stream_t stream);
+
 /* W = M^T M = inv(G), full symmetric np x np (what regularized_inverse returns). */
 int socks_lauum(const double* M, int64_t n, int64_t ldm, double* W, int64_t ldw, socks_stream_t stream);
 

@@ -35,6 +35,7 @@ SIGNATURES = {
     "socks_potrf_inv": (_I, [_P, _L, _L, _P, _L, _P, _P, _I, _P]),
     "socks_trtri": (_I, [_P, _L, _L, _P, _P, _L, _P, _P]),
     "socks_diag_inv": (_I, [_P, _L, _L, _P, _P, _P]),
+    "socks_potrs": (_I, [_P, _L, _L, _P, _L, _L, _P, _P]),
     "socks_lauum": (_I, [_P, _L, _L, _P, _L, _P]),
     "socks_sr_recursion": (_I, [_P, _L, _L, _L, _P, _I, _P, _I, _I, _P, _L, _P, _L, _P, _P]),
     "socks_sr_predict_work_bytes": (_L, [_L, _L]),

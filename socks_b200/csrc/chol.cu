@@ -601,6 +601,29 @@ extern "C" int socks_colsumsq(const double* Zm, int64_t n, int64_t m, int64_t ld
     return SOCKS_OK;
 }
 
+// X = inv(G) B = M^T (M B) for nrhs right-hand sides (nrhs a multiple of 128, rows padded to np):
+// two triangular DMMA products.  B (np x nrhs) is overwritten by X; work holds np x nrhs doubles.
+extern "C" int socks_potrs(const double* M, int64_t n, int64_t ldm, double* B, int64_t nrhs, int64_t ldb, double* work,
+                           socks_stream_t stream) {
+    int rc = check_square(M, n, ldm, 1);
+    if (rc) return rc;
+    SOCKS_CHECK_ARG(B != nullptr && (reinterpret_cast<uintptr_t>(B) & 15) == 0, 4);
+    SOCKS_CHECK_ARG(nrhs >= 128 && nrhs % 128 == 0, 5);
+    SOCKS_CHECK_ARG(ldb >= nrhs && ldb % 2 == 0, 6);
+    SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 15) == 0, 7);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t np = socks_padded_dim(n);
+    // Z = M B (M lower: k <= i), then X = M^T Z (A(i,k) = M[k][i], zero for k < i)
+    cudaError_t e = gemm_f64<false, false>(M, ldm, B, ldb, work, nrhs, np, nrhs, np, 1.0, 0.0, GEMM_A_K_LE_M, 0, st);
+    if (e == cudaSuccess)
+        e = gemm_f64<true, false>(M, ldm, work, nrhs, B, ldb, np, nrhs, np, 1.0, 0.0, GEMM_A_K_GE_M, 0, st);
+    if (e != cudaSuccess) {
+        set_error("socks_potrs: CUDA launch failed: %s", cudaGetErrorString(e));
+        return SOCKS_ECUDA;
+    }
+    return SOCKS_OK;
+}
+
 extern "C" int socks_lauum(const double* M, int64_t n, int64_t ldm, double* W, int64_t ldw, socks_stream_t stream) {
     int rc = check_square(M, n, ldm, 1);
     if (rc) return rc;

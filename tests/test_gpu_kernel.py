@@ -219,3 +219,23 @@ def test_gemm_f64_forms(ta, tb, cfg):
                   dv.stream())
         got, want = np.tril(Cd.cpu().numpy()), np.tril(L1.T @ L1)
         assert np.max(np.abs(got - want)) <= 1e-12 * np.abs(want).max()
+
+
+def test_potrs_against_numpy_solve():
+    torch, dv, _lib, mt = _mods()
+    rng = np.random.default_rng(9)
+    n, q = 700, 5
+    X = rng.uniform(-1, 1, (n, 2))
+    fac = mt.factorize(X, None, mt.RBFSpec(sigma=0.3), 1e-3)
+    fac.check()
+    G = orc.rbf_kernel(X, X, 0.3)
+    G[np.diag_indices(n)] += 1e-3 * n
+    Bh = rng.standard_normal((n, q))
+    npad = fac.np
+    B = dv.zeros(npad, 128)
+    B[:n, :q].copy_(dv.to_dev(Bh))
+    wk = dv.empty(npad, 128)
+    _lib.call("socks_potrs", dv.ptr(fac.inverse_factor()), n, npad, dv.ptr(B), 128, 128, dv.ptr(wk), dv.stream())
+    want = np.linalg.solve(G, Bh)
+    got = B[:n, :q].cpu().numpy()
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 100 * np.linalg.cond(G) * 2.0 ** -53
