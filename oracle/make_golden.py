@@ -207,6 +207,11 @@ def embedding_case(name, seed):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "mid":
+        # mid-size cases in the regimes the reference's benchmarks/examples use
+        srmax_case("srmax_n1200_p100_fht.npz", 1200, 400, 100, 5, 0.1, 1.0, "FHT", seed=8)   # kernel_sr_max defaults
+        fwd_case("fwd_tracking_regime.npz", 1500, 3.0, 1e-7, 6, seed=12345, constrained=False)  # tracking.py regime
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "emb":
         embedding_case("embedding_mmd.npz", seed=41)
         sys.exit(0)

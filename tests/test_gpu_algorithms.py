@@ -198,7 +198,7 @@ def alg_dev(a):
     return dv.to_dev(a)
 
 
-@pytest.mark.parametrize("name", ["srmax_fht.npz", "srmax_tht_batch.npz"])
+@pytest.mark.parametrize("name", ["srmax_fht.npz", "srmax_tht_batch.npz", "srmax_n1200_p100_fht.npz"])
 def test_kernel_sr_max_golden(name):
     _, _, KernelMaximalSR, kernel_sr_max, _, rbf = _api()
     g = load_golden(name)
@@ -232,7 +232,7 @@ def test_kernel_sr_max_medium_vs_oracle():
     assert np.max(np.abs(alg.predict(pts) - o.predict(pts))) <= TOL
 
 
-@pytest.mark.parametrize("name", ["fwd_unconstrained.npz", "fwd_constrained.npz"])
+@pytest.mark.parametrize("name", ["fwd_unconstrained.npz", "fwd_constrained.npz", "fwd_tracking_regime.npz"])
 @pytest.mark.parametrize("heuristic", [True, False])
 def test_kernel_control_fwd_golden(name, heuristic):
     _, _, _, _, KernelControlFwd, rbf = _api()

@@ -63,7 +63,7 @@ def test_kernel_sr_golden(name):
     assert np.max(np.abs(alg.predict(g["pts"]) - g["out"])) < 1e-11
 
 
-@pytest.mark.parametrize("name", ["srmax_fht.npz", "srmax_tht_batch.npz"])
+@pytest.mark.parametrize("name", ["srmax_fht.npz", "srmax_tht_batch.npz", "srmax_n1200_p100_fht.npz"])
 def test_kernel_sr_max_golden(name):
     g = load_golden(name)
     alg = orc.KernelMaximalSROracle(int(g["T"]), tubes_from(g["ctube"]), tubes_from(g["ttube"]),
@@ -74,7 +74,7 @@ def test_kernel_sr_max_golden(name):
     assert np.max(np.abs(alg.predict(g["pts"]) - g["out"])) < 1e-11
 
 
-@pytest.mark.parametrize("name", ["fwd_unconstrained.npz", "fwd_constrained.npz"])
+@pytest.mark.parametrize("name", ["fwd_unconstrained.npz", "fwd_constrained.npz", "fwd_tracking_regime.npz"])
 def test_control_fwd_golden(name):
     from socks_b200 import synthetic as syn
 
