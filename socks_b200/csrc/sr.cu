@@ -8,9 +8,10 @@
 // known, all T-1 steps collapse into ONE contraction
 //     acc[r][j] = sum_i coef[i][r] k(x_i, pts_j),  coef[.][0] = w, coef[.][r] = vf[t0+r] * w
 // evaluated on the fly: each lane computes the kernel value of one (sample, point) pair in
-// registers (FMA pipe: distance + exp) and feeds it straight into DMMA.8x8x4 as the B fragment,
-// the 16 coefficient rows being the A fragments (tensor pipe).  FP64-pipe bound:
-// N*M*(3d+2+E) flops on the FMA pipe + 2*16*N*M on the tensor pipe, 8*M*(d+T) bytes.
+// registers (distance + table exp, exp_f64.cuh) and feeds it straight into DMMA.8x8x4 as the B fragment,
+// the 16 coefficient rows being the A fragments.  On B200 DMMA and DFMA share the FP64 pipe, so the
+// kernel is FP64-pipe bound: per pair 11 scalar instructions + 2/32 of two DMMA (= 16 FMA-equivalents);
+// algorithmic work N*M*(3d+2+E+2T) flops with E = 12, 8*M*(d+T) bytes of I/O.
 #include <climits>
 #include <cmath>
 

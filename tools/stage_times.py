@@ -107,8 +107,8 @@ def main(n=20000, m=250000, T=15, out_path=None, hbm_gbs=6546.2):
         key = "predict_dmma" if variant == 0 else "predict_fma"
         res[key + "_s"] = t
         res[key + "_pts_per_s"] = m / t
-        res[key + "_fma_pipe_tflops"] = n * m * (3 * d + 2 + EXP_FLOPS) / t / 1e12
-        res[key + "_contraction_tflops"] = n * m * 2 * T / t / 1e12
+        # algorithmic flops as in bench.py: distance 3d+2, exp (table variant 12 / CUDA exp 31), contraction 2T
+        res[key + "_tflops"] = n * m * (3 * d + 2 + (12 if variant == 0 else EXP_FLOPS) + 2 * T) / t / 1e12
     res["gram_solve_two_pass_s"] = res["gram_sym_s"] + res["potrf_s"] + res["trtri_s"] + res["diag_inv_s"]
     res["gram_solve_s"] = res["gram_sym_s"] + res["potrf_inv_s"] + res["diag_inv_s"]
     res["vf_range"] = [float(vf.min()), float(vf.max())]
