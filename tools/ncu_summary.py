@@ -28,6 +28,8 @@ for i, name in enumerate(h):
     if name in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
                 "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
                 "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+                "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+                "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
                 "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
                 "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct"):
         print(f"{name} = {v[i]} {u[i]}")
