@@ -60,13 +60,42 @@ __global__ void __launch_bounds__(256) probe_fp64_kernel(int mode, int iters, do
     out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// mode 6: legacy warp-level int8 tensor op (mma.sync.m16n8k32.s8 -> SASS IMMA): 8 independent accumulators.
+// Feasibility probe for an Ozaki-scheme fp64 GEMM on the integer tensor cores (round-2 idea).
+__global__ void __launch_bounds__(256) probe_imma_kernel(int iters, int* __restrict__ out) {
+    int acc[8][4];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[u][e] = 0;
+    const unsigned a0 = 0x01020304u * (threadIdx.x + 1), a1 = a0 ^ 0x11111111u, a2 = a0 + 7, a3 = a1 + 3;
+    const unsigned b0 = 0x01010101u + threadIdx.x, b1 = b0 * 3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            asm volatile(
+                "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                : "+r"(acc[u][0]), "+r"(acc[u][1]), "+r"(acc[u][2]), "+r"(acc[u][3])
+                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+    int s = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += acc[u][0] + acc[u][1] + acc[u][2] + acc[u][3];
+    out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace socks
 
 extern "C" int socks_probe_fp64(int mode, int iters, double* out_dev, int blocks, socks_stream_t stream) {
-    SOCKS_CHECK_ARG(mode >= 0 && mode <= 5, 1);
+    SOCKS_CHECK_ARG(mode >= 0 && mode <= 6, 1);
     SOCKS_CHECK_ARG(iters >= 1, 2);
     SOCKS_CHECK_ARG(out_dev != nullptr, 3);
     SOCKS_CHECK_ARG(blocks >= 1, 4);
+    if (mode == 6) {
+        socks::probe_imma_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, reinterpret_cast<int*>(out_dev));
+        SOCKS_CHECK_LAUNCH();
+        return SOCKS_OK;
+    }
     socks::probe_fp64_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mode, iters, out_dev);
     SOCKS_CHECK_LAUNCH();
     return SOCKS_OK;

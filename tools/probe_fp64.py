@@ -37,12 +37,14 @@ def probe(mode, iters=20000, blocks=148 * 8):
         return {"exp_per_s": threads * iters * 4 / best}
     if mode == 4:
         return {"fp64_fma_distinct_operands_tflops": threads * iters * 8 * 2 / best / 1e12}
+    if mode == 6:  # m16n8k32: 16*8*32*2 ops per warp instruction
+        return {"legacy_mma_sync_int8_tops": warps * iters * 8 * 16 * 8 * 32 * 2 / best / 1e12}
     return {"fp64_fma_mul_crossfed_instr_per_s": threads * iters * 16 / best}
 
 
 def measure():
     res = {}
-    for mode in range(6):
+    for mode in range(7):
         res.update(probe(mode, iters=4000 if mode == 3 else 20000))
     return res
 
