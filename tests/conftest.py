@@ -13,6 +13,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu under gpurun)")
+    # the CUDA library is a build artefact (git-ignored): build it once if this is a fresh checkout
+    lib = os.path.join(ROOT, "socks_b200", "libsocksb200.so")
+    if not os.path.exists(lib):
+        import subprocess
+
+        subprocess.run(["make", "-C", os.path.join(ROOT, "socks_b200", "csrc"), "-j", "8"], check=False,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 def load_golden(name):
