@@ -48,6 +48,10 @@ typedef void* socks_stream_t;
 int socks_version(void);
 const char* socks_last_error(void);
 int64_t socks_padded_dim(int64_t n);
+/* rows x width_bytes strided copy in one enqueue (kind: 1 host->device, 2 device->host, 3 device->device): the read
+ * of a column block of the (T, M) result into the caller's (pinned) ndarray, kernel_sr.py:344 `return out`. */
+int socks_copy2d(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width_bytes, int64_t rows,
+                 int kind, socks_stream_t stream);
 
 /* ---- Gram builders: gym_socks/kernel/metrics.py:119-138 (rbf_kernel) ------------------- */
 
@@ -139,10 +143,22 @@ int socks_sr_recursion(const double* B, int64_t n, int64_t m, int64_t ldb, const
 
 /* Fused predict (kernel_sr.py:329-342 without materialising K(X,pts)):
  *   out[t][j] = step(pts_j, sum_i vf[t+1][i] w_i k(x_i,pts_j) / sum_i w_i k(x_i,pts_j)).
- * work: socks_sr_predict_work_bytes(n, m) bytes (packed coefficients + per-split partial sums).
- * variant: 0 = DMMA contraction (default), 1 = FMA-pipe contraction.  The sample axis is cut into fixed
- * 2048-sample splits summed in order, so each output column is bit-identical however the test points
- * are chunked or sharded. */
+ * Two steps: socks_sr_pack turns the fitted state (X, w = diag(inv G), vf) into the packed operand of the predict
+ * kernels once per fit (centred samples, coefficient rows, admissibility of the factored evaluation);
+ * socks_sr_predict_packed evaluates any number of test-point batches against it.  socks_sr_predict does both in one
+ * call (pack at the head of `work`).
+ * variant: 0 = automatic (factored exponent on the tensor cores, direct form for the columns / launches where a
+ * factor could over- or underflow), 1 = FMA-pipe contraction with CUDA's exp, 2 = direct form on the tensor cores,
+ * 3 / 4 = automatic with the CTA shape forced to 8 / 4 warps (measurement).  The sample axis is cut into fixed
+ * 2048-sample splits summed in order, and the form chosen for a column depends only on that column and the fitted
+ * state, so each output column is bit-identical however the test points are chunked or sharded. */
+int64_t socks_sr_pack_bytes(int64_t n, int d, int T);
+int socks_sr_pack(const double* X, const double* w, const double* vf, int64_t ldvf, int64_t n, int d, double scale,
+                  int divide, int T, double* pack, socks_stream_t stream);
+int64_t socks_sr_predict_packed_work_bytes(int64_t n, int64_t m);
+int socks_sr_predict_packed(const double* pack, const double* X, int64_t n, int d, double scale, int divide,
+                            const double* pts, int64_t m, const double* tubes, int problem, int T, double* out,
+                            int64_t ldout, double* work, int variant, socks_stream_t stream);
 int64_t socks_sr_predict_work_bytes(int64_t n, int64_t m);
 int socks_sr_predict(const double* X, const double* w, const double* vf, int64_t ldvf, int64_t n, int d,
                      double scale, int divide, const double* pts, int64_t m, const double* tubes, int problem, int T,

@@ -20,6 +20,7 @@ SIGNATURES = {
     "socks_version": (_I, []),
     "socks_last_error": (c_char_p, []),
     "socks_padded_dim": (_L, [_L]),
+    "socks_copy2d": (_I, [_P, _L, _P, _L, _L, _L, _I, _P]),
     "socks_gram_rbf": (_I, [_P, _L, _P, _L, _I, _D, _I, _P, _P, _L, _P]),
     "socks_gram_kernel": (_I, [_I, _P, _L, _P, _L, _I, _D, _I, _P, _P, _L, _P]),
     "socks_dist": (_I, [_P, _L, _P, _L, _I, _P, _L, _P]),
@@ -38,6 +39,10 @@ SIGNATURES = {
     "socks_potrs": (_I, [_P, _L, _L, _P, _L, _L, _P, _P]),
     "socks_lauum": (_I, [_P, _L, _L, _P, _L, _P]),
     "socks_sr_recursion": (_I, [_P, _L, _L, _L, _P, _I, _P, _I, _I, _P, _L, _P, _L, _P, _P]),
+    "socks_sr_pack_bytes": (_L, [_L, _I, _I]),
+    "socks_sr_pack": (_I, [_P, _P, _P, _L, _L, _I, _D, _I, _I, _P, _P]),
+    "socks_sr_predict_packed_work_bytes": (_L, [_L, _L]),
+    "socks_sr_predict_packed": (_I, [_P, _P, _L, _I, _D, _I, _P, _L, _P, _I, _I, _P, _L, _P, _I, _P]),
     "socks_sr_predict_work_bytes": (_L, [_L, _L]),
     "socks_sr_predict": (_I, [_P, _P, _P, _L, _L, _I, _D, _I, _P, _L, _P, _I, _I, _P, _L, _P, _I, _P]),
     "socks_srmax_pack": (_I, [_P, _L, _I, _P, _P, _L, _I, _I, _I, _P, _L, _L, _P]),

@@ -12,7 +12,7 @@ import numpy as np
 from socks_b200 import _device as dv
 from socks_b200 import _lib
 from socks_b200.algorithms.reach.common import PROBLEM_CODE, pack_tubes
-from socks_b200.kernel.metrics import factorize, gram_dev, resolve_kernel
+from socks_b200.kernel.metrics import factorize, gram_dev, resolve_kernel, sharded_bandwidth_guard
 from socks_b200.sampling.transform import transpose_sample
 
 logger = logging.getLogger(__name__)
@@ -36,7 +36,7 @@ class KernelSR:
     attributes `X`, `W`, `value_functions`.  `batch_size` is accepted for API parity and does not change
     results (test points are independent columns; the fused predict kernel streams them anyway)."""
 
-    predict_variant = 0  # 0: DMMA contraction, 1: FMA-pipe contraction (csrc/sr.cu)
+    predict_variant = 0  # 0: automatic, 1: FMA-pipe contraction, 2: direct form on the tensor cores (csrc/sr_predict.cu)
 
     def __init__(self, time_horizon=None, constraint_tube=None, target_tube=None, problem="THT", kernel_fn=None,
                  regularization_param=None, batch_size=None, verbose=False, *args, **kwargs):
@@ -145,7 +145,7 @@ class KernelSR:
         nchunks = self.predict_chunks if m >= 65536 else 1
         chunk = -(-(-(-m // nchunks)) // 256) * 256
         cs = dv.copy_stream()
-        kparams = self._spec.params_for(self._Xd, pts)  # once for the whole call (sigma=None: median over K(X,T))
+        kparams = self._kparams_for(pts)  # once for the whole call (sigma=None: median over K(X,T))
         for s in range(0, m, chunk):
             e = min(m, s + chunk)
             self._predict_into(pts[s:e], out[:, s:e], kparams)
@@ -153,19 +153,20 @@ class KernelSR:
             ev.record()
             with torch.cuda.stream(cs):
                 cs.wait_event(ev)
-                for t in range(Th):  # row segments are contiguous on both sides: plain async memcpys
-                    host[t, s:e].copy_(out[t, s:e], non_blocking=True)
+                # Th row segments of this column block -> pinned host, one strided enqueue
+                _lib.call("socks_copy2d", host.data_ptr() + 8 * s, 8 * m, out.data_ptr() + 8 * s, 8 * out.stride(0),
+                          8 * (e - s), Th, 2, cs.cuda_stream)
         cs.synchronize()
         return finish()
 
-    def predict_dev(self, pts):
+    def predict_dev(self, pts, kparams=None):
         """Device in, device out: (m, d) test points -> (time_horizon, m) safety probabilities."""
         m = pts.shape[0]
         Th = int(self.time_horizon)
         out = dv.empty(max(Th, 1), max(m, 1))[:Th, :m]
         if m == 0 or Th == 0:
             return out
-        self._predict_into(pts, out)
+        self._predict_into(pts, out, kparams)
         return out
 
     def _cached(self, name, shape):
@@ -177,20 +178,39 @@ class KernelSR:
 
     max_launch_points = 1 << 20  # bounds the per-split partial-sum workspace (16 * splits * 8 B per point)
 
+    def _packed(self, kparams):
+        """Packed operand of the predict kernels (socks_sr_pack): a function of the fitted state and the bandwidth,
+        so it is built once per fit (once per call only when sigma=None makes the bandwidth data dependent)."""
+        key = (float(kparams[0]), int(kparams[1]), self._vf.data_ptr(), self._w.data_ptr())
+        if getattr(self, "_pack_key", None) != key:
+            Th = int(self.time_horizon)
+            self._pack = dv.work(_lib.load().socks_sr_pack_bytes(self._n, self._d, Th))
+            _lib.call("socks_sr_pack", dv.ptr(self._Xd), dv.ptr(self._w), dv.ptr(self._vf), self._n, self._n, self._d,
+                      key[0], key[1], Th, dv.ptr(self._pack), dv.stream())
+            self._pack_key = key
+        return self._pack
+
+    def _kparams_for(self, pts):
+        """(scale, divide) for K(X, pts).  With sigma=None the reference takes the median over the whole
+        len(X) x len(T) distance matrix (metrics.py:130-131), which this path would have to materialise."""
+        sharded_bandwidth_guard(self._spec)
+        return self._spec.params_for(self._Xd, pts)
+
     def _predict_into(self, pts, out, kparams=None):
         m = pts.shape[0]
         if kparams is None:
-            kparams = self._spec.params_for(self._Xd, pts)
+            kparams = self._kparams_for(pts)
         if m > self.max_launch_points:
             for s in range(0, m, self.max_launch_points):
                 e = min(m, s + self.max_launch_points)
                 self._predict_into(pts[s:e], out[:, s:e], kparams)
             return
         scale, divide = kparams
-        nbytes = _lib.load().socks_sr_predict_work_bytes(self._n, m)
+        pack = self._packed(kparams)
+        nbytes = _lib.load().socks_sr_predict_packed_work_bytes(self._n, m)
         work = self._cached("work", ((nbytes + 7) // 8 + 2,))
-        _lib.call("socks_sr_predict", dv.ptr(self._Xd), dv.ptr(self._w), dv.ptr(self._vf), self._n, self._n, self._d,
-                  float(scale), int(divide), dv.ptr(pts), m, dv.ptr(self._tubes), PROBLEM_CODE[self.problem],
+        _lib.call("socks_sr_predict_packed", dv.ptr(pack), dv.ptr(self._Xd), self._n, self._d, float(scale),
+                  int(divide), dv.ptr(pts), m, dv.ptr(self._tubes), PROBLEM_CODE[self.problem],
                   int(self.time_horizon), dv.ptr(out), out.stride(0), dv.ptr(work), int(self.predict_variant),
                   dv.stream())
 

@@ -12,7 +12,7 @@ import numpy as np
 from socks_b200 import _device as dv
 from socks_b200 import _lib
 from socks_b200.algorithms.reach.common import PROBLEM_CODE, pack_tubes
-from socks_b200.kernel.metrics import factorize, gram_dev, resolve_kernel
+from socks_b200.kernel.metrics import factorize, gram_dev, resolve_kernel, sharded_bandwidth_guard
 from socks_b200.sampling.transform import transpose_sample
 
 logger = logging.getLogger(__name__)
@@ -137,7 +137,7 @@ class KernelMaximalSR:
         self._validate_data(T)
         return self.predict_dev(dv.to_dev(dv.as2d(T))).cpu().numpy()
 
-    def predict_dev(self, pts):
+    def predict_dev(self, pts, kparams=None):
         m = pts.shape[0]
         Th = int(self.time_horizon)
         n, d, P = self._n, self._d, self._P
@@ -147,7 +147,9 @@ class KernelMaximalSR:
             return out
         st = dv.stream()
         prob = PROBLEM_CODE[self.problem]
-        kparams = self._spec.params_for(self._Xd, pts)
+        if kparams is None:
+            sharded_bandwidth_guard(self._spec)
+            kparams = self._spec.params_for(self._Xd, pts)
         # all rows at once: r = 0 normaliser, r = 1..T-1 time steps 0..T-2
         R = Th
         ldbm = -(-R * P // 128) * 128

@@ -461,12 +461,15 @@ static void potrf_inv_rec(CholCtx& cx, double* A, int64_t lda, double* M, int64_
 }
 
 static int chol_configure() {
-    static bool done = false;
-    if (done) return SOCKS_OK;
+    static std::atomic<bool> done[SOCKS_MAX_DEVICES];  // dynamic-smem opt-in is per device
+    int dev = 0;
+    SOCKS_CUDA(cudaGetDevice(&dev));
+    const bool tracked = dev >= 0 && dev < SOCKS_MAX_DEVICES;
+    if (tracked && done[dev].load(std::memory_order_acquire)) return SOCKS_OK;
     SOCKS_CUDA(cudaFuncSetAttribute(potf2_inv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM));
     SOCKS_CUDA(cudaFuncSetAttribute(potf2_inv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM));
     SOCKS_CUDA(cudaFuncSetAttribute(trsm_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
-    done = true;
+    if (tracked) done[dev].store(true, std::memory_order_release);
     return SOCKS_OK;
 }
 

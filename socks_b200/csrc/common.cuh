@@ -9,6 +9,7 @@
 namespace socks {
 
 constexpr int TILE = SOCKS_TILE;
+constexpr int SOCKS_MAX_DEVICES = 64;  // per-device one-time kernel attribute flags
 
 void set_error(const char* fmt, ...);
 

@@ -92,9 +92,21 @@ __device__ __forceinline__ void exp_scaled_x4(const double (&d2)[4], double (&ou
     for (int i = 0; i < 4; ++i) p[i] = fma(p[i], r[i], P.c1);
 #pragma unroll
     for (int i = 0; i < 4; ++i) p[i] = p[i] * r[i];
-    // results near or below the normal range (x < ~-707) need the two-step scaling: test once for all four
-    const int kmin = min(min(k[0], k[1]), min(k[2], k[3]));
-    if ((kmin >> 11) >= -1020) {
+    // Fast path iff every k lies in [-1020*2048, 0].  The test uses the full 64-bit integer bits(t) - bits(magic)
+    // (= k exactly while |k| < 2^51), not the 32-bit low word: for pairs more than ~1200 sigma apart
+    // (|kmul d2| >= 2^31 ln2/2048 = 7.3e5) the low word wraps and would otherwise pass for a small exponent.
+    // NaN / inf arguments land on the slow path as well.
+    const long long kMagicBits = 0x4338000000000000LL;
+    const long long kSpan = 1020LL * 2048LL;
+    long long k64[4];
+    unsigned long long umax = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        k64[i] = __double_as_longlong(t[i]) - kMagicBits;
+        const unsigned long long u = (unsigned long long)(k64[i] + kSpan);
+        umax = u > umax ? u : umax;
+    }
+    if (umax <= (unsigned long long)kSpan) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const double res = fma(T[i], p[i], T[i]);
@@ -105,17 +117,17 @@ __device__ __forceinline__ void exp_scaled_x4(const double (&d2)[4], double (&ou
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         double res = fma(T[i], p[i], T[i]);
-        int e = k[i] >> 11;
-        if (e < -1020) {
+        if (k64[i] < -kSpan || k64[i] > 0) {
             const double x = d2[i] * P.kmul;
-            if (!(x >= -800.0)) {
+            if (!(x >= -800.0)) {  // underflows to exactly 0 (as numpy's exp); NaN propagates
                 out[i] = (x != x) ? x : 0.0;
                 continue;
             }
-            e += 1000;
+            // -800 <= x: k64 >= -2.4e6 fits the low word; two-step scaling so subnormals round like IEEE
+            const int e = (k[i] >> 11) + 1000;
             res = __hiloint2double(__double2hiint(res) + (e << 20), __double2loint(res)) * 0x1p-1000;
         } else {
-            res = __hiloint2double(__double2hiint(res) + (e << 20), __double2loint(res));
+            res = __hiloint2double(__double2hiint(res) + ((k[i] >> 11) << 20), __double2loint(res));
         }
         out[i] = res;
     }

@@ -14,6 +14,8 @@
 // units of 128) and `lower_only` (skip output tiles strictly above the block diagonal).
 // Default tile configuration: 64 x 64 CTA tiles (4 warps of 32 x 32), 3 stages, three CTAs per SM.
 #pragma once
+#include <atomic>
+
 #include "common.cuh"
 
 namespace socks {
@@ -165,11 +167,15 @@ inline cudaError_t gemm_f64_launch(const double* A, int64_t lda, const double* B
                                    int lower_only, cudaStream_t st) {
     using Cfg = GemmCfg<BM, BN, WM, WN, STAGES>;
     auto kern = gemm_f64_kernel<TA, TB, BM, BN, WM, WN, STAGES, MINB>;
-    static bool configured = false;
-    if (!configured) {
+    // the opt-in to > 48 KB of dynamic shared memory is a per-DEVICE attribute: track it per device ordinal
+    static std::atomic<bool> configured[SOCKS_MAX_DEVICES];
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess) return e0;
+    if (dev < 0 || dev >= SOCKS_MAX_DEVICES || !configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < SOCKS_MAX_DEVICES) configured[dev].store(true, std::memory_order_release);
     }
     dim3 grid((unsigned)(n / BN), (unsigned)(m / BM));
     kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, flags, lower_only);

@@ -122,6 +122,9 @@ def sqdist_dev(Xd, Yd, squared=True):
 def _median_sqdist(Xd, Yd, squared=True):
     """np.median of the (squared) distance matrix (metrics.py:130-131, :199-200): mean of the two middle order
     statistics for an even count.  Distances come from the CUDA kernel; torch.kthvalue only selects."""
+    if Xd.shape[0] * Yd.shape[0] * 8 > MEDIAN_BYTES_LIMIT:
+        raise ValueError(f"sigma=None takes the median of the full {Xd.shape[0]} x {Yd.shape[0]} distance matrix "
+                         "(metrics.py:130-131), which does not fit the device workspace limit; pass an explicit sigma.")
     D = sqdist_dev(Xd, Yd, squared).reshape(-1)
     cnt = D.numel()
     hi = torch.kthvalue(D, cnt // 2 + 1).values
@@ -129,6 +132,19 @@ def _median_sqdist(Xd, Yd, squared=True):
         return float(hi)
     lo = torch.kthvalue(D, cnt // 2).values
     return float((lo + hi) / 2)  # same rounding as numpy's mean of the two middle values
+
+
+MEDIAN_BYTES_LIMIT = 16 << 30  # largest distance matrix the median heuristic may materialise on the device
+
+
+def sharded_bandwidth_guard(spec):
+    """sigma=None makes the bandwidth a function of ALL test points: a rank that only sees its shard would use a
+    different kernel than the single-GPU / reference run.  Raise instead of silently diverging."""
+    import torch.distributed as dist
+
+    if spec.data_dependent and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        raise ValueError("sigma=None (median heuristic) depends on ALL test points: compute the bandwidth once on the "
+                         "full set and pass kparams to predict_dev on every rank.")
 
 
 class Factorization:

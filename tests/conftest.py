@@ -13,13 +13,19 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu under gpurun)")
-    # the CUDA library is a build artefact (git-ignored): build it once if this is a fresh checkout
-    lib = os.path.join(ROOT, "socks_b200", "libsocksb200.so")
-    if not os.path.exists(lib):
-        import subprocess
+    # the CUDA library is a build artefact (git-ignored).  `make` is incremental: it rebuilds when any csrc/*.cu,
+    # *.cuh or the public header is newer than the .so, so a stale binary is never tested; a failed build fails loudly.
+    import shutil
+    import subprocess
 
-        subprocess.run(["make", "-C", os.path.join(ROOT, "socks_b200", "csrc"), "-j", "8"], check=False,
-                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    csrc = os.path.join(ROOT, "socks_b200", "csrc")
+    lib = os.path.join(ROOT, "socks_b200", "libsocksb200.so")
+    if shutil.which("nvcc") and shutil.which("make"):
+        r = subprocess.run(["make", "-C", csrc, "-j", "8"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise pytest.UsageError("building socks_b200/libsocksb200.so failed:\n" + r.stdout[-4000:])
+    elif not os.path.exists(lib):
+        raise pytest.UsageError("socks_b200/libsocksb200.so is missing and nvcc/make are not available to build it")
 
 
 def load_golden(name):
