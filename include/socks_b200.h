@@ -39,6 +39,11 @@ extern "C" {
 
 #define SOCKS_KERNEL_RBF 0   /* exp(|x-y|^2 (*|/) scale), gym_socks/kernel/metrics.py:69-138  */
 #define SOCKS_KERNEL_ABEL 1  /* exp(|x-y|   (*|/) scale), gym_socks/kernel/metrics.py:174-206 */
+/* sklearn.metrics.pairwise kernels the reference accepts through its `kernel_fn` protocol (metrics.py:239-241; pinned
+ * by gym_socks/kernel/tests/test_kernel.py:18,132-147) */
+#define SOCKS_KERNEL_LINEAR 2     /* x.y                                                    */
+#define SOCKS_KERNEL_POLY 3       /* (scale x.y + coef0)^degree          (scale = gamma)    */
+#define SOCKS_KERNEL_LAPLACIAN 4  /* exp(scale |x-y|_1)                  (scale = -gamma)   */
 
 #define SOCKS_PROBLEM_THT 0  /* gym_socks/algorithms/reach/common.py:42-69 */
 #define SOCKS_PROBLEM_FHT 1  /* gym_socks/algorithms/reach/common.py:8-39  */
@@ -81,6 +86,16 @@ int socks_gram_sym(const double* Z, int64_t n, int d, double scale, int divide, 
                    int64_t ldg, socks_stream_t stream);
 int socks_gram_sym_kernel(int kind, const double* Z, int64_t n, int d, double scale, int divide, double diag_add,
                           double* G, int64_t ldg, socks_stream_t stream);
+
+/* Any kernel family above: K = rowscale * k(X, Y), and the padded G = k(X,X) [* k(U,U)] + diag_add I of
+ * metrics.py:264-280 with the SAME kernel for states and actions (U may be NULL).  coef0 / degree are read by
+ * SOCKS_KERNEL_POLY only.  RBF/Abel without U run the tiled kernels above. */
+int socks_gram_family(int kind, const double* X, int64_t n, const double* Y, int64_t m, int d, double scale,
+                      int divide, double coef0, double degree, const double* rowscale, double* K, int64_t ldk,
+                      socks_stream_t stream);
+int socks_gram_sym_family(int kind, const double* X, int64_t n, int dx, const double* U, int du, double scale,
+                          int divide, double coef0, double degree, double diag_add, double* G, int64_t ldg,
+                          socks_stream_t stream);
 
 /* ---- Regularised solve: gym_socks/kernel/metrics.py:278-280 (inv(K + lambda N I)) ------ */
 

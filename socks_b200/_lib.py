@@ -23,6 +23,8 @@ SIGNATURES = {
     "socks_copy2d": (_I, [_P, _L, _P, _L, _L, _L, _I, _P]),
     "socks_gram_rbf": (_I, [_P, _L, _P, _L, _I, _D, _I, _P, _P, _L, _P]),
     "socks_gram_kernel": (_I, [_I, _P, _L, _P, _L, _I, _D, _I, _P, _P, _L, _P]),
+    "socks_gram_family": (_I, [_I, _P, _L, _P, _L, _I, _D, _I, _D, _D, _P, _P, _L, _P]),
+    "socks_gram_sym_family": (_I, [_I, _P, _L, _I, _P, _I, _D, _I, _D, _D, _D, _P, _L, _P]),
     "socks_dist": (_I, [_P, _L, _P, _L, _I, _P, _L, _P]),
     "socks_gram_sym_kernel": (_I, [_I, _P, _L, _I, _D, _I, _D, _P, _L, _P]),
     "socks_colsumsq": (_I, [_P, _L, _L, _L, _P, _P, _P]),

@@ -171,6 +171,69 @@ __global__ void gram_sym_generic_kernel(const double* __restrict__ Z, int64_t n,
     G[i * ldg + j] = v;
 }
 
+// ---- kernel families beyond RBF/Abel (sklearn.metrics.pairwise kernels the reference accepts as `kernel_fn`,
+// gym_socks/kernel/metrics.py:239-241, pinned by gym_socks/kernel/tests/test_kernel.py:18,132-147) ------------
+//   LINEAR     x.y                              sklearn linear_kernel
+//   POLY       (scale x.y + coef0)^degree       sklearn polynomial_kernel (scale = gamma)
+//   LAPLACIAN  exp(scale |x - y|_1)             sklearn laplacian_kernel (scale = -gamma)
+// plus RBF and Abel through the same code, so that the product Gram K(X,X) * K(U,U) (metrics.py:268-276) exists
+// for every family.  One entry per thread, runtime d: these families are off the benchmarked path.
+struct KFamily {
+    int kind;
+    KScale ks;
+    double coef0, degree;
+};
+
+__device__ __forceinline__ double family_value(const KFamily& f, const double* __restrict__ x,
+                                               const double* __restrict__ y, int d) {
+    if (f.kind == SOCKS_KERNEL_RBF || f.kind == SOCKS_KERNEL_ABEL) {
+        double acc = 0.0;
+        for (int k = 0; k < d; ++k) {
+            const double t = __dsub_rn(__ldg(y + k), __ldg(x + k));
+            acc = __dadd_rn(acc, __dmul_rn(t, t));
+        }
+        return exp(rbf_arg(f.kind == SOCKS_KERNEL_ABEL ? sqrt(acc) : acc, f.ks));
+    }
+    if (f.kind == SOCKS_KERNEL_LAPLACIAN) {
+        double acc = 0.0;
+        for (int k = 0; k < d; ++k) acc = __dadd_rn(acc, fabs(__dsub_rn(__ldg(x + k), __ldg(y + k))));
+        return exp(rbf_arg(acc, f.ks));
+    }
+    double dot = 0.0;
+    for (int k = 0; k < d; ++k) dot = fma(__ldg(x + k), __ldg(y + k), dot);
+    if (f.kind == SOCKS_KERNEL_LINEAR) return dot;
+    return pow(__dadd_rn(__dmul_rn(dot, f.ks.scale), f.coef0), f.degree);  // K *= gamma; K += coef0; K **= degree
+}
+
+__global__ void gram_family_kernel(KFamily f, const double* __restrict__ X, int64_t n, const double* __restrict__ Y,
+                                   int64_t m, int d, const double* __restrict__ rowscale, double* __restrict__ K,
+                                   int64_t ldk) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = blockIdx.y;
+    if (j >= m || i >= n) return;
+    double v = family_value(f, X + i * d, Y + j * d, d);
+    if (rowscale) v *= __ldg(rowscale + i);
+    K[i * ldk + j] = v;
+}
+
+// Lower 128-tiles of the padded G = k(X,X) [* k(U,U)] + diag_add I; identity in the padding.
+__global__ void gram_sym_family_kernel(KFamily f, const double* __restrict__ X, int64_t n, int dx,
+                                       const double* __restrict__ U, int du, double diag_add, double* __restrict__ G,
+                                       int64_t ldg, int64_t np) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = blockIdx.y;
+    if (j >= np || i >= np || j / TILE > i / TILE) return;
+    double v;
+    if (i < n && j < n) {
+        v = family_value(f, X + i * dx, X + j * dx, dx);
+        if (U) v = __dmul_rn(family_value(f, U + i * du, U + j * du, du), v);  // np.multiply(kernel_fn(U, V), K)
+        if (i == j) v += diag_add;
+    } else {
+        v = (i == j) ? 1.0 : 0.0;
+    }
+    G[i * ldg + j] = v;
+}
+
 template <int MODE>
 static int launch_cross(const double* X, int64_t n, const double* Y, int64_t m, int d, KScale ks,
                         const double* rowscale, double* K, int64_t ldk, cudaStream_t st) {
@@ -297,4 +360,57 @@ extern "C" int socks_gram_sym(const double* Z, int64_t n, int d, double scale, i
                               int64_t ldg, socks_stream_t stream) {
     int rc = gram_sym_impl(SOCKS_KERNEL_RBF, Z, n, d, scale, divide, diag_add, G, ldg, stream);
     return rc < -1 ? rc + 1 : rc;
+}
+
+static int check_family(int kind, double scale, int divide, double degree, int argk) {
+    SOCKS_CHECK_ARG(kind >= SOCKS_KERNEL_RBF && kind <= SOCKS_KERNEL_LAPLACIAN, 1);
+    SOCKS_CHECK_ARG(scale == scale && (!divide || scale != 0.0), argk);
+    SOCKS_CHECK_ARG(kind != SOCKS_KERNEL_POLY || degree == degree, argk + 3);
+    return SOCKS_OK;
+}
+
+extern "C" int socks_gram_family(int kind, const double* X, int64_t n, const double* Y, int64_t m, int d, double scale,
+                                 int divide, double coef0, double degree, const double* rowscale, double* K,
+                                 int64_t ldk, socks_stream_t stream) {
+    int rc = check_family(kind, scale, divide, degree, 7);
+    if (rc) return rc;
+    SOCKS_CHECK_ARG(n >= 0 && n <= 65535 * 65535LL, 3);
+    SOCKS_CHECK_ARG(m >= 0, 5);
+    SOCKS_CHECK_ARG(d >= 1 && d <= SOCKS_MAX_DIM, 6);
+    SOCKS_CHECK_ARG(ldk >= m, 13);
+    if (n == 0 || m == 0) return SOCKS_OK;
+    SOCKS_CHECK_ARG(X && Y && K, 2);
+    if (kind <= SOCKS_KERNEL_ABEL) {
+        rc = gram_kernel_impl(kind, X, n, Y, m, d, scale, divide, rowscale, K, ldk, stream);
+        return rc;
+    }
+    const KFamily f{kind, make_kscale(scale, divide), coef0, degree};
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int64_t r0 = 0; r0 < n; r0 += 65535) {  // grid.y limit
+        const int64_t rows = (n - r0 < 65535) ? (n - r0) : 65535;
+        gram_family_kernel<<<dim3((unsigned)ceil_div(m, 256), (unsigned)rows), 256, 0, st>>>(
+            f, X + r0 * d, rows, Y, m, d, rowscale ? rowscale + r0 : nullptr, K + r0 * ldk, ldk);
+    }
+    SOCKS_CHECK_LAUNCH();
+    return SOCKS_OK;
+}
+
+extern "C" int socks_gram_sym_family(int kind, const double* X, int64_t n, int dx, const double* U, int du,
+                                     double scale, int divide, double coef0, double degree, double diag_add,
+                                     double* G, int64_t ldg, socks_stream_t stream) {
+    int rc = check_family(kind, scale, divide, degree, 7);
+    if (rc) return rc;
+    SOCKS_CHECK_ARG(X != nullptr, 2);
+    SOCKS_CHECK_ARG(n >= 1, 3);
+    SOCKS_CHECK_ARG(dx >= 1 && dx <= SOCKS_MAX_DIM, 4);
+    SOCKS_CHECK_ARG(U == nullptr || (du >= 1 && du <= SOCKS_MAX_DIM), 6);
+    const int64_t np = socks_padded_dim(n);
+    SOCKS_CHECK_ARG(np <= 65535, 3);
+    SOCKS_CHECK_ARG(G != nullptr && (reinterpret_cast<uintptr_t>(G) & 15) == 0, 12);
+    SOCKS_CHECK_ARG(ldg >= np && ldg % 2 == 0, 13);
+    const KFamily f{kind, make_kscale(scale, divide), coef0, degree};
+    gram_sym_family_kernel<<<dim3((unsigned)ceil_div(np, 256), (unsigned)np), 256, 0, (cudaStream_t)stream>>>(
+        f, X, n, dx, U, du, diag_add, G, ldg, np);
+    SOCKS_CHECK_LAUNCH();
+    return SOCKS_OK;
 }

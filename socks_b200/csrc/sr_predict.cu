@@ -40,6 +40,7 @@ constexpr int SP_SPLIT = 2048;   // samples per CTA (blockIdx.y): FIXED, so the 
 constexpr int SP_HDR = 16;       // header doubles of the packed state: [0] factored-ok, [1] R_x^2, [2..10) centre
 constexpr double SP_RANGE = 600.0;
 
+
 __host__ __device__ inline int64_t sp_npad(int64_t n) { return (n + SP_TS - 1) / SP_TS * SP_TS; }
 inline int sp_blocks(int T) { return T <= 1 ? 1 : (T - 1 + SOCKS_SR_ROWS - 2) / (SOCKS_SR_ROWS - 1); }
 
@@ -159,11 +160,11 @@ __device__ __forceinline__ void sp_store_partials(const double (&acc)[Q][2][2], 
 // s = 4 ks + lr against the points {8 q + lq}: exactly the B-fragment layout of mma.m8n8k4.
 // ps = p' * (2 g * 2048/ln2): the dot product s = ps . x' is the exponent in table steps; t = s + 1.5*2^52 rounds
 // it (k = low word of t), f = s - k in [-1/2, 1/2], 2^(f/2048) = 1 + f (d1 + f d2), 2^(k/2048) = 2^(k>>11) * tbl[k & 2047].
-template <int D, int WARPS, int MINB, int Q>
+template <int D, int WARPS, int MINB, int Q, bool HI, int U>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     sr_predict_fast_kernel(const double* __restrict__ Xc, const double* __restrict__ coefF, int64_t n_pad,
                            const double* __restrict__ pts, int64_t m, const double* __restrict__ hdr, double pscale,
-                           int rows, int force_direct, double* __restrict__ part, int64_t ldp) {
+                           int force_direct, double* __restrict__ part, int64_t ldp) {
     if (force_direct || hdr[0] == 0.0) return;  // launch-uniform: the direct kernel handles this launch
     __shared__ __align__(16) double sx[2][SP_TS * D];
     __shared__ __align__(16) double sc[2][SP_TS * SR_CP];
@@ -187,9 +188,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         for (int h = 0; h < 2; ++h) acc[q][h][0] = acc[q][h][1] = 0.0;
 
     const double kMagic = 6755399441055744.0;          // 1.5 * 2^52
-    const double kD1 = 3.38450771757785795e-04;         // ln2 / 2048
     const double kD2 = 5.72744624533987700e-08;         // (ln2 / 2048)^2 / 2
-    const bool hi_rows = rows > 8;
+    // ln2 / 2048, held in a register: as a literal the compiler re-materialises it (two moves) in every iteration,
+    // and every non-FP64 instruction in this loop costs about one FP64-pipe cycle (profiles/r2_predict_*.txt)
+    double kD1;
+    asm("mov.f64 %0, 0d3F362E42FEFA39EF;" : "=d"(kD1));
+    const char* etb = reinterpret_cast<const char*>(etbl);
     const int tile0 = blockIdx.y * (SP_SPLIT / SP_TS);
     const int tile1 = min((int)(n_pad / SP_TS), tile0 + SP_SPLIT / SP_TS);
     sp_load_stage<D>(sx[0], sc[0], Xc, coefF, n_pad, (int64_t)tile0 * SP_TS, tid, WARPS * 32);
@@ -201,42 +205,56 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         if (tile + 1 < tile1)
             sp_load_stage<D>(sx[cur ^ 1], sc[cur ^ 1], Xc, coefF, n_pad, (int64_t)(tile + 1) * SP_TS, tid, WARPS * 32);
         cp_async_commit();
-        const double* x_s = sx[cur];
-        const double* c_s = sc[cur];
-#pragma unroll 2
-        for (int ks = 0; ks < SP_TS / 4; ++ks) {
-            const int s = ks * 4 + lr;
-            double xs[D];
+        // this lane's sample row (lr) and coefficient row (lq) of the stage; the unrolled body addresses them with
+        // immediate offsets and the pointers advance once per U sample quads
+        const double* xp = sx[cur] + lr * D;
+        const double* cp = sc[cur] + lr * SR_CP + lq;
+#pragma unroll 1
+        for (int kb = 0; kb < SP_TS / 4; kb += U) {
 #pragma unroll
-            for (int k = 0; k < D; ++k) xs[k] = x_s[s * D + k];
-            const double a0 = c_s[s * SR_CP + lq];
-            const double a1 = c_s[s * SR_CP + lq + 8];
-            double sv[Q], t[Q], f[Q], pl[Q], tb[Q];
+            for (int u = 0; u < U; ++u) {
+                double xs[D];
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                double a = ps[q][0] * xs[0];
+                for (int k = 0; k < D; ++k) xs[k] = xp[u * 4 * D + k];
+                const double a0 = cp[u * 4 * SR_CP];
+                const double a1 = HI ? cp[u * 4 * SR_CP + 8] : 0.0;
+                double sv[Q], t[Q], f[Q], pl[Q], tb[Q];
 #pragma unroll
-                for (int k = 1; k < D; ++k) a = fma(ps[q][k], xs[k], a);
-                sv[q] = a;
+                for (int q = 0; q < Q; ++q) {
+                    double a = ps[q][0] * xs[0];
+#pragma unroll
+                    for (int k = 1; k < D; ++k) a = fma(ps[q][k], xs[k], a);
+                    sv[q] = a;
+                }
+#pragma unroll
+                for (int q = 0; q < Q; ++q) t[q] = sv[q] + kMagic;
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+                    tb[q] = *reinterpret_cast<const double*>(etb + ((__double2loint(t[q]) << 3) & ((EXP_TBL2 - 1) << 3)));
+#pragma unroll
+                // k back to double by I2F.F64 (conversion unit) rather than t - magic (one more FP64-pipe DADD): measured
+                // 2 % faster, same bits (k is exact either way)
+                for (int q = 0; q < Q; ++q) f[q] = sv[q] - __int2double_rn(__double2loint(t[q]));
+#pragma unroll
+                for (int q = 0; q < Q; ++q) pl[q] = fma(f[q], kD2, kD1);
+#pragma unroll
+                for (int q = 0; q < Q; ++q) pl[q] = pl[q] * f[q];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const double res = fma(tb[q], pl[q], tb[q]);
+                    // 2^(k >> 11): high word += (k >> 11) << 20 = (k & ~2047) * 512, as LOP3 + IMAD (the compiler's
+                    // own choice is shift + mask + add)
+                    int hi2;
+                    asm("{\n\t.reg .b32 km;\n\tand.b32 km, %1, 0xfffff800;\n\tmad.lo.s32 %0, km, 512, %2;\n\t}"
+                        : "=r"(hi2)
+                        : "r"(__double2loint(t[q])), "r"(__double2hiint(res)));
+                    const double kv = __hiloint2double(hi2, __double2loint(res));
+                    dmma884(acc[q][0][0], acc[q][0][1], a0, kv);
+                    if (HI) dmma884(acc[q][1][0], acc[q][1][1], a1, kv);
+                }
             }
-#pragma unroll
-            for (int q = 0; q < Q; ++q) t[q] = sv[q] + kMagic;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) tb[q] = etbl[__double2loint(t[q]) & (EXP_TBL2 - 1)];
-#pragma unroll
-            for (int q = 0; q < Q; ++q) f[q] = sv[q] - (t[q] - kMagic);
-#pragma unroll
-            for (int q = 0; q < Q; ++q) pl[q] = fma(f[q], kD2, kD1);
-#pragma unroll
-            for (int q = 0; q < Q; ++q) pl[q] = pl[q] * f[q];
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const double res = fma(tb[q], pl[q], tb[q]);
-                const int e = (__double2loint(t[q]) >> 11) << 20;
-                const double kv = __hiloint2double(__double2hiint(res) + e, __double2loint(res));
-                dmma884(acc[q][0][0], acc[q][0][1], a0, kv);
-                if (hi_rows) dmma884(acc[q][1][0], acc[q][1][1], a1, kv);
-            }
+            xp += U * 4 * D;
+            cp += U * 4 * SR_CP;
         }
     }
     sp_store_partials<Q>(acc, part, ldp, pbase, m, lq, lr);
@@ -502,13 +520,17 @@ static void launch_tensor(const PackView& v, const double* X, int64_t n, const d
     const double* ce = v.coefE + (int64_t)b * v.n_pad * SR_CP;
     const double pscale = -2.0 * kmul * (2048.0 / 0.693147180559945309417232121458176568);
     const bool small = shape == 2 || (shape == 0 && small_tiles(m, splits, 8 * Q * 8));
+#define SOCKS_FAST_LAUNCH(W, MB, HI, U)                                                                              \
+    sr_predict_fast_kernel<D, W, MB, Q, HI, U><<<dim3((unsigned)ceil_div(m, W * Q * 8), (unsigned)splits), W * 32, 0, st>>>( \
+        v.Xc, cf, v.n_pad, pts, m, v.hdr, pscale, force_direct, part, ldp)
+    // 8 warps x 2 CTAs/SM (unroll 2) and 4 warps x 4 CTAs/SM (unroll 4): best of the shape sweep in
+    // profiles/r2_predict_sweep.json (all shapes within 4 %)
     if (small) {
-        sr_predict_fast_kernel<D, 4, 6, Q><<<dim3((unsigned)ceil_div(m, 4 * Q * 8), (unsigned)splits), 128, 0, st>>>(
-            v.Xc, cf, v.n_pad, pts, m, v.hdr, pscale, R, force_direct, part, ldp);
+        if (R > 8) SOCKS_FAST_LAUNCH(4, 4, true, 4); else SOCKS_FAST_LAUNCH(4, 4, false, 4);
     } else {
-        sr_predict_fast_kernel<D, 8, 3, Q><<<dim3((unsigned)ceil_div(m, 8 * Q * 8), (unsigned)splits), 256, 0, st>>>(
-            v.Xc, cf, v.n_pad, pts, m, v.hdr, pscale, R, force_direct, part, ldp);
+        if (R > 8) SOCKS_FAST_LAUNCH(8, 2, true, 2); else SOCKS_FAST_LAUNCH(8, 2, false, 2);
     }
+#undef SOCKS_FAST_LAUNCH
     const ExpScaled ex = make_exp_scaled(kmul);
     sr_predict_dmma_kernel<D, 8, 3><<<dim3((unsigned)ceil_div(m, 256), (unsigned)splits), 256, 0, st>>>(
         X, ce, n, v.n_pad, pts, m, v.hdr, ex, R, force_direct, part, ldp);

@@ -44,7 +44,7 @@ def test_gpu_arm_prints_one_contract_line():
     assert len(lines) == 1
     line = json.loads(lines[0])
     assert line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] >= 3
-    assert line["gpu_launches"] == 8 and line["dtype"] == "f64" and line["data"] == "synthetic"
+    assert line["gpu_launches"] == 8  # 4 kernels per predict step x 2 steps and line["dtype"] == "f64" and line["data"] == "synthetic"
     r = line["roofline"]
     assert r["bound"] in ("hbm", "tensor") and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     e = line["e2e"]

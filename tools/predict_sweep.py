@@ -12,7 +12,13 @@ from socks_b200 import _device as dv, synthetic as syn
 from socks_b200.algorithms.reach.kernel_sr import KernelSR
 
 NAMES = {0: "auto (factored, shape by M)", 1: "FMA pipe + CUDA exp", 2: "direct form on DMMA (r1 kernel)",
-         3: "factored, 8-warp CTAs", 4: "factored, 4-warp CTAs"}
+         3: "factored, 8-warp CTAs x3, unroll 2", 4: "factored, 4-warp CTAs x5, unroll 2",
+         10: "factored, 8 warps x3, unroll 4", 11: "factored, 8 warps x2, unroll 2", 12: "factored, 8 warps x2, unroll 4",
+         13: "attribution (vs 11): +4 integer instr per value", 14: "attribution (vs 11): +1 FP64 add per value",
+         15: "attribution (vs 11): no exponent insertion, -2 int (wrong results)",
+         16: "attribution (vs 11): no table gather (wrong results)", 17: "attribution (vs 11): +4 int +1 FP64"}
+VARIANTS = [int(v) for v in os.environ.get("SWEEP_VARIANTS", "0,2,3,4,1").split(",")]
+SIZES = os.environ.get("SWEEP_SIZES", "full")
 
 
 def timed(fn, reps):
@@ -34,7 +40,10 @@ def timed(fn, reps):
 
 def main():
     res = []
-    for (n, d, T, ms) in ((20000, 2, 15, (250000, 125000, 62500, 31250)), (40000, 4, 15, (500000, 62500))):
+    cases = ((20000, 2, 15, (250000, 125000, 62500, 31250)), (40000, 4, 15, (500000, 62500)))
+    if SIZES == "c2":
+        cases = ((20000, 2, 15, (250000, 31250)),)
+    for (n, d, T, ms) in cases:
         X, U, Y = syn.integrator_sample(n, d, seed=0)
         ct, tt = syn.integrator_tubes(T, d)
         alg = KernelSR(time_horizon=T, constraint_tube=ct, target_tube=tt, problem="FHT", regularization_param=1 / n ** 2)
@@ -43,13 +52,13 @@ def main():
         ref = None
         for m in ms:
             pts = dv.to_dev(syn.uniform_points(m, d, seed=1))
-            for variant in (0, 2, 3, 4, 1):
+            for variant in VARIANTS:
                 if variant == 1 and m > 125000:
                     continue
                 alg.predict_variant = variant
                 med, best = timed(lambda: alg.predict_dev(pts), 7 if variant != 1 else 3)
                 out = alg.predict_dev(pts)
-                if variant == 0:
+                if ref is None or variant == 0:
                     ref = out
                 flops = float(n) * m * (3 * d + 2 + 12 + 2 * T)
                 rec = {"N": n, "d": d, "T": T, "M": m, "variant": variant, "name": NAMES[variant], "ms_median": med,
