@@ -90,9 +90,9 @@ class KernelControlBwd:
         Xd, Yd, Ud, Ad = dv.to_dev(Xh), dv.to_dev(Yh), dv.to_dev(Uh), dv.to_dev(Ah)
         self._Xd = Xd
         logger.debug("Computing covariance matrices.")
-        self._CUA = gram_dev(Ud, Ad, self._spec.params_for(Ud, Ad), kind=self._spec.kind, ld=P)
+        self._CUA = gram_dev(Ud, Ad, self._spec.params_for(Ud, Ad), kind=self._spec.kind, extra=self._spec.extra, ld=P)
         Kmat = dv.zeros(npad, npad)  # K(X, Y), the GEMM's (K x m) left operand, zero padded
-        gram_dev(Xd, Yd, self._spec.params_for(Xd, Yd), kind=self._spec.kind, out=Kmat, ld=npad)
+        gram_dev(Xd, Yd, self._spec.params_for(Xd, Yd), kind=self._spec.kind, extra=self._spec.extra, out=Kmat, ld=npad)
         Yarr = np.array(Y)
         self.cost_fn = partial(self.cost_fn, state=Yarr)  # kernel_control_bwd.py:387
         if self.constraint_fn is not None:

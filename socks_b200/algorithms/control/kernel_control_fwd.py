@@ -86,7 +86,7 @@ class KernelControlFwd:
         self._Xd = dv.to_dev(Xh)
         Ud, Ad = dv.to_dev(Uh), dv.to_dev(Ah)
         logger.debug("Computing covariance matrix.")
-        self._CUA = gram_dev(Ud, Ad, self._spec.params_for(Ud, Ad), kind=self._spec.kind, ld=self._P)  # :200
+        self._CUA = gram_dev(Ud, Ad, self._spec.params_for(Ud, Ad), kind=self._spec.kind, extra=self._spec.extra, ld=self._P)  # :200
         Yarr = np.array(Y)
         self.cost_fn = partial(self.cost_fn, state=Yarr)  # :203
         if self.constraint_fn is not None:

@@ -52,9 +52,6 @@ class KernelSR:
     # -- validation: same order and exception types as kernel_sr.py:224-264
     def _validate_params(self, S):
         self._spec = resolve_kernel(self.kernel_fn, default_sigma=0.1)
-        if self._spec.kind != 0:
-            raise NotImplementedError("KernelSR's fused predict kernel evaluates the RBF kernel; abel_kernel is "
-                                      "supported by rbf-free paths only (SeparatingKernelClassifier)")
         if self.regularization_param is None:
             self.regularization_param = 1
         if self.time_horizon is None:
@@ -112,7 +109,7 @@ class KernelSR:
         self._tubes = pack_tubes(self.constraint_tube, self.target_tube, T, d)
         logger.debug("Computing covariance matrix.")
         ldb = dv.even(n)
-        B = gram_dev(Xd, Yd, self._spec.params_for(Xd, Yd), kind=self._spec.kind, rowscale=w, ld=ldb)  # un-normalised beta, kernel_sr.py:45
+        B = gram_dev(Xd, Yd, self._spec.params_for(Xd, Yd), kind=self._spec.kind, extra=self._spec.extra, rowscale=w, ld=ldb)  # un-normalised beta, kernel_sr.py:45
         logger.debug("Computing value functions.")
         vf = dv.empty(max(T, 1), n)
         lib = _lib.load()
@@ -205,6 +202,8 @@ class KernelSR:
                 e = min(m, s + self.max_launch_points)
                 self._predict_into(pts[s:e], out[:, s:e], kparams)
             return
+        if self._spec.kind != 0:
+            return self._predict_materialised(pts, out, kparams)
         scale, divide = kparams
         pack = self._packed(kparams)
         nbytes = _lib.load().socks_sr_predict_packed_work_bytes(self._n, m)
@@ -213,6 +212,24 @@ class KernelSR:
                   int(divide), dv.ptr(pts), m, dv.ptr(self._tubes), PROBLEM_CODE[self.problem],
                   int(self.time_horizon), dv.ptr(out), out.stride(0), dv.ptr(work), int(self.predict_variant),
                   dv.stream())
+
+    def _predict_materialised(self, pts, out, kparams):
+        """Kernel families other than RBF (abel, and sklearn's linear / polynomial / laplacian): the fused predict
+        kernel evaluates exp(-g |x - p|^2) only, so these take the path the fit uses -- B = diag(w) K(X, chunk) resident
+        in HBM, T-1 GEMV passes with the step fused (socks_sr_recursion), chunk by chunk (kernel_sr.py:329-342)."""
+        m, n = pts.shape[0], self._n
+        lib = _lib.load()
+        chunk = max(256, min(m, (1 << 28) // max(n, 1)))  # <= 2 GiB of B per chunk
+        for s in range(0, m, chunk):
+            p = pts[s:s + chunk]
+            cnt = p.shape[0]
+            ldb = dv.even(cnt)
+            B = gram_dev(self._Xd, p, kparams, kind=self._spec.kind, extra=self._spec.extra, rowscale=self._w, ld=ldb)
+            wk = dv.work(lib.socks_reduce_work_bytes(cnt) + 8 * (cnt + 2))
+            o = out[:, s:s + cnt]
+            _lib.call("socks_sr_recursion", dv.ptr(B), n, cnt, ldb, dv.ptr(p), self._d, dv.ptr(self._tubes),
+                      PROBLEM_CODE[self.problem], int(self.time_horizon), dv.ptr(self._vf), n, dv.ptr(o),
+                      out.stride(0), dv.ptr(wk), dv.stream())
 
     # -- attributes the reference exposes (kernel_sr.py:286-309)
     @property

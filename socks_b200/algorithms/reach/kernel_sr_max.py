@@ -104,11 +104,11 @@ class KernelMaximalSR:
         self._Xd, self._w = Xd, w
         self._tubes = pack_tubes(self.constraint_tube, self.target_tube, T, d)
         logger.debug("Computing covariance matrices.")
-        CUA = gram_dev(Ud, Ad, self._spec.params_for(Ud, Ad), kind=self._spec.kind, ld=P)  # (n, P) contiguous, kernel_sr_max.py:332
+        CUA = gram_dev(Ud, Ad, self._spec.params_for(Ud, Ad), kind=self._spec.kind, extra=self._spec.extra, ld=P)  # (n, P) contiguous, kernel_sr_max.py:332
         self._CUA = CUA
         # K(X, Y) as the GEMM's left operand: (K = npad rows) x (m = npad columns), zero padding
         Kmat = dv.zeros(npad, npad)
-        gram_dev(Xd, Yd, self._spec.params_for(Xd, Yd), kind=self._spec.kind, out=Kmat, ld=npad)
+        gram_dev(Xd, Yd, self._spec.params_for(Xd, Yd), kind=self._spec.kind, extra=self._spec.extra, out=Kmat, ld=npad)
         logger.debug("Computing value functions.")
         vf = dv.empty(max(T, 1), n)
         ldbm = -(-P // 128) * 128
@@ -164,7 +164,7 @@ class KernelMaximalSR:
             if cnt < mc:
                 Kmat.zero_()
             p = pts[s:s + cnt]
-            gram_dev(self._Xd, p, kparams, out=Kmat, ld=mc, kind=self._spec.kind)
+            gram_dev(self._Xd, p, kparams, out=Kmat, ld=mc, kind=self._spec.kind, extra=self._spec.extra)
             _lib.call("socks_gemm_tn", dv.ptr(Kmat), mc, dv.ptr(Bm), ldbm, dv.ptr(Cm), ldbm, mc, ldbm, npad, st)
             _lib.call("socks_srmax_step", dv.ptr(Cm), ldbm, 0, 0, cnt, P, R, 0, dv.ptr(p), d, dv.ptr(self._tubes), prob,
                       Th, dv.ptr(out[:, s:]), out.stride(0), 1, st)

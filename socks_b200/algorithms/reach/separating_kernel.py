@@ -57,7 +57,7 @@ class SeparatingKernelClassifier:
             cnt = min(mc, m - s)
             if cnt < mc:
                 Kmat.zero_()
-            gram_dev(self._Xd, pts[s:s + cnt], kp, out=Kmat, ld=mc, kind=self._spec.kind)
+            gram_dev(self._Xd, pts[s:s + cnt], kp, out=Kmat, ld=mc, kind=self._spec.kind, extra=self._spec.extra)
             # Z = M K, M lower triangular: k-range of each output tile clipped at its row block (flag 1)
             _lib.call("socks_gemm_f64", 0, 0, dv.ptr(M), npad, dv.ptr(Kmat), mc, dv.ptr(Z), mc, npad, mc, npad, 1.0, 0.0,
                       1, 0, 0, st)

@@ -4,9 +4,11 @@ Same names, argument order, defaults, assertion behaviour and return types as
 `gym_socks/kernel/metrics.py:69-138` and `:209-280`; the arithmetic runs in libsocksb200
 (gram.cu, chol.cu).  `kernel_fn` follows the reference's callable protocol
 (`kernel_fn(X, Y=None) -> (n, m) ndarray`, metrics.py:239-241) but must be recognisable as an RBF
-kernel (this package's, gym_socks's or sklearn's `rbf_kernel`, bare or wrapped in
-`functools.partial` with `sigma=` / `gamma=`): arbitrary Python callables cannot run on the GPU and
-there is no CPU fallback, so anything else raises TypeError.
+kernel (this package's or gym_socks's `rbf_kernel` / `abel_kernel`, or sklearn's `rbf_kernel`, `linear_kernel`,
+`polynomial_kernel`, `laplacian_kernel` -- the four the reference's own test feeds to `regularized_inverse`,
+`gym_socks/kernel/tests/test_kernel.py:18,132-147` -- bare or wrapped in `functools.partial` with keyword
+parameters): arbitrary Python callables cannot run on the GPU and there is no CPU fallback, so anything else
+raises TypeError.
 """
 from functools import partial
 
@@ -19,7 +21,7 @@ from socks_b200 import _lib
 __all__ = ["rbf_kernel", "abel_kernel", "euclidean_distance", "regularized_inverse", "RBFSpec", "resolve_kernel",
            "Factorization"]
 
-KIND_RBF, KIND_ABEL = 0, 1  # SOCKS_KERNEL_RBF / SOCKS_KERNEL_ABEL
+KIND_RBF, KIND_ABEL, KIND_LINEAR, KIND_POLY, KIND_LAPLACIAN = 0, 1, 2, 3, 4  # SOCKS_KERNEL_* of include/socks_b200.h
 
 
 # ----------------------------------------------------------------------------- kernel_fn protocol
@@ -31,8 +33,9 @@ class RBFSpec:
     `gamma`-style (sklearn semantics): gamma used as is; gamma=None -> 1 / n_features.
     """
 
-    def __init__(self, sigma=None, gamma=None, style="sigma", kind=KIND_RBF):
+    def __init__(self, sigma=None, gamma=None, style="sigma", kind=KIND_RBF, coef0=1.0, degree=3.0):
         self.sigma, self.gamma, self.style, self.kind = sigma, gamma, style, kind
+        self.coef0, self.degree = float(coef0), float(degree)  # polynomial_kernel only
         if style == "sigma" and sigma is not None:
             assert sigma > 0, "sigma must be a strictly positive real value."
 
@@ -40,9 +43,11 @@ class RBFSpec:
         """(scale, divide) of the C ABI for one kernel evaluation between device arrays Xd (n, d), Yd (m, d):
         k = exp(d2 / scale) with scale = -2 sigma^2 (the reference divides, metrics.py:135) or
         k = exp(d2 * scale) with scale = -gamma (sklearn multiplies)."""
-        if self.style == "gamma":
+        if self.kind == KIND_LINEAR:
+            return (1.0, 0)
+        if self.style == "gamma":  # sklearn: gamma=None -> 1 / n_features
             g = float(self.gamma) if self.gamma is not None else 1.0 / Xd.shape[1]
-            return (-g, 0)
+            return (g, 0) if self.kind == KIND_POLY else (-g, 0)
         if self.kind == KIND_ABEL:  # exp(dist / -sigma), sigma=None -> median of the distances (metrics.py:199-204)
             sigma = float(self.sigma) if self.sigma is not None else _median_sqdist(Xd, Yd, squared=False)
             return (-sigma, 1)
@@ -55,12 +60,29 @@ class RBFSpec:
         return -1.0 / scale if divide else -scale
 
     @property
+    def extra(self):
+        """(coef0, degree) of the C ABI (read by SOCKS_KERNEL_POLY only)."""
+        return (self.coef0, self.degree)
+
+    @property
+    def separable(self):
+        """k([x|u], [x'|u']) == k(x, x') k(u, u') for one shared scale (product Gram as ONE kernel on [X | U])."""
+        return self.kind == KIND_RBF
+
+    @property
     def data_dependent(self):
         return self.style == "sigma" and self.sigma is None
 
 
+_SKLEARN_KINDS = {"rbf_kernel": KIND_RBF, "linear_kernel": KIND_LINEAR, "polynomial_kernel": KIND_POLY,
+                  "laplacian_kernel": KIND_LAPLACIAN}
+_SKLEARN_KEYWORDS = {"rbf_kernel": {"gamma"}, "linear_kernel": {"dense_output"},
+                     "polynomial_kernel": {"gamma", "degree", "coef0"}, "laplacian_kernel": {"gamma"}}
+
+
 def _is_rbf_function(fn):
-    return callable(fn) and getattr(fn, "__name__", "") in ("rbf_kernel", "abel_kernel")
+    return callable(fn) and getattr(fn, "__name__", "") in ("rbf_kernel", "abel_kernel", "linear_kernel",
+                                                            "polynomial_kernel", "laplacian_kernel")
 
 
 def resolve_kernel(kernel_fn, default_sigma):
@@ -76,19 +98,18 @@ def resolve_kernel(kernel_fn, default_sigma):
         fn, kw = kernel_fn.func, dict(kernel_fn.keywords or {})
     if not _is_rbf_function(fn):
         raise TypeError(
-            "socks_b200 runs the kernel on the GPU and only accepts RBF kernels: pass "
-            "functools.partial(rbf_kernel, sigma=...) (this package's or gym_socks's) or sklearn's "
-            f"rbf_kernel with gamma=...; got {kernel_fn!r}. There is no CPU fallback."
+            "socks_b200 runs the kernel on the GPU and accepts the kernel families it implements there: "
+            "rbf_kernel / abel_kernel (this package's or gym_socks's, sigma=...) and sklearn's rbf_kernel, "
+            f"linear_kernel, polynomial_kernel, laplacian_kernel; got {kernel_fn!r}. There is no CPU fallback."
         )
     module = getattr(fn, "__module__", "") or ""
     kw.pop("distance_fn", None)  # accepted and ignored by the reference (metrics.py:114-117)
-    if module.startswith("sklearn"):
-        if fn.__name__ != "rbf_kernel":
-            raise TypeError("only sklearn's rbf_kernel is supported among the sklearn pairwise kernels")
-        extra = set(kw) - {"gamma"}
+    if module.startswith("sklearn") or fn.__name__ in ("linear_kernel", "polynomial_kernel", "laplacian_kernel"):
+        extra = set(kw) - _SKLEARN_KEYWORDS[fn.__name__]
         if extra:
-            raise TypeError(f"unsupported keyword(s) for sklearn rbf_kernel: {sorted(extra)}")
-        return RBFSpec(gamma=kw.get("gamma"), style="gamma")
+            raise TypeError(f"unsupported keyword(s) for sklearn {fn.__name__}: {sorted(extra)}")
+        return RBFSpec(gamma=kw.get("gamma"), style="gamma", kind=_SKLEARN_KINDS[fn.__name__],
+                       coef0=kw.get("coef0", 1), degree=kw.get("degree", 3))
     extra = set(kw) - {"sigma"}
     if extra:
         raise TypeError(f"unsupported keyword(s) for {fn.__name__}: {sorted(extra)}")
@@ -97,7 +118,7 @@ def resolve_kernel(kernel_fn, default_sigma):
 
 
 # ----------------------------------------------------------------------------- device primitives
-def gram_dev(Xd, Yd, kparams, rowscale=None, out=None, ld=None, kind=KIND_RBF):
+def gram_dev(Xd, Yd, kparams, rowscale=None, out=None, ld=None, kind=KIND_RBF, extra=(1.0, 3.0)):
     """K = rowscale[:, None] * k(X_i, Y_j) on the device, kparams = (scale, divide); returns an (n, ld) tensor
     whose first m columns hold K (ld = m rounded up to even so rows stay 16-byte aligned)."""
     n, d = Xd.shape
@@ -106,8 +127,8 @@ def gram_dev(Xd, Yd, kparams, rowscale=None, out=None, ld=None, kind=KIND_RBF):
         ld = dv.even(m)
     if out is None:
         out = dv.empty(n, ld)
-    _lib.call("socks_gram_kernel", int(kind), dv.ptr(Xd), n, dv.ptr(Yd), m, d, float(kparams[0]), int(kparams[1]),
-              dv.ptr(rowscale), dv.ptr(out), ld, dv.stream())
+    _lib.call("socks_gram_family", int(kind), dv.ptr(Xd), n, dv.ptr(Yd), m, d, float(kparams[0]), int(kparams[1]),
+              float(extra[0]), float(extra[1]), dv.ptr(rowscale), dv.ptr(out), ld, dv.stream())
     return out
 
 
@@ -155,15 +176,20 @@ class Factorization:
     kernel_sr.py:45), `full()` is inv(G) itself.  `keep_l=True` also leaves the complete factor L in `self.L`;
     `two_pass=True` uses the separate socks_potrf + socks_trtri entry points instead of the fused recursion."""
 
-    def __init__(self, Zd, kparams, diag_add, kind=KIND_RBF, keep_l=False, two_pass=False):
+    def __init__(self, Zd, kparams, diag_add, kind=KIND_RBF, keep_l=False, two_pass=False, Ud=None, extra=(1.0, 3.0)):
         n, d = Zd.shape
         self.n, self.np = n, dv.padded(n)
         npad = self.np
         st = dv.stream()
         lib = _lib.load()
         self.L = dv.empty(npad, npad)
-        _lib.call("socks_gram_sym_kernel", int(kind), dv.ptr(Zd), n, d, float(kparams[0]), int(kparams[1]),
-                  float(diag_add), dv.ptr(self.L), npad, st)
+        if Ud is None and kind in (KIND_RBF, KIND_ABEL):
+            _lib.call("socks_gram_sym_kernel", int(kind), dv.ptr(Zd), n, d, float(kparams[0]), int(kparams[1]),
+                      float(diag_add), dv.ptr(self.L), npad, st)
+        else:  # any family, optional second factor k(U, U) with the same kernel (metrics.py:268-276)
+            _lib.call("socks_gram_sym_family", int(kind), dv.ptr(Zd), n, d, dv.ptr(Ud), 0 if Ud is None else Ud.shape[1],
+                      float(kparams[0]), int(kparams[1]), float(extra[0]), float(extra[1]), float(diag_add),
+                      dv.ptr(self.L), npad, st)
         self.info = torch.zeros(1, dtype=torch.int32, device=Zd.device)
         self._M = dv.empty(npad, npad)
         wk = dv.work(lib.socks_trtri_work_bytes(n))
@@ -322,21 +348,26 @@ def factorize(Xh, Uh, spec, regularization_param, keep_l=False, two_pass=False):
     The product of two RBF kernels with the same bandwidth is the RBF kernel of the concatenated
     vectors, so the product Gram of metrics.py:268-276 is one kernel evaluation on Z = [X | U].
     With the median heuristic each factor has its own bandwidth; the columns are rescaled so a single
-    gamma applies."""
+    gamma applies.  The other kernel families multiply the two factors explicitly."""
     n = Xh.shape[0]
     Xd = dv.to_dev(Xh)
     kp = spec.params_for(Xd, Xd)
+    Ud = None
     if Uh is None:
         Zd = Xd
-    elif spec.kind != KIND_RBF:
-        raise NotImplementedError("the product Gram K(X,X) * K(U,U) is fused as one kernel on [X | U], which only "
-                                  "holds for the RBF kernel; no algorithm of the reference uses it with abel_kernel")
     else:
-        Ud = dv.to_dev(Uh)
-        ku = spec.params_for(Ud, Ud)
-        if ku == kp:
-            Zd = dv.to_dev(np.concatenate([Xh, Uh], axis=1))
-        else:  # data-dependent bandwidths differ: rescale U so one scale applies
-            gx, gu = spec.gamma_for(Xd, Xd), spec.gamma_for(Ud, Ud)
-            Zd = dv.to_dev(np.concatenate([Xh, Uh * np.sqrt(gu / gx)], axis=1))
-    return Factorization(Zd, kp, regularization_param * n, kind=spec.kind, keep_l=keep_l, two_pass=two_pass)
+        Ud0 = dv.to_dev(Uh)
+        ku = spec.params_for(Ud0, Ud0)  # what the reference's kernel_fn(U, V) call would use
+        if spec.separable:
+            if ku == kp:
+                Zd = dv.to_dev(np.concatenate([Xh, Uh], axis=1))
+            else:  # data-dependent bandwidths differ: rescale U so one scale applies
+                gx, gu = spec.gamma_for(Xd, Xd), spec.gamma_for(Ud0, Ud0)
+                Zd = dv.to_dev(np.concatenate([Xh, Uh * np.sqrt(gu / gx)], axis=1))
+        else:  # general product Gram k(X,X) * k(U,U) (socks_gram_sym_family), one parameter set for both factors
+            if ku != kp:
+                raise NotImplementedError(f"product Gram with different kernel parameters for states and actions "
+                                          f"({kp} vs {ku}): pass explicit kernel parameters")
+            Zd, Ud = Xd, Ud0
+    return Factorization(Zd, kp, regularization_param * n, kind=spec.kind, keep_l=keep_l, two_pass=two_pass, Ud=Ud,
+                         extra=spec.extra)

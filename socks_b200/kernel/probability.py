@@ -15,7 +15,7 @@ __all__ = ["maximum_mean_discrepancy", "witness_function"]
 def _colsums(Xd, Yd, spec):
     """Column sums of k(X, Y): device vector of len(Y)."""
     n, m = Xd.shape[0], Yd.shape[0]
-    K = gram_dev(Xd, Yd, spec.params_for(Xd, Yd), kind=spec.kind)
+    K = gram_dev(Xd, Yd, spec.params_for(Xd, Yd), kind=spec.kind, extra=spec.extra)
     y = dv.empty(1, m)
     wk = dv.work(_lib.load().socks_reduce_work_bytes(m))
     _lib.call("socks_gemv_t", dv.ptr(K), n, m, K.stride(0), 0, 0, 1, dv.ptr(y), m, dv.ptr(wk), dv.stream())

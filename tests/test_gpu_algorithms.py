@@ -326,3 +326,30 @@ def test_conditional_embedding_and_mmd_golden():
     assert abs(maximum_mean_discrepancy(g["P"], g["Q"], kernel_fn=kf, biased=True, squared=True) - float(g["mmd_biased_sq"])) <= 1e-13
     assert abs(maximum_mean_discrepancy(g["P"], g["Q"], squared=True) - float(g["mmd_default"])) <= 1e-13
     assert np.max(np.abs(witness_function(g["P"], g["Q"], g["t"], kernel_fn=kf) - g["witness"])) <= 1e-13
+
+
+@pytest.mark.parametrize("family", ["abel", "laplacian"])
+def test_kernel_sr_other_kernel_families(family):
+    """KernelSR with a non-RBF kernel_fn (the reference accepts any pairwise kernel, kernel_sr.py:202,226-227): the
+    materialising predict path against a numpy restatement built on the same kernel matrices."""
+    KernelSR, _, _, _, _, _ = _api()
+    from sklearn.metrics.pairwise import laplacian_kernel
+
+    from socks_b200.kernel.metrics import abel_kernel
+
+    kfn = partial(abel_kernel, sigma=0.3) if family == "abel" else partial(laplacian_kernel, gamma=4.0)
+    cpu = (lambda A, B: orc.abel_kernel(A, B, 0.3)) if family == "abel" else (lambda A, B: laplacian_kernel(A, B, gamma=4.0))
+    n, T, lam = 400, 6, 1e-2
+    X, U, Y = syn.integrator_sample(n, seed=71)
+    pts = syn.uniform_points(333, seed=72, low=-1.05, high=1.05)
+    ct, tt = syn.integrator_tubes(T)
+    alg = KernelSR(time_horizon=T, constraint_tube=ct, target_tube=tt, problem="FHT", kernel_fn=kfn,
+                   regularization_param=lam)
+    alg.fit(syn.as_sample(X, U, Y))
+    W = np.linalg.inv(cpu(X, X) + lam * n * np.identity(n))
+    w = np.diag(W).copy()
+    vf = np.empty((T, n))
+    vf = orc.sr_recursion(Y, w, cpu(X, Y), T, ct, tt, vf, "FHT", out=vf)
+    want = orc.sr_recursion(pts, w, cpu(X, pts), T, ct, tt, vf, "FHT")
+    assert np.max(np.abs(alg.value_functions - vf)) <= TOL
+    assert np.max(np.abs(alg.predict(pts) - want)) <= TOL

@@ -239,3 +239,63 @@ def test_potrs_against_numpy_solve():
     want = np.linalg.solve(G, Bh)
     got = B[:n, :q].cpu().numpy()
     assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 100 * np.linalg.cond(G) * 2.0 ** -53
+
+
+# ---------------------------------------------------------------------------------------------- kernel families
+def test_sklearn_kernels_work_with_regularized_inverse():
+    """Port of gym_socks/kernel/tests/test_kernel.py:132-147 (`test_sklearn_kernels`): the four sklearn pairwise
+    kernels must be accepted by regularized_inverse(Y, Y, kernel_fn=...) -- and here also give the reference's matrix."""
+    from sklearn.metrics.pairwise import laplacian_kernel, linear_kernel, polynomial_kernel, rbf_kernel
+
+    from socks_b200.kernel.metrics import regularized_inverse
+
+    Y = np.arange(4).reshape((2, 2))
+    for kernel_fn in [linear_kernel, polynomial_kernel, rbf_kernel, laplacian_kernel]:
+        W = regularized_inverse(Y, Y, kernel_fn=kernel_fn)
+        want = np.linalg.inv(kernel_fn(Y, Y) + (1 / 4) * 2 * np.identity(2))  # metrics.py:251-252, 278-280
+        assert W.shape == (2, 2) and np.allclose(W, want, rtol=1e-12, atol=0), kernel_fn.__name__
+
+
+@pytest.mark.parametrize("name", ["linear", "poly_default", "poly_params", "laplacian", "laplacian_gamma"])
+def test_kernel_families_inverse_and_product_gram(name):
+    """regularized_inverse with each family, with and without the product Gram K(U,U) * K(X,X) (metrics.py:268-276),
+    against numpy on sklearn's matrices (cond-aware, as for the RBF W)."""
+    from functools import partial
+
+    from sklearn.metrics.pairwise import laplacian_kernel, linear_kernel, polynomial_kernel
+
+    from socks_b200.kernel.metrics import regularized_inverse
+
+    fn = {"linear": linear_kernel, "poly_default": polynomial_kernel,
+          "poly_params": partial(polynomial_kernel, gamma=0.3, degree=2, coef0=0.5), "laplacian": laplacian_kernel,
+          "laplacian_gamma": partial(laplacian_kernel, gamma=2.5)}[name]
+    rng = np.random.default_rng(11)
+    X = rng.uniform(-1, 1, (300, 3))
+    U = rng.uniform(-1, 1, (300, 3))  # same width as X: sklearn's gamma=None is 1 / n_features of its argument
+    lam = 1e-3
+    for Uarg in (None, U):
+        G = fn(X, X) if Uarg is None else fn(Uarg, Uarg) * fn(X, X)
+        G = G + lam * 300 * np.identity(300)
+        want = np.linalg.inv(G)
+        got = regularized_inverse(X, U=Uarg, regularization_param=lam, kernel_fn=fn)
+        tol = max(1e-10, 100 * np.linalg.cond(G) * 2.0 ** -53)
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) <= tol
+
+
+def test_kernel_family_rejections():
+    from sklearn.metrics.pairwise import sigmoid_kernel
+
+    from socks_b200.kernel.metrics import regularized_inverse
+
+    with pytest.raises(TypeError):
+        regularized_inverse(np.eye(3), kernel_fn=sigmoid_kernel)
+    with pytest.raises(TypeError):
+        regularized_inverse(np.eye(3), kernel_fn=lambda X, Y=None: X @ X.T)
+    # an indefinite matrix is reported, not silently "inverted" through a failed Cholesky
+    from functools import partial
+
+    from sklearn.metrics.pairwise import polynomial_kernel
+
+    with pytest.raises(np.linalg.LinAlgError):
+        regularized_inverse(np.array([[1.0, 0.0], [0.0, 2.0], [3.0, 1.0]]), regularization_param=1e-9,
+                            kernel_fn=partial(polynomial_kernel, degree=1, coef0=-5.0))

@@ -28,10 +28,19 @@ def test_resolve_kernel_forms():
     assert resolve_kernel(sk_rbf, 1).params_for(np.zeros((2, 4)), None) == (-0.25, 0)  # sklearn default 1/n_features
     assert RBFSpec(sigma=0.1).params_for(None, None) == (-2 * 0.1 ** 2, 1)  # the reference divides by -2 sigma^2
     assert RBFSpec(sigma=0.1).gamma_for(None, None) == pytest.approx(50.0)
-    from sklearn.metrics.pairwise import laplacian_kernel
+    # the sklearn kernels the reference's own test feeds to regularized_inverse (test_kernel.py:18,132-147)
+    from sklearn.metrics.pairwise import laplacian_kernel, linear_kernel, polynomial_kernel, sigmoid_kernel
 
+    lap = resolve_kernel(partial(laplacian_kernel, gamma=2.0), 1)
+    assert lap.kind == 4 and lap.params_for(np.zeros((2, 3)), None) == (-2.0, 0)
+    assert resolve_kernel(laplacian_kernel, 1).params_for(np.zeros((2, 4)), None) == (-0.25, 0)
+    pol = resolve_kernel(partial(polynomial_kernel, degree=2, coef0=0.5), 1)
+    assert pol.kind == 3 and pol.extra == (0.5, 2.0) and pol.params_for(np.zeros((2, 5)), None) == (0.2, 0)
+    assert resolve_kernel(linear_kernel, 1).kind == 2
     with pytest.raises(TypeError):
-        resolve_kernel(laplacian_kernel, 1)
+        resolve_kernel(sigmoid_kernel, 1)
+    with pytest.raises(TypeError):
+        resolve_kernel(partial(polynomial_kernel, bogus=1), 1)
     with pytest.raises(TypeError):
         resolve_kernel(lambda X, Y=None: X, 1)
     with pytest.raises(AssertionError):
