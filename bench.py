@@ -1,17 +1,24 @@
 """bench.py — KernelSR test points/sec (N=20k samples, T=15, fp64) on 1..8 B200 + Gram/solve seconds.
 
-Workload (BASELINE.json configs[1], SURVEY.md §8(d) "C2"): 2-D stochastic integrator, N = 20 000 samples,
-T = 15, FHT, sigma = 0.1, lambda = 1/N^2, M = 250 000 test points per GPU.  A "step" is one pass of the
-fused predict path (socks_sr_predict: pack + the DMMA kernel) over the rank's M resident test points; the
-fit (Gram + Cholesky + triangular inverse + diag + T-1 GEMV passes) runs once on rank 0, is reported as
-`gram_solve_s` / `fit_s`, and its state (X, w, value functions: ~2.9 MB) is broadcast over NCCL.
-Test points are independent, so ranks need no data-path collective: weak scaling, M points per rank.
+Workload (BASELINE.json configs[1], SURVEY.md §8(d) "C2"): 2-D stochastic integrator, N = 20 000 samples, T = 15, FHT,
+sigma = 0.1, lambda = 1/N^2, M = 250 000 test points.  A "step" is one pass of the fused predict path
+(socks_sr_predict_packed: the tensor-core kernel + finish) over the rank's resident test points.  The fit (Gram +
+Cholesky/triangular inverse + diag + T-1 GEMV passes + pack) runs once on rank 0, is reported stage by stage
+(`gram_solve_s`, `potrf_inv_tflops`, `fit_recursion_gbs`, ...), and its state (X, w, value functions: ~2.9 MB) is
+broadcast over NCCL.  Test points are independent columns, so ranks need no data-path collective.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+Scaling: with --gpus N > 1 the DEFAULT is strong scaling -- the 250 000 points of configs[1] are split over the ranks
+(north_star: ">= 7x scaling of test-point throughput from 1 to 8 B200") -- and the weak-scaling number (250 000 points
+per rank) is measured in the same run and reported under "weak".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling strong|weak]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-`--impl reference` times the CPU oracle port of the reference's predict (numpy, all host threads) on a
-bounded sample of the same workload and never touches the CUDA library.
+`--impl reference` times the UNMODIFIED reference (`gym_socks.algorithms.reach.kernel_sr.KernelSR`, imported from
+/root/reference or from the verbatim copy oracle/vendor_ref.py leaves in oracle/_ref) on the host cores: one reference
+fit at full N (untimed, reported), then `predict` on a bounded sample of the same test points per step.  It never
+touches the CUDA library.  If the reference cannot be imported, the numpy oracle port is timed instead
+(`cpu_baseline.kind: "port"`).
 """
 import argparse
 import json
@@ -28,8 +35,10 @@ if ROOT not in sys.path:
 
 SIGMA, PROBLEM = 0.1, "FHT"
 DIM = 2  # state dimension of the headline workload; --d overrides it (BASELINE.json configs[4] uses d = 4)
-# algorithmic FP64 work per (sample, test point) pair of the fused predict:
-# distance 3d+2, shipped exp (exp_f64.cuh exp_scaled_x4: 5 DFMA + DADD + DMUL = 12 flop), contraction 2T
+METRIC = "KernelSR test points/sec (N=20k, T=15, fp64)"
+# algorithmic FP64 work per (sample, test point) pair of the fused predict: distance 3d+2, exp E = 12
+# (the figure of the round-1 table exp, kept so that fractions stay comparable across rounds; the shipped factored
+# exponent issues fewer instructions than that), contraction 2T
 EXP_FLOPS = 12
 
 
@@ -37,8 +46,13 @@ def pair_flops(d, T):
     return 3 * d + 2 + EXP_FLOPS + 2 * T
 
 
+def workload_name(n, m, T, d):
+    return (f"KernelSR predict, {d}-D integrator, N={n}, T={T}, M={m}, sigma={SIGMA}, {PROBLEM}, lambda=1/N^2 "
+            f"(BASELINE.json configs[1])")
+
+
 class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons during the timed region (nvidia-smi based)."""
+    """Samples SM clock / throttle reasons during the timed region (NVML)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -65,7 +79,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if mask & bit:
                         self.reasons.add(name)
-                time.sleep(0.02)
+                time.sleep(0.01)
         except Exception as e:  # clocks are evidence, not a dependency of the measurement
             self.reasons.add(f"sampler_error:{type(e).__name__}")
 
@@ -76,62 +90,139 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_predict_sample(n, T, m_sample, w=None, vf=None, X=None, seed=1):
-    """Oracle (numpy port of kernel_sr.py:329-342) predict on m_sample test points at N = n. Returns (pts/s, desc)."""
-    from oracle import socks_oracle as orc
-    from socks_b200 import synthetic as syn
-
-    ct, tt = syn.integrator_tubes(T, DIM)
-    alg = orc.KernelSROracle(T, ct, tt, PROBLEM, SIGMA, 1 / n ** 2, chunk=1000)
-    rng = np.random.default_rng(123)
-    if X is None:
-        X = syn.integrator_sample(n, DIM, seed=0)[0]
-    alg.X = X
-    alg.w_diag = w if w is not None else 1.0 + rng.random(n)
-    alg.value_functions = vf if vf is not None else rng.random((T, n))
-    pts = syn.uniform_points(m_sample, DIM, seed=seed)
-    alg.predict(pts[:200])  # warm-up
-    t0 = time.perf_counter()
-    alg.predict(pts)
-    dt = time.perf_counter() - t0
-    return m_sample / dt, dt
-
-
-def run_reference(args):
-    """CPU arm: the oracle port of the reference's predict path on the host cores (no CUDA)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    n, T, m_s = args.n, args.T, args.cpu_sample
+# ------------------------------------------------------------------------------------------- CPU side (oracle/)
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm may use every host thread."""
     cores = os.cpu_count()
-    try:  # torchrun exports OMP_NUM_THREADS=1; the reference arm may use every host thread
+    try:
         from threadpoolctl import threadpool_limits
 
         threadpool_limits(limits=cores)
     except Exception:
         pass
-    vals, secs = [], []
-    for i in range(args.warmup + args.steps):
-        v, dt = cpu_predict_sample(n, T, m_s, seed=10 + i)
-        if i >= args.warmup:
-            vals.append(v)
-            secs.append(dt)
+    return cores
+
+
+def _blas_name():
+    try:
+        from threadpoolctl import threadpool_info
+
+        return ",".join(sorted({f"{i.get('internal_api')}:{i.get('num_threads')}" for i in threadpool_info()}))
+    except Exception:
+        return "unknown"
+
+
+def reference_predictor(n, T, d, X=None, w=None, vf=None):
+    """-> (predict(pts) callable, info dict).  The unmodified reference's KernelSR with the kernel_fn its own benchmark
+    uses (sklearn rbf_kernel, gamma = 1/(2 sigma^2): benchmarks/kernel_sr/baseline.py:20,134-144).  With (X, w, vf) given
+    the fitted state is injected (W only enters through its diagonal, kernel_sr.py:45, so a zero matrix carrying diag(W)
+    reproduces predict exactly); otherwise the reference fits itself on the synthetic sample (minutes at N = 20 000)."""
+    from functools import partial
+
+    from oracle import ref_loader
+    from sklearn.metrics.pairwise import rbf_kernel as sk_rbf
+    from socks_b200 import synthetic as syn
+
+    ref = ref_loader.load()
+    gym = ref["gym"]
+    box = lambda b: gym.spaces.Box(low=-b, high=b, shape=(d,), dtype=np.float32)
+    alg = ref["KernelSR"](time_horizon=T, constraint_tube=[box(1.0)] * T, target_tube=[box(0.5)] * T, problem=PROBLEM,
+                          kernel_fn=partial(sk_rbf, gamma=1 / (2 * SIGMA ** 2)), regularization_param=1 / n ** 2)
+    info = {"root": ref["root"], "kernel_fn": "sklearn.metrics.pairwise.rbf_kernel(gamma=1/(2 sigma^2))"}
+    if X is None:
+        Xs, Us, Ys = syn.integrator_sample(n, d, seed=0)
+        t0 = time.perf_counter()
+        alg.fit(list(zip(Xs, Us, Ys)))
+        info["fit_s"] = time.perf_counter() - t0
+        info["state"] = "fitted by the reference itself"
+    else:
+        alg._validate_params(None)
+        W = np.zeros((n, n))  # calloc: only the diagonal's pages are ever touched
+        W[np.diag_indices(n)] = w
+        alg.X, alg.W, alg.value_functions = np.asarray(X), W, np.asarray(vf)
+        info["state"] = "X, diag(W), value functions taken from the GPU fit"
+    return alg.predict, info
+
+
+def port_predictor(n, T, d, X=None, w=None, vf=None):
+    """Oracle (numpy port of kernel_sr.py:329-342) predict; stand-in state if none is given."""
+    from oracle import socks_oracle as orc
+    from socks_b200 import synthetic as syn
+
+    ct, tt = syn.integrator_tubes(T, d)
+    alg = orc.KernelSROracle(T, ct, tt, PROBLEM, SIGMA, 1 / n ** 2, chunk=1000)
+    rng = np.random.default_rng(123)
+    alg.X = X if X is not None else syn.integrator_sample(n, d, seed=0)[0]
+    alg.w_diag = w if w is not None else 1.0 + rng.random(n)
+    alg.value_functions = vf if vf is not None else rng.random((T, n))
+    return alg.predict, {"state": "from the GPU fit" if w is not None else "stand-in (w, value_functions)"}
+
+
+def time_cpu(predict, pts_list):
+    """Seconds per call of predict over the given point batches (first batch is an untimed warm-up)."""
+    predict(pts_list[0][:200])
+    secs = []
+    for p in pts_list:
+        t0 = time.perf_counter()
+        predict(p)
+        secs.append(time.perf_counter() - t0)
+    return secs
+
+
+def run_reference(args):
+    """CPU arm: the unmodified reference's predict path on the host cores (no CUDA)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from socks_b200 import synthetic as syn
+
+    n, T, m_s, d = args.n, args.T, args.cpu_sample, DIM
+    cores = _use_all_host_threads()
+    kind, info = "reference", {}
+    try:
+        if args.ref_state == "port":
+            raise ImportError("--ref-state port")
+        predict, info = reference_predictor(n, T, d)
+    except Exception as e:  # reference not importable on this box: the numpy port is the CPU arm
+        kind = "port"
+        predict, info = port_predictor(n, T, d)
+        info["why_port"] = f"{type(e).__name__}: {e}"[:200]
+    allp = syn.uniform_points(args.m, d, seed=1)
+    k = args.warmup + args.steps
+    batches = [allp[(i * m_s) % max(args.m - m_s, 1):][:m_s] for i in range(k)]
+    secs = time_cpu(predict, batches)[args.warmup:]
     value = m_s * len(secs) / sum(secs)
-    sample = (f"{m_s} of the {args.m} test points per step at N={n}, T={T} (numpy port of kernel_sr.py:329-342, "
-              f"BLAS threads unrestricted); stand-in fitted state (w, value_functions): per-point cost does not depend "
-              f"on their values, and a CPU fit at N={n} alone takes ~130 s (BASELINE.md)")
+    sample = (f"{m_s} of the {args.m} test points per step at N={n}, T={T}: unmodified gym_socks KernelSR.predict "
+              f"(kernel_sr.py:311-344), {info.get('kernel_fn', 'numpy port')}, state {info.get('state')}; BLAS {_blas_name()}")
     line = {
-        "impl": "reference", "metric": "KernelSR test points/sec (N=20k, T=15, fp64)", "value": value,
-        "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"KernelSR predict, {DIM}-D integrator, N={n}, T={T}, M={args.m}/GPU, sigma=0.1, FHT",
-                   "sample_points_per_step": m_s},
-        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(n, args.m, T, d)},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "reference_fit_s": info.get("fit_s"), "reference_root": info.get("root"),
     }
+    if "why_port" in info:
+        line["reference_unavailable"] = info["why_port"]
     _emit(line)
+
+
+# ------------------------------------------------------------------------------------------------- GPU side
+def _ncu_traffic(kernel_prefix, shape):
+    """dram bytes per launch from the committed ncu capture of this exact kernel and shape (tools/ncu_summary.py
+    writes profiles/*.json next to the text summary); None when there is no capture for the shape."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if not (name.startswith("r2_ncu_") and name.endswith(".json")):
+            continue
+        try:
+            rec = json.load(open(os.path.join(pdir, name)))
+        except Exception:
+            continue
+        if rec.get("kernel", "").startswith(kernel_prefix) and rec.get("shape") == shape:
+            best = {"bytes": rec.get("dram_bytes_read", 0) + rec.get("dram_bytes_write", 0), "source": "profiles/" + name}
+    return best
 
 
 def run_ours(args):
@@ -148,8 +239,9 @@ def run_ours(args):
 
     from functools import partial
 
-    from socks_b200 import _device as dv, _lib, synthetic as syn
+    from socks_b200 import _device as dv, synthetic as syn
     from socks_b200.algorithms.reach.kernel_sr import KernelSR
+    from socks_b200.distributed import broadcast_state, shard_bounds
     from socks_b200.kernel.metrics import rbf_kernel
 
     n, m, T, d = args.n, args.m, args.T, DIM
@@ -157,10 +249,8 @@ def run_ours(args):
     alg = KernelSR(time_horizon=T, constraint_tube=ct, target_tube=tt, problem=PROBLEM,
                    kernel_fn=partial(rbf_kernel, sigma=SIGMA), regularization_param=1 / n ** 2)
     alg._validate_params(None)
+    alg._keep_factors = False
     X, U, Y = syn.integrator_sample(n, d, seed=0)
-
-    def ev():
-        return torch.cuda.Event(enable_timing=True)
 
     fit_info = {}
     if rank == 0:
@@ -168,146 +258,180 @@ def run_ours(args):
         KernelSR(time_horizon=3, constraint_tube=ct, target_tube=tt, problem=PROBLEM,
                  regularization_param=1e-3).fit_arrays(small[0], small[2])  # module load / attribute warm-up
         torch.cuda.synchronize()
-        e0, e1 = ev(), ev()
-        e0.record()
+        dv.stage_marks = []
         alg.fit_arrays(X, Y)
-        e1.record()
         torch.cuda.synchronize()
-        fit_info["fit_s"] = e0.elapsed_time(e1) * 1e-3
-        # Gram + solve alone (gram_sym + potrf + trtri + diag), re-timed on the resident inputs
-        from socks_b200.kernel.metrics import factorize
-
-        e0, e1 = ev(), ev()
-        e0.record()
-        fac = factorize(X, None, alg._spec, alg.regularization_param)
-        fac.diag()
-        e1.record()
-        torch.cuda.synchronize()
-        fit_info["gram_solve_s"] = e0.elapsed_time(e1) * 1e-3
-        npad = fac.np
-        fit_info["gram_solve_tflops"] = (2 * npad ** 3 / 3) / fit_info["gram_solve_s"] / 1e12
-        del fac
-        alg._fac.release_factors()
-        torch.cuda.empty_cache()
+        st = dv.stage_times()
+        dv.stage_marks = None
+        npad = dv.padded(n)
+        fit_info = {
+            "fit_s": sum(st.values()),
+            "gram_solve_s": st["gram_sym"] + st["potrf_inv"] + st["diag_inv"],
+            "gram_solve_tflops": (2 * npad ** 3 / 3) / (st["gram_sym"] + st["potrf_inv"] + st["diag_inv"]) / 1e12,
+            "potrf_inv_s": st["potrf_inv"], "potrf_inv_tflops": (2 * npad ** 3 / 3) / st["potrf_inv"] / 1e12,
+            "gram_sym_s": st["gram_sym"], "gram_cross_s": st["gram_cross"],
+            "fit_recursion_s": st["fit_recursion"],
+            # HBM-bound stage: (T-1) GEMV passes over the resident N x N beta, bytes = (T-1) * 8 * N^2 (the
+            # normaliser pass and the step kernels are inside the time but not in the bytes)
+            "fit_recursion_gbs": (T - 1) * 8.0 * n * n / st["fit_recursion"] / 1e9,
+            "stages_s": st,
+        }
     else:
         alg.allocate_state(n, d)
     if world > 1:  # fit state broadcast over NCCL/NVLink: the only collective on the path
-        from socks_b200.distributed import broadcast_state
-
         fit_info["broadcast_bytes"] = broadcast_state(alg.state_tensors(), src=0)
 
-    if args.scaling == "strong":  # one global set of M points, contiguous block per rank
-        from socks_b200.distributed import shard_bounds
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    if "fit_recursion_gbs" in fit_info and peaks.get("hbm_gbs"):
+        fit_info["fit_recursion_frac_hbm"] = fit_info["fit_recursion_gbs"] / peaks["hbm_gbs"]
 
-        lo, hi = shard_bounds(m, world, rank)
-        pts_host = np.ascontiguousarray(syn.uniform_points(m, d, seed=1)[lo:hi])
-        m_total, m = m, hi - lo
-    else:
-        pts_host = syn.uniform_points(m, d, seed=1 + rank)
-        m_total = world * m
-    pts = dv.to_dev(pts_host)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
-    def step():
-        return alg.predict_dev(pts)
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
 
-    for _ in range(max(args.warmup, 3)):
-        out = step()
-    torch.cuda.synchronize()
+    def measure(mode):
+        """Device-timed and end-to-end throughput of one sharding mode; returns a dict (identical on all ranks)."""
+        if mode == "strong":  # one global set of M points, contiguous block per rank
+            lo, hi = shard_bounds(m, world, rank)
+            pts_host = np.ascontiguousarray(syn.uniform_points(m, d, seed=1)[lo:hi])
+            m_total = m
+        else:
+            pts_host = syn.uniform_points(m, d, seed=1 + rank)
+            m_total = world * m
+        pts = dv.to_dev(pts_host)
+        for _ in range(max(args.warmup, 3)):
+            out = alg.predict_dev(pts)
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        sampler.start()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        starts, ends = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            flush.zero_()  # evict L2 between timed steps (outside the per-step event pair)
+            starts[i].record()
+            out = alg.predict_dev(pts)
+            ends[i].record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        wall = time.perf_counter() - t_wall0
+        dev_s = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) * 1e-3
+        clocks = sampler.stop()
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    starts, ends = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.zero_()  # evict L2 between timed steps (outside the per-step event pair)
-        starts[i].record()
-        out = step()
-        ends[i].record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    wall = time.perf_counter() - t_wall0
-    dev_s = sum(s.elapsed_time(e) for s, e in zip(starts, ends)) * 1e-3
-    clocks = sampler.stop()
+        # end to end through the public API: host ndarray in (H2D inside), host ndarray out (D2H inside)
+        def e2e(arr):
+            for _ in range(2):
+                res = alg.predict(arr)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                res = alg.predict(arr)
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0, res
 
-    # end to end through the public API: host ndarray in (H2D inside), host ndarray out (D2H inside)
-    pinned = torch.from_numpy(pts_host).pin_memory()
-    pts_np = pinned.numpy()
-    for _ in range(2):
-        res = alg.predict(pts_np)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = alg.predict(pts_np)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+        pinned = torch.from_numpy(pts_host).pin_memory()
+        e2e_s, res = e2e(pinned.numpy())
+        e2e_pageable_s, _ = e2e(pts_host)  # what a drop-in caller passes: a plain (pageable) ndarray
+        tmax = torch.tensor([dev_s, e2e_s, e2e_pageable_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s, e2e_pageable_s = (float(x) for x in tmax)
+        del out
+        return {"m_rank": int(pts_host.shape[0]), "m_total": m_total, "dev_s": dev_s, "e2e_s": e2e_s,
+                "e2e_pageable_s": e2e_pageable_s, "wall": wall, "clocks": clocks, "h2d": int(pts_host.nbytes),
+                "d2h": int(res.nbytes), "pts": pts}
 
-    tmax = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dev_s, e2e_s = float(tmax[0]), float(tmax[1])
+    main_mode = args.scaling
+    r = measure(main_mode)
+    other = None
+    if world > 1 and not args.no_extras:
+        other = measure("weak" if main_mode == "strong" else "strong")
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         from probe_fp64 import probe
 
         fp64_peak = probe(0, iters=8000)["fp64_fma_tflops"]
         dmma_peak = probe(1, iters=8000)["fp64_dmma_tflops"]
-        ms_step = 1e3 * dev_s / args.steps
-        flops_launch = float(n) * m * pair_flops(d, T)  # rank 0's launch
+        ms_step = 1e3 * r["dev_s"] / args.steps
+        flops_launch = float(n) * r["m_rank"] * pair_flops(d, T)  # rank 0's launch
         achieved = flops_launch / (ms_step * 1e-3) / 1e12
+        traffic = _ncu_traffic("sr_predict_fast_kernel", [n, r["m_rank"], T, d])
         line = {
-            "metric": "KernelSR test points/sec (N=20k, T=15, fp64)",
-            "value": m_total * args.steps / dev_s, "unit": "points/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"KernelSR predict, {d}-D integrator, N={n}, T={T}, M={args.m}"
-                                   f"{'/GPU' if args.scaling == 'weak' else ' in total'}, sigma=0.1, FHT, "
-                                   f"lambda=1/N^2 (BASELINE.json configs[1])",
+            "metric": METRIC, "value": r["m_total"] * args.steps / r["dev_s"], "unit": "points/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": main_mode, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(n, m, T, d),
+                       "points": f"{r['m_total']} in total, {r['m_rank']} on rank 0",
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step event pair)",
-                       "parallelism": f"test points sharded, {world} rank(s), fit on rank 0 + NCCL broadcast"},
-            "e2e": {"value": m_total * args.steps / e2e_s, "unit": "points/s", "h2d_bytes_per_step": int(pts_host.nbytes),
-                    "d2h_bytes_per_step": int(res.nbytes)},
-            "gpu_launches": 4 * args.steps,  # per step: factored kernel, direct kernel (exits at once unless the factored form is inadmissible), finish, flagged-column kernel
+                       "parallelism": f"test points sharded over {world} rank(s), fit on rank 0 + NCCL broadcast"},
+            "e2e": {"value": r["m_total"] * args.steps / r["e2e_s"], "unit": "points/s",
+                    "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                    "input": "pinned host ndarray (contract); pageable_input_value = plain ndarray, as a drop-in caller passes",
+                    "pageable_input_value": r["m_total"] * args.steps / r["e2e_pageable_s"]},
+            "gpu_launches": 4 * args.steps,  # per step: factored kernel, direct-form kernel (exits at once unless
+            # the factored form is inadmissible), finish, flagged-column kernel
             "roofline": {"bound": "tensor", "peak_kind": "fp64 DMMA (mma.sync.m8n8k4.f64), measured live",
-                         "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
-                         "frac": achieved / dmma_peak,
-                         # dram__bytes_read + dram__bytes_write of one launch at this exact shape, from the ncu
-                         # --set full capture summarised in profiles/r1_ncu_sr_predict_dmma_n20000_m250000.txt
-                         "traffic": 279.1e6 if (n, m, T, d) == (20000, 250000, 15, 2) else None,
-                         "kernel": "sr_predict_dmma_kernel<2>",
-                         "note": "algorithmic flops = N*M*(3d+2+E+2T), E=12 (exp_f64.cuh); FMA and DMMA share the "
-                                 "FP64 pipe on B200 (tools/probe_fp64.py: 36.5 / 37.1 TFLOP/s alone, 35.7 combined), so the fp64 "
-                                 "tensor peak bounds the whole kernel; measured live by socks_probe_fp64 "
-                                 "(MEASURED_PEAKS.json has HBM and bf16 only)",
+                         "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
+                         "traffic": traffic["bytes"] if traffic else None,
+                         "traffic_source": traffic["source"] if traffic else None,
+                         "kernel": f"sr_predict_fast_kernel<{d}, ...> (csrc/sr_predict.cu)",
+                         "note": "algorithmic flops = N*M*(3d+2+E+2T), E=12; FMA and DMMA share the FP64 pipe on B200 "
+                                 "(tools/probe_fp64.py: 36.5 / 37.1 TFLOP/s alone, 35.7 combined), so the fp64 tensor "
+                                 "peak bounds the whole kernel; measured live by socks_probe_fp64 (MEASURED_PEAKS.json "
+                                 "has HBM and bf16 only)",
                          "fp64_fma_peak": fp64_peak, "hbm_peak_gbs": peaks.get("hbm_gbs")},
-            "clocks": clocks,
-            "wall_s_timed_region": wall,
+            "clocks": r["clocks"],
+            "wall_s_timed_region": r["wall"],
         }
+        if other is not None:
+            line["weak" if main_mode == "strong" else "strong"] = {
+                "value": other["m_total"] * args.steps / other["dev_s"], "unit": "points/s",
+                "ms_per_step": 1e3 * other["dev_s"] / args.steps, "points_total": other["m_total"],
+                "e2e_value": other["m_total"] * args.steps / other["e2e_s"], "clocks": other["clocks"]}
         line.update(fit_info)
         if world == 1 and not args.no_extras and d == 2:
-            line["kernel_maximal_sr"] = maximal_sr_extra(n, m, T, d, ct, tt, X, U, Y, pts)
+            line["kernel_maximal_sr"] = maximal_sr_extra(n, m, T, d, ct, tt, X, U, Y, r["pts"])
         if world == 1:
-            wh, vfh = alg._w.cpu().numpy(), alg._vf.cpu().numpy()
-            v, dt = cpu_predict_sample(n, T, args.cpu_sample, w=wh, vf=vfh, X=X)
-            line["cpu_baseline"] = {
-                "value": v, "unit": "points/s", "cores": os.cpu_count(), "kind": "port",
-                "sample": f"oracle predict of {args.cpu_sample} of the {m} test points at N={n}, T={T} on the host "
-                          f"cores ({dt:.1f} s), fitted state taken from the GPU fit"}
+            line["cpu_baseline"] = cpu_baseline(alg, n, T, d, m, args.cpu_sample, X)
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_baseline(alg, n, T, d, m, m_s, X):
+    """The reference's predict on the host cores, on a bounded sample of the same workload, with the fitted state of the
+    GPU fit injected; the numpy port beside it."""
+    from socks_b200 import synthetic as syn
+
+    cores = _use_all_host_threads()
+    wh, vfh = alg._w.cpu().numpy(), alg._vf.cpu().numpy()
+    pts = syn.uniform_points(m, d, seed=1)[:m_s]
+    out = {"unit": "points/s", "cores": cores}
+    secs_p = time_cpu(port_predictor(n, T, d, X, wh, vfh)[0], [pts])
+    out["port_value"] = m_s / secs_p[0]
+    try:
+        predict, info = reference_predictor(n, T, d, X, wh, vfh)
+        secs = time_cpu(predict, [pts])
+        out.update(value=m_s / secs[0], kind="reference",
+                   sample=f"unmodified gym_socks KernelSR.predict (kernel_sr.py:311-344, {info['kernel_fn']}) on {m_s} "
+                          f"of the {m} test points at N={n}, T={T} ({secs[0]:.1f} s on the host cores; numpy port: "
+                          f"{secs_p[0]:.1f} s); {info['state']}; BLAS {_blas_name()}")
+    except Exception as e:
+        out.update(value=out["port_value"], kind="port",
+                   sample=f"oracle port predict of {m_s} of the {m} test points at N={n}, T={T} ({secs_p[0]:.1f} s); "
+                          f"reference not importable: {type(e).__name__}: {e}"[:300])
+    return out
 
 
 def maximal_sr_extra(n, m, T, d, ct, tt, X, U, Y, pts, P=100):
@@ -340,7 +464,7 @@ def maximal_sr_extra(n, m, T, d, ct, tt, X, U, Y, pts, P=100):
     cols = -(-T * P // 128) * 128
     res = {"P": P, "fit_s": t_fit, "predict_s": t_pred, "points_per_s": m / t_pred,
            "predict_gemm_tflops": 2.0 * npad * m * cols / t_pred / 1e12,
-           "note": "predict = Gram chunks + one DMMA GEMM K(X,pts)^T [diag(coef_r) CUA]_r per chunk + fused max/step"}
+           "note": "predict = one DMMA GEMM K(X,pts)^T [diag(coef_r) CUA]_r per chunk of test points + fused max/step"}
     del alg, out
     torch.cuda.empty_cache()
     return res
@@ -373,9 +497,12 @@ def main():
     ap.add_argument("--m", "--points", dest="m", type=int, default=250000)
     ap.add_argument("--T", "--horizon", dest="T", type=int, default=15)
     ap.add_argument("--cpu-sample", type=int, default=4000)
-    ap.add_argument("--no-extras", action="store_true", help="skip the KernelMaximalSR side measurement")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: --m test points per GPU (default, the driver's contract); strong: --m in total")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the KernelMaximalSR side measurement and the second scaling mode")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (default): --m test points in total, split over the ranks; weak: --m per GPU")
+    ap.add_argument("--ref-state", default="reference", choices=["reference", "port"],
+                    help="--impl reference: 'reference' = the unmodified gym_socks code (fit + predict), 'port' = numpy port")
     ap.add_argument("--d", "--dim", dest="d", type=int, default=DIM, help="state dimension (chain of integrators)")
     args = ap.parse_args()
     globals()["DIM"] = args.d

@@ -9,6 +9,26 @@ from socks_b200 import _lib
 F64 = torch.float64
 
 
+# Optional stage timing (bench.py, tools/): when `stage_marks` is a list, mark(name) records a CUDA event on the
+# current stream after the work enqueued so far; stage_times() turns consecutive marks into seconds.
+stage_marks = None
+
+
+def mark(name):
+    if stage_marks is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        stage_marks.append((name, e))
+
+
+def stage_times():
+    """{name: seconds since the previous mark} (call after a synchronize)."""
+    out = {}
+    for (_, e0), (name, e1) in zip(stage_marks[:-1], stage_marks[1:]):
+        out[name] = out.get(name, 0.0) + e0.elapsed_time(e1) * 1e-3
+    return out
+
+
 def device():
     if not torch.cuda.is_available():
         raise _lib.SocksError("socks_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")

@@ -110,6 +110,7 @@ class KernelSR:
         logger.debug("Computing covariance matrix.")
         ldb = dv.even(n)
         B = gram_dev(Xd, Yd, self._spec.params_for(Xd, Yd), kind=self._spec.kind, extra=self._spec.extra, rowscale=w, ld=ldb)  # un-normalised beta, kernel_sr.py:45
+        dv.mark("gram_cross")
         logger.debug("Computing value functions.")
         vf = dv.empty(max(T, 1), n)
         lib = _lib.load()
@@ -117,9 +118,13 @@ class KernelSR:
         if T >= 1:
             _lib.call("socks_sr_recursion", dv.ptr(B), n, n, ldb, dv.ptr(Yd), d, dv.ptr(self._tubes),
                       PROBLEM_CODE[self.problem], T, dv.ptr(vf), n, dv.ptr(vf), n, dv.ptr(wk), dv.stream())
+        dv.mark("fit_recursion")
         self._vf = vf[:T]
         self._vf_host = None
         del B
+        if not self._spec.data_dependent and self._spec.kind == 0 and T >= 1:
+            self._packed(self._spec.params_for(Xd, Xd))  # predict operand, once per fit
+            dv.mark("pack")
         return self
 
     _keep_factors = True  # `.W` stays available; set False to free L and M right after fit

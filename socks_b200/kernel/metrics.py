@@ -183,6 +183,7 @@ class Factorization:
         st = dv.stream()
         lib = _lib.load()
         self.L = dv.empty(npad, npad)
+        dv.mark("start")
         if Ud is None and kind in (KIND_RBF, KIND_ABEL):
             _lib.call("socks_gram_sym_kernel", int(kind), dv.ptr(Zd), n, d, float(kparams[0]), int(kparams[1]),
                       float(diag_add), dv.ptr(self.L), npad, st)
@@ -193,6 +194,7 @@ class Factorization:
         self.info = torch.zeros(1, dtype=torch.int32, device=Zd.device)
         self._M = dv.empty(npad, npad)
         wk = dv.work(lib.socks_trtri_work_bytes(n))
+        dv.mark("gram_sym")
         if two_pass:
             dinv = dv.work(lib.socks_potrf_work_bytes(n))
             _lib.call("socks_potrf", dv.ptr(self.L), n, npad, dv.ptr(dinv), dv.ptr(self.info), st)
@@ -202,6 +204,7 @@ class Factorization:
                       1 if keep_l else 0, st)
             if not keep_l:
                 self.L = None  # only scratch is left in it
+        dv.mark("potrf_inv")
         self._w = None
         self._W = None
 
@@ -241,6 +244,7 @@ class Factorization:
             self._w = dv.empty(self.n)
             wk = dv.work(_lib.load().socks_reduce_work_bytes(self.np))
             _lib.call("socks_diag_inv", dv.ptr(M), self.n, self.np, dv.ptr(self._w), dv.ptr(wk), dv.stream())
+            dv.mark("diag_inv")
         return self._w
 
     def full(self):

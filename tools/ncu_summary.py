@@ -1,7 +1,9 @@
 """Summarise an .ncu-rep (first kernel) into text: key sections, top stall reasons, DRAM traffic.
-Usage: python tools/ncu_summary.py report.ncu-rep > profiles/<name>.txt"""
+Usage: python tools/ncu_summary.py report.ncu-rep [--json profiles/<name>.json --shape N,M,T,d] > profiles/<name>.txt
+The JSON (kernel name, launch shape, DRAM bytes per launch, duration) is what bench.py reads for `roofline.traffic`."""
 import csv
 import io
+import json
 import subprocess
 import sys
 
@@ -42,3 +44,24 @@ for i, name in enumerate(h):
             pass
 tot = sum(x for x, _ in st) or 1.0
 print("# warp stall samples: " + ", ".join(f"{n} {100 * x / tot:.1f}%" for x, n in sorted(st, reverse=True)[:7]))
+
+if "--json" in sys.argv:
+    def num(name):
+        i = h.index(name)
+        x = float(v[i].replace(",", ""))
+        unit = u[i].lower()
+        scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1,
+                 "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1}.get(unit, 1)
+        return x * scale
+
+    rec = {"kernel": rows[1][ik].replace("void ", "").replace("socks::", ""), "report": rep,
+           "dram_bytes_read": num("dram__bytes_read.sum"), "dram_bytes_write": num("dram__bytes_write.sum"),
+           "duration_s": num("gpu__time_duration.sum")}
+    if "--shape" in sys.argv:
+        rec["shape"] = [int(x) for x in sys.argv[sys.argv.index("--shape") + 1].split(",")]
+    for name in ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+                 "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+                 "launch__registers_per_thread"):
+        if name in h:
+            rec[name] = float(v[h.index(name)].replace(",", ""))
+    json.dump(rec, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
