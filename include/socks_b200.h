@@ -124,6 +124,11 @@ int socks_pad_spd(const double* Gin, int64_t n, int64_t ldin, double diag_add, d
  * blocks (L21 = A21 inv(L11)^T), so there are no leaf TRSM kernels.  work: socks_trtri_work_bytes(n). */
 int socks_potrf_inv(double* G, int64_t n, int64_t ldg, double* M, int64_t ldm, double* work, int* info_dev,
                     int keep_l, socks_stream_t stream);
+/* socks_potrf_inv factors right-looking over nb-wide block columns with a look-ahead of one (the next diagonal block and
+ * panel run on an internal high-priority stream while the trailing update proceeds; the library owns that stream and
+ * joins it back into `stream` before returning).  nb: multiple of 128, default 1024; 0 = single-stream recursion.
+ * Returns the previous value. */
+int socks_potrf_inv_set_block(int nb);
 
 /* w[i] = sum_k M[k][i]^2 = diag(inv(G))[i]  (the only part of W the SR algorithms use:
  * np.einsum("ii,ij->ij", W, CXY), kernel_sr.py:45).  work: socks_reduce_work_bytes(np). */

@@ -11,6 +11,9 @@
 //   trtri     = M11 = inv(L11), M22 = inv(L22), M21 = -(M22 L21) M11
 // Roofline: N^3/3 flops each for potrf, trtri and lauum; FP64 DMMA (tensor pipe) bound.
 #include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "gemm_f64.cuh"
 #include "reduce.cuh"
@@ -460,6 +463,134 @@ static void potrf_inv_rec(CholCtx& cx, double* A, int64_t lda, double* M, int64_
     cx.note(gemm_f64<false, false>(work, n1, M, ldm, M21, ldm, n2, n1, n1, -1.0, 0.0, GEMM_B_K_GE_N, 0, cx.st));
 }
 
+// ---- look-ahead variant (what socks_potrf_inv runs) -------------------------------------------------------
+// The pure recursion above serialises ~N/128 single-CTA leaves (64 us each, 147 SMs idle) and the tiny GEMMs of its
+// bottom levels behind the large updates: 82 % of the DMMA peak at N = 20 000 while the GEMMs alone reach 95 %
+// (profiles/r1_bench_launch_summary.txt).  Here the factorisation is right-looking over NB-wide block columns with a
+// look-ahead of one: the trailing update of step k is split into the next block column (done first) and the rest, and
+// the whole critical path of step k+1 -- factor+invert of the NB x NB diagonal block (the recursion above, on that
+// block only) and the panel solve L21 = A21 inv(L_kk)^T -- runs on a second, high-priority stream while the rest of
+// step k's update keeps the SMs busy.  inv(L) is then completed by the same block recursion as before
+// (M21 = -(M22 L21) M11, large GEMMs only).  Same arithmetic per block as the pure recursion, different association
+// across blocks, i.e. results differ at the rounding level (~cond * eps; tests compare both).
+struct Lookahead {
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_panel = nullptr, ev_col = nullptr;
+    bool ready = false;
+};
+
+static Lookahead* lookahead_for_device(int* rc_out) {
+    static Lookahead la[SOCKS_MAX_DEVICES];
+    static std::mutex mu;
+    *rc_out = SOCKS_OK;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= SOCKS_MAX_DEVICES) {
+        *rc_out = SOCKS_ECUDA;
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    Lookahead& l = la[dev];
+    if (!l.ready) {
+        int lo = 0, hi = 0;
+        cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = greatest priority (numerically lowest)
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&l.s2, cudaStreamNonBlocking, hi);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l.ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l.ev_panel, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l.ev_col, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            set_error("socks_potrf_inv: creating the look-ahead stream failed: %s", cudaGetErrorString(e));
+            *rc_out = SOCKS_ECUDA;
+            return nullptr;
+        }
+        l.ready = true;
+    }
+    return &l;
+}
+
+static int g_potrf_nb = 1024;  // block-column width of the look-ahead factorisation (multiple of 128; 0 = pure recursion)
+
+// inv(L) from its diagonal-block inverses: the merges M21 = -(M22 L21) M11 of the block recursion, in post-order
+// (children before parents).  A merge over blocks [lo, hi) is ready as soon as block hi-1 has been factored, reads L
+// only in rows [mid, hi) x columns [lo, mid) -- which no later trailing update reads -- and overwrites exactly that.
+struct Merge {
+    int lo, mid, hi;
+};
+static void plan_merges(int lo, int hi, std::vector<Merge>& out) {
+    if (hi - lo <= 1) return;
+    const int mid = lo + (hi - lo) / 2;
+    plan_merges(lo, mid, out);
+    plan_merges(mid, hi, out);
+    out.push_back(Merge{lo, mid, hi});
+}
+static void run_merge(CholCtx& cx, double* M, int64_t ldm, const int64_t* bnd, const Merge& g, double* work) {
+    const int64_t o1 = bnd[g.lo], o2 = bnd[g.mid], n1 = bnd[g.mid] - bnd[g.lo], n2 = bnd[g.hi] - bnd[g.mid];
+    double* M11 = M + o1 * ldm + o1;
+    double* M21 = M + o2 * ldm + o1;  // holds L21
+    double* M22 = M + o2 * ldm + o2;
+    cx.note(gemm_f64<false, false>(M22, ldm, M21, ldm, work, n1, n2, n1, n2, 1.0, 0.0, GEMM_A_K_LE_M, 0, cx.st));
+    cx.note(gemm_f64<false, false>(work, n1, M11, ldm, M21, ldm, n2, n1, n1, -1.0, 0.0, GEMM_B_K_GE_N, 0, cx.st));
+}
+
+static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, int64_t np, double* work, int* info,
+                               bool keep_l, cudaStream_t s1, int64_t NB) {
+    int rc;
+    Lookahead* la = lookahead_for_device(&rc);
+    if (!la) return rc;
+    CholCtx c1{s1}, c2{la->s2};
+    std::vector<int64_t> bnd;
+    for (int64_t o = 0; o < np; o += NB) bnd.push_back(o);
+    bnd.push_back(np);
+    const int nb = (int)bnd.size() - 1;
+    std::vector<Merge> merges;
+    plan_merges(0, nb, merges);
+    constexpr int kSmallMerge = 4;  // merges spanning <= 4 block columns ride on the panel stream
+    c1.note(cudaEventRecord(la->ev_fork, s1));  // everything already enqueued on s1 (the Gram build) precedes s2's work
+    c2.note(cudaStreamWaitEvent(la->s2, la->ev_fork, 0));
+    for (int k = 0; k < nb; ++k) {
+        const int64_t k0 = bnd[k], bk = bnd[k + 1] - k0, rem = np - k0 - bk;
+        double* Akk = A + k0 * lda + k0;
+        double* Mkk = M + k0 * ldm + k0;
+        if (k > 0) c2.note(cudaStreamWaitEvent(la->s2, la->ev_col, 0));
+        potrf_inv_rec(c2, Akk, lda, Mkk, ldm, bk, work, info, k0, keep_l);
+        if (rem > 0) {  // panel: L21 = A21 * inv(L_kk)^T, stored in M's (2,1) block until the inverse overwrites it
+            double* A21 = A + (k0 + bk) * lda + k0;
+            double* L21 = M + (k0 + bk) * ldm + k0;
+            c2.note(gemm_f64<false, true>(A21, lda, Mkk, ldm, L21, ldm, rem, bk, bk, 1.0, 0.0, GEMM_B_K_LE_N, 0, c2.st));
+            if (keep_l) {
+                copy_block_kernel<<<(unsigned)std::min<int64_t>(4096, ceil_div(rem * bk, 256)), 256, 0, c2.st>>>(
+                    L21, ldm, A21, lda, rem, bk);
+                c2.note(cudaGetLastError());
+            }
+        }
+        c2.note(cudaEventRecord(la->ev_panel, la->s2));
+        c1.note(cudaStreamWaitEvent(s1, la->ev_panel, 0));
+        // small merges of the inverse that end at this block: on the panel stream, in the shadow of s1's column update
+        for (const Merge& g : merges)
+            if (g.hi == k + 1 && g.hi - g.lo <= kSmallMerge) run_merge(c2, M, ldm, bnd.data(), g, work);
+        if (rem == 0) break;
+        const int64_t b1 = bnd[k + 2] - bnd[k + 1];
+        const double* L21 = M + (k0 + bk) * ldm + k0;
+        double* A22 = A + (k0 + bk) * lda + (k0 + bk);
+        // next block column first (rows rem x cols b1), then the rest of the trailing lower triangle
+        c1.note(gemm_f64<false, true>(L21, ldm, L21, ldm, A22, lda, rem, b1, bk, -1.0, 1.0, 0, 1, s1));
+        c1.note(cudaEventRecord(la->ev_col, s1));
+        if (rem > b1)
+            c1.note(gemm_f64<false, true>(L21 + b1 * ldm, ldm, L21 + b1 * ldm, ldm, A22 + b1 * lda + b1, lda, rem - b1,
+                                          rem - b1, bk, -1.0, 1.0, 0, 1, s1));
+    }
+    // join, then the large merges (most of the inverse's flops: machine-filling GEMMs) in post-order on the caller's stream
+    c2.note(cudaEventRecord(la->ev_panel, la->s2));
+    c1.note(cudaStreamWaitEvent(s1, la->ev_panel, 0));
+    for (const Merge& g : merges)
+        if (g.hi - g.lo > kSmallMerge) run_merge(c1, M, ldm, bnd.data(), g, work);
+    const cudaError_t err = (c1.err != cudaSuccess) ? c1.err : c2.err;
+    if (err != cudaSuccess) {
+        set_error("socks_potrf_inv: CUDA call failed: %s", cudaGetErrorString(err));
+        return SOCKS_ECUDA;
+    }
+    return SOCKS_OK;
+}
+
 static int chol_configure() {
     static std::atomic<bool> done[SOCKS_MAX_DEVICES];  // dynamic-smem opt-in is per device
     int dev = 0;
@@ -560,13 +691,24 @@ extern "C" int socks_potrf_inv(double* G, int64_t n, int64_t ldg, double* M, int
     SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 15) == 0, 6);
     SOCKS_CHECK_ARG(info_dev != nullptr, 7);
     if ((rc = chol_configure())) return rc;
+    const int64_t np = socks_padded_dim(n);
+    if (g_potrf_nb > 0 && np > 2 * g_potrf_nb)
+        return potrf_inv_lookahead(G, ldg, M, ldm, np, work, info_dev, keep_l != 0, (cudaStream_t)stream, g_potrf_nb);
     CholCtx cx{(cudaStream_t)stream};
-    potrf_inv_rec(cx, G, ldg, M, ldm, socks_padded_dim(n), work, info_dev, 0, keep_l != 0);
+    potrf_inv_rec(cx, G, ldg, M, ldm, np, work, info_dev, 0, keep_l != 0);
     if (cx.err != cudaSuccess) {
         set_error("socks_potrf_inv: CUDA launch failed: %s", cudaGetErrorString(cx.err));
         return SOCKS_ECUDA;
     }
     return SOCKS_OK;
+}
+
+// Block-column width of socks_potrf_inv's look-ahead factorisation (multiple of 128); 0 selects the pure recursion.
+// Returns the previous value.  Tuning / measurement knob (tools/run_potrf.py); not thread-safe against running calls.
+extern "C" int socks_potrf_inv_set_block(int nb) {
+    const int old = g_potrf_nb;
+    if (nb >= 0 && nb % LF == 0) g_potrf_nb = nb;
+    return old;
 }
 
 extern "C" int socks_diag_inv(const double* M, int64_t n, int64_t ldm, double* w, double* work,

@@ -146,6 +146,41 @@ def test_factorization_pieces(n, d, sigma, lam, with_u, two_pass):
         assert np.array_equal(Wp[n:, n:], np.eye(npad - n)) and not Wp[n:, :n].any() and not Wp[:n, n:].any()
 
 
+@pytest.mark.parametrize("n,nb,keep_l", [(3300, 1024, True), (2900, 512, False), (1400, 256, True), (2100, 1024, False)])
+def test_potrf_inv_lookahead_matches_recursion_and_numpy(n, nb, keep_l):
+    """socks_potrf_inv's look-ahead factorisation (second stream, block columns of `nb`, ragged last block) against the
+    single-stream recursion (nb = 0) and float64 numpy: L residual, M L = I, diag(inv G)."""
+    torch, dv, _lib, mt = _mods()
+    lib = _lib.load()
+    rng = np.random.default_rng(n)
+    X = rng.uniform(-1.1, 1.1, (n, 2))
+    G = orc.rbf_kernel(X, X, 0.2)
+    G[np.diag_indices(n)] += 1e-4 * n
+    cond = np.linalg.cond(G)
+    res = {}
+    old = lib.socks_potrf_inv_set_block(nb)
+    try:
+        for mode, block in (("lookahead", nb), ("recursion", 0)):
+            lib.socks_potrf_inv_set_block(block)
+            fac = mt.factorize(X, None, mt.RBFSpec(sigma=0.2), 1e-4, keep_l=keep_l)
+            fac.check()
+            res[mode] = (np.tril(fac.inverse_factor()[:n, :n].cpu().numpy()), fac.diag().cpu().numpy(),
+                         np.tril(fac.L[:n, :n].cpu().numpy()) if keep_l else None)
+    finally:
+        lib.socks_potrf_inv_set_block(old)
+    M, w, L = res["lookahead"]
+    M0, w0, L0 = res["recursion"]
+    Lref = np.linalg.cholesky(G)
+    if keep_l:
+        assert np.linalg.norm(L @ L.T - G) / np.linalg.norm(G) < 1e-14
+        assert np.linalg.norm(L - L0) / np.linalg.norm(L0) < 1e-13
+    assert np.linalg.norm(M @ Lref - np.eye(n)) / np.sqrt(n) < 50 * np.sqrt(cond) * 2.0 ** -53 * n ** 0.5
+    assert np.linalg.norm(M - M0) / np.linalg.norm(M0) <= 100 * cond * 2.0 ** -53
+    wref = np.diag(np.linalg.inv(G))
+    assert np.max(np.abs(w - wref) / wref) <= 100 * cond * 2.0 ** -53
+    assert np.max(np.abs(w - w0) / w0) <= 100 * cond * 2.0 ** -53
+
+
 def test_not_positive_definite_reports():
     torch, dv, _lib, mt = _mods()
     n = 130
