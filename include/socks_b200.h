@@ -124,11 +124,9 @@ int socks_pad_spd(const double* Gin, int64_t n, int64_t ldin, double diag_add, d
  * blocks (L21 = A21 inv(L11)^T), so there are no leaf TRSM kernels.  work: socks_trtri_work_bytes(n). */
 int socks_potrf_inv(double* G, int64_t n, int64_t ldg, double* M, int64_t ldm, double* work, int* info_dev,
                     int keep_l, socks_stream_t stream);
-/* socks_potrf_inv factors right-looking over nb-wide block columns with a look-ahead of one (the next diagonal block and
- * panel run on an internal high-priority stream while the trailing update proceeds; the library owns that stream and
- * joins it back into `stream` before returning).  nb: multiple of 128, default 1024; 0 = single-stream recursion.
- * Returns the previous value. */
-int socks_potrf_inv_set_block(int nb);
+/* socks_potrf_inv factors right-looking over 1024-wide block columns with a look-ahead of one: the next diagonal block
+ * and panel run on an internal high-priority stream while the trailing update proceeds; the library owns that stream
+ * and joins it back into `stream` before returning. */
 
 /* w[i] = sum_k M[k][i]^2 = diag(inv(G))[i]  (the only part of W the SR algorithms use:
  * np.einsum("ii,ij->ij", W, CXY), kernel_sr.py:45).  work: socks_reduce_work_bytes(np). */
@@ -243,11 +241,64 @@ int socks_fwd_weights(const double* X, int64_t n, int d, double scale, int divid
  * occurrence on ties (gym_socks/algorithms/control/common.py:96-100, 166-174). idx_dev: device int. */
 int socks_argmin_masked(const double* C, const double* D, int P, int* idx_dev, socks_stream_t stream);
 
-/* ---- Measurement helpers (tools/, bench.py): register-resident FP64 peak probes -------- */
-int socks_probe_fp64(int mode, int iters, double* out_dev, int blocks, socks_stream_t stream);
-/* clock64() at the phase boundaries of the 128 x 128 leaf factorisation (cycles: 16 int64 on the device). */
-int socks_dev_potf2_phases(double* A, int64_t lda, double* dinv, int* info_dev, long long* cycles,
-                           socks_stream_t stream);
+/* ---- Composite entry points: one enqueue per algorithm step of the reference's classes ------------------ */
+
+/* KernelSR.fit after the inverse (kernel_sr.py:286-309): B = diag(w) K(X,Y) resident in `work`, in-place recursion into
+ * vf (T x n, row stride ldvf); if pack != NULL also socks_sr_pack (the predict operand). */
+int64_t socks_sr_fit_work_bytes(int64_t n);
+int socks_sr_fit(const double* X, const double* Y, const double* w, int64_t n, int d, double scale, int divide,
+                 const double* tubes, int problem, int T, double* vf, int64_t ldvf, double* pack, double* work,
+                 socks_stream_t stream);
+
+/* KernelMaximalSR.fit after the inverse (kernel_sr_max.py:323-366): CUA = K(U,A) (n x P, out), value functions vf
+ * (T x n, out).  w = diag(inv(K(X,X) * K(U,U) + lambda N I)). */
+int64_t socks_srmax_fit_work_bytes(int64_t n, int P);
+int socks_srmax_fit(const double* X, const double* Y, const double* U, const double* A, const double* w, int64_t n,
+                    int d, int du, int P, double scale, int divide, const double* tubes, int problem, int T,
+                    double* CUA, double* vf, int64_t ldvf, double* work, socks_stream_t stream);
+
+/* KernelMaximalSR.predict (kernel_sr_max.py:368-384): out (T x m); test points are processed `chunk` at a time (one
+ * Gram tile + one DMMA GEMM for all T rows + fused divide/max/step per chunk). */
+int64_t socks_srmax_predict_work_bytes(int64_t n, int P, int T, int64_t chunk);
+int socks_srmax_predict(const double* X, const double* w, const double* vf, int64_t ldvf, const double* CUA, int64_t n,
+                        int d, int P, double scale, int divide, const double* pts, int64_t m, const double* tubes,
+                        int problem, int T, double* out, int64_t ldout, double* work, int64_t chunk,
+                        socks_stream_t stream);
+
+/* KernelControlFwd.__call__ (kernel_control_fwd.py:217-232): scores[r][a] = c_r^T W (K(X,s) * CUA)[:, a] for the R <= 2
+ * row vectors c (float32-rounded cost / constraint values as float64, row stride ldc); W = inv(G) (n x n, ld ldw);
+ * scores is R x P contiguous.  socks_fwd_policy adds the heuristic selection of control/common.py:96-100,166-174
+ * (idx_dev: device int). */
+int64_t socks_fwd_scores_work_bytes(int64_t n, int P);
+int socks_fwd_scores(const double* W, int64_t ldw, const double* X, const double* CUA, int64_t n, int d, int P,
+                     double scale, int divide, const double* state, const double* c, int64_t ldc, int R,
+                     double* scores, double* work, socks_stream_t stream);
+int socks_fwd_policy(const double* W, int64_t ldw, const double* X, const double* CUA, int64_t n, int d, int P,
+                     double scale, int divide, const double* state, const double* c, int64_t ldc, int R,
+                     double* scores, double* work, int* idx_dev, socks_stream_t stream);
+
+/* *result_dev = np.median of the n x m matrix of squared (squared != 0) or plain Euclidean distances: the sigma=None
+ * bandwidth of rbf_kernel (metrics.py:130-131) / abel_kernel (:199-200).  Exact order statistics by radix select. */
+int64_t socks_median_work_bytes(int64_t n, int64_t m);
+int socks_median_sq_dist(const double* X, int64_t n, const double* Y, int64_t m, int d, int squared, double* work,
+                         double* result_dev, socks_stream_t stream);
+
+/* ---- Context and collectives (optional: every entry point above is stateless and takes the caller's stream) ----
+ * A context owns a non-blocking stream, a grow-only device workspace and, after socks_comm_init, an NCCL
+ * communicator (libnccl.so.2 is bound at run time with dlopen; there is no link-time dependency).  One context per
+ * GPU / rank, used from one thread.  socks_bcast / socks_allgather enqueue on the context stream: the single
+ * broadcast of the fitted state (X, w, value functions -- or W for the control algorithms) and the gather of the
+ * result shards are the only collectives the path has. */
+typedef struct socks_ctx socks_ctx;
+int socks_ctx_create(int device, socks_ctx** out);
+int socks_ctx_destroy(socks_ctx* ctx);
+socks_stream_t socks_ctx_stream(socks_ctx* ctx);
+int socks_ctx_workspace(socks_ctx* ctx, int64_t bytes, void** ptr);
+int socks_ctx_synchronize(socks_ctx* ctx);
+int socks_comm_unique_id(void* id128);                                  /* 128 bytes, made on one rank, sent to all  */
+int socks_comm_init(socks_ctx* ctx, int rank, int nranks, const void* id128);
+int socks_bcast(socks_ctx* ctx, void* ptr, int64_t bytes, int root);    /* in place                                   */
+int socks_allgather(socks_ctx* ctx, const void* send, void* recv, int64_t bytes_per_rank);
 
 #ifdef __cplusplus
 }

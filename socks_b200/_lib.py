@@ -15,7 +15,7 @@ _lib = None
 
 _P, _I, _L, _D = c_void_p, c_int, c_int64, c_double
 
-# name -> (restype, argtypes); must list every symbol include/socks_b200.h declares
+# name -> (restype, argtypes); must list every symbol include/socks_b200.h and include/socks_b200_dev.h declare
 SIGNATURES = {
     "socks_version": (_I, []),
     "socks_last_error": (c_char_p, []),
@@ -57,6 +57,26 @@ SIGNATURES = {
     "socks_gemv_t": (_I, [_P, _L, _L, _L, _P, _L, _I, _P, _L, _P, _P]),
     "socks_fwd_weights": (_I, [_P, _L, _I, _D, _I, _P, _P, _L, _I, _P, _L, _P]),
     "socks_argmin_masked": (_I, [_P, _P, _I, _P, _P]),
+    "socks_sr_fit_work_bytes": (_L, [_L]),
+    "socks_sr_fit": (_I, [_P, _P, _P, _L, _I, _D, _I, _P, _I, _I, _P, _L, _P, _P, _P]),
+    "socks_srmax_fit_work_bytes": (_L, [_L, _I]),
+    "socks_srmax_fit": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _D, _I, _P, _I, _I, _P, _P, _L, _P, _P]),
+    "socks_srmax_predict_work_bytes": (_L, [_L, _I, _I, _L]),
+    "socks_srmax_predict": (_I, [_P, _P, _P, _L, _P, _L, _I, _I, _D, _I, _P, _L, _P, _I, _I, _P, _L, _P, _L, _P]),
+    "socks_fwd_scores_work_bytes": (_L, [_L, _I]),
+    "socks_fwd_scores": (_I, [_P, _L, _P, _P, _L, _I, _I, _D, _I, _P, _P, _L, _I, _P, _P, _P]),
+    "socks_fwd_policy": (_I, [_P, _L, _P, _P, _L, _I, _I, _D, _I, _P, _P, _L, _I, _P, _P, _P, _P]),
+    "socks_median_work_bytes": (_L, [_L, _L]),
+    "socks_median_sq_dist": (_I, [_P, _L, _P, _L, _I, _I, _P, _P, _P]),
+    "socks_ctx_create": (_I, [_I, _P]),
+    "socks_ctx_destroy": (_I, [_P]),
+    "socks_ctx_stream": (_P, [_P]),
+    "socks_ctx_workspace": (_I, [_P, _L, _P]),
+    "socks_ctx_synchronize": (_I, [_P]),
+    "socks_comm_unique_id": (_I, [_P]),
+    "socks_comm_init": (_I, [_P, _I, _I, _P]),
+    "socks_bcast": (_I, [_P, _P, _L, _I]),
+    "socks_allgather": (_I, [_P, _P, _P, _L]),
     "socks_dev_potf2_phases": (_I, [_P, _L, _P, _P, _P, _P]),
     "socks_probe_fp64": (_I, [_I, _I, _P, _I, _P]),
 }

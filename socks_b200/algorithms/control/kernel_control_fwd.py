@@ -92,44 +92,68 @@ class KernelControlFwd:
         if self.constraint_fn is not None:
             self.constraint_fn = partial(self.constraint_fn, state=Yarr)  # :206-207
         lib = _lib.load()
-        self._wk = dv.work(max(lib.socks_reduce_work_bytes(n), lib.socks_reduce_work_bytes(self._P)))
+        self._wk = dv.work(lib.socks_fwd_scores_work_bytes(n, self._P))
         self._idx = torch.zeros(1, dtype=torch.int32, device=self._Xd.device)
+        self._idx_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        # per-call inputs travel in ONE pinned buffer -> ONE host-to-device copy: [state (d, padded to 8) | cost | constraint]
+        self._ldc = dv.even(n)
+        self._stage_h = torch.zeros(8 + 2 * self._ldc, dtype=torch.float64).pin_memory()
+        self._stage_d = dv.zeros(8 + 2 * self._ldc)
+        self._scores = dv.zeros(2, self._P)
+        self._h2d_done = None
         return self
+
+    def _enqueue(self, time, state, policy):
+        """Upload (state, float32-rounded cost/constraint rows) and enqueue socks_fwd_scores / socks_fwd_policy
+        (csrc/compose.cu): z = W c, q = z * K(X, s), scores = q^T CUA [, masked argmin].  Returns R."""
+        n, d, P = self._n, self._d, self._P
+        sh = np.asarray(state, dtype=np.float64).reshape(-1)
+        if sh.size != d:
+            raise ValueError("KernelControlFwd evaluates one state per call (kernel_control_fwd.py:222 broadcasts "
+                             "an (N, 1) column against CUA).")
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()  # the previous call's copy has left the pinned buffer
+        host = self._stage_h.numpy()
+        host[:d] = sh
+        host[8:8 + n] = np.array(self.cost_fn(time=time), dtype=np.float32)  # float32 rounding, :225
+        R = 1
+        if self.constraint_fn is not None:
+            host[8 + self._ldc:8 + self._ldc + n] = np.array(self.constraint_fn(time=time), dtype=np.float32)  # :231
+            R = 2
+        self._stage_d.copy_(self._stage_h, non_blocking=True)
+        self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record()
+        scale, divide = self._spec.params_for(self._Xd, self._Xd)
+        base = self._stage_d.data_ptr()
+        args = (dv.ptr(self._Wd), self._np, dv.ptr(self._Xd), dv.ptr(self._CUA), n, d, P, float(scale), int(divide), base,
+                base + 64, self._ldc, R, dv.ptr(self._scores), dv.ptr(self._wk))
+        if policy:
+            _lib.call("socks_fwd_policy", *args, dv.ptr(self._idx), dv.stream())
+        else:
+            _lib.call("socks_fwd_scores", *args, dv.stream())
+        return R
 
     def scores(self, time=0, state=None):
         """Device (R, P) tensor: row 0 = cost scores C, row 1 = constraint scores D (if constrained)."""
-        n, d, P = self._n, self._d, self._P
-        st = dv.stream()
-        sd = dv.to_dev(np.asarray(state, dtype=np.float64).reshape(-1))
-        if sd.numel() != d:
-            raise ValueError("KernelControlFwd evaluates one state per call (kernel_control_fwd.py:222 broadcasts "
-                             "an (N, 1) column against CUA).")
-        rows = [np.array(self.cost_fn(time=time), dtype=np.float32)]  # float32 rounding, :225
-        if self.constraint_fn is not None:
-            rows.append(np.array(self.constraint_fn(time=time), dtype=np.float32))  # :231
-        R = len(rows)
-        c = dv.to_dev(np.stack(rows).astype(np.float64))  # (R, n)
-        z = dv.empty(R, n)
-        _lib.call("socks_gemv_t", dv.ptr(self._Wd), n, n, self._np, dv.ptr(c), n, R, dv.ptr(z), n, dv.ptr(self._wk), st)
-        q = dv.empty(R, n)
-        scale, divide = self._spec.params_for(self._Xd, sd.reshape(1, d))
-        _lib.call("socks_fwd_weights", dv.ptr(self._Xd), n, d, float(scale), int(divide), dv.ptr(sd), dv.ptr(z), n, R, dv.ptr(q), n, st)
-        y = dv.empty(R, P)
-        _lib.call("socks_gemv_t", dv.ptr(self._CUA), n, P, P, dv.ptr(q), n, R, dv.ptr(y), P, dv.ptr(self._wk), st)
-        return y
+        if self._spec.data_dependent:
+            raise NotImplementedError("KernelControlFwd with sigma=None: the bandwidth of K(X, s) would be the median of "
+                                      "one column; pass an explicit sigma")
+        R = self._enqueue(time, state, policy=False)
+        return self._scores[:R].clone()
 
     def __call__(self, time=0, state=None, *args, **kwargs):
         if state is None:
             print("Must supply a state to the policy.")
             return None
-        y = self.scores(time=time, state=state)
         if self.heuristic is True:
-            Dp = dv.ptr(y[1]) if y.shape[0] > 1 else 0
-            _lib.call("socks_argmin_masked", dv.ptr(y[0]), Dp, self._P, dv.ptr(self._idx), dv.stream())
-            idx = int(self._idx.item())
+            self._enqueue(time, state, policy=True)
+            self._idx_host.copy_(self._idx, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            idx = int(self._idx_host[0])
         else:
-            yh = y.cpu().numpy()
-            sol = compute_solution(yh[0], yh[1] if yh.shape[0] > 1 else None, heuristic=False)
+            R = self._enqueue(time, state, policy=False)
+            yh = self._scores[:R].cpu().numpy()
+            sol = compute_solution(yh[0], yh[1] if R > 1 else None, heuristic=False)
             idx = int(np.argmax(sol))
         return np.array(self.A[idx], dtype=np.float32)
 

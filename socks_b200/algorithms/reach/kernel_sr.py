@@ -107,13 +107,30 @@ class KernelSR:
         Xd, Yd = dv.to_dev(Xh), dv.to_dev(Yh)
         self._Xd, self._w = Xd, w
         self._tubes = pack_tubes(self.constraint_tube, self.target_tube, T, d)
+        lib = _lib.load()
+        vf = dv.empty(max(T, 1), n)
+        kparams = self._spec.params_for(Xd, Yd)
+        fused_pack = self._spec.kind == 0 and not self._spec.data_dependent and T >= 1
+        if self._spec.kind == 0 and T >= 1 and dv.stage_marks is None:
+            # one enqueue: beta = diag(w) K(X,Y), in-place recursion, predict operand (csrc/compose.cu: socks_sr_fit)
+            logger.debug("Computing covariance matrix and value functions.")
+            wk = dv.work(lib.socks_sr_fit_work_bytes(n))
+            pack = dv.work(lib.socks_sr_pack_bytes(n, d, T)) if fused_pack else None
+            _lib.call("socks_sr_fit", dv.ptr(Xd), dv.ptr(Yd), dv.ptr(w), n, d, float(kparams[0]), int(kparams[1]),
+                      dv.ptr(self._tubes), PROBLEM_CODE[self.problem], T, dv.ptr(vf), n, dv.ptr(pack), dv.ptr(wk),
+                      dv.stream())
+            self._vf = vf[:T]
+            if fused_pack:
+                self._pack = pack
+                self._pack_key = (float(kparams[0]), int(kparams[1]), self._vf.data_ptr(), self._w.data_ptr())
+            self._vf_host = None
+            return self
+        # the same kernels enqueued one by one: other kernel families, and when stage timing is on (bench.py)
         logger.debug("Computing covariance matrix.")
         ldb = dv.even(n)
-        B = gram_dev(Xd, Yd, self._spec.params_for(Xd, Yd), kind=self._spec.kind, extra=self._spec.extra, rowscale=w, ld=ldb)  # un-normalised beta, kernel_sr.py:45
+        B = gram_dev(Xd, Yd, kparams, kind=self._spec.kind, extra=self._spec.extra, rowscale=w, ld=ldb)  # un-normalised beta, kernel_sr.py:45
         dv.mark("gram_cross")
         logger.debug("Computing value functions.")
-        vf = dv.empty(max(T, 1), n)
-        lib = _lib.load()
         wk = dv.work(lib.socks_reduce_work_bytes(n) + 8 * (n + 2))
         if T >= 1:
             _lib.call("socks_sr_recursion", dv.ptr(B), n, n, ldb, dv.ptr(Yd), d, dv.ptr(self._tubes),
@@ -122,8 +139,8 @@ class KernelSR:
         self._vf = vf[:T]
         self._vf_host = None
         del B
-        if not self._spec.data_dependent and self._spec.kind == 0 and T >= 1:
-            self._packed(self._spec.params_for(Xd, Xd))  # predict operand, once per fit
+        if fused_pack:
+            self._packed(kparams)  # predict operand, once per fit
             dv.mark("pack")
         return self
 

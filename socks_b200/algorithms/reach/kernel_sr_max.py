@@ -103,20 +103,34 @@ class KernelMaximalSR:
         Xd, Yd, Ud, Ad = dv.to_dev(Xh), dv.to_dev(Yh), dv.to_dev(Uh), dv.to_dev(Ah)
         self._Xd, self._w = Xd, w
         self._tubes = pack_tubes(self.constraint_tube, self.target_tube, T, d)
+        lib = _lib.load()
+        st = dv.stream()
+        prob = PROBLEM_CODE[self.problem]
+        vf = dv.empty(max(T, 1), n)
+        kp_xy, kp_ua = self._spec.params_for(Xd, Yd), self._spec.params_for(Ud, Ad)
+        if self._spec.kind == 0 and kp_xy == kp_ua and T >= 1:
+            # one enqueue (csrc/compose.cu: socks_srmax_fit): CUA, K(X,Y), normaliser GEMM, T-1 x (pack, GEMM, max/step)
+            logger.debug("Computing covariance matrices and value functions.")
+            CUA = dv.empty(n, P)
+            wk = dv.work(lib.socks_srmax_fit_work_bytes(n, P))
+            _lib.call("socks_srmax_fit", dv.ptr(Xd), dv.ptr(Yd), dv.ptr(Ud), dv.ptr(Ad), dv.ptr(w), n, d, Ud.shape[1], P,
+                      float(kp_xy[0]), int(kp_xy[1]), dv.ptr(self._tubes), prob, T, dv.ptr(CUA), dv.ptr(vf), n,
+                      dv.ptr(wk), st)
+            self._CUA = CUA
+            self._vf = vf[:T]
+            self._vf_host = None
+            return self
         logger.debug("Computing covariance matrices.")
-        CUA = gram_dev(Ud, Ad, self._spec.params_for(Ud, Ad), kind=self._spec.kind, extra=self._spec.extra, ld=P)  # (n, P) contiguous, kernel_sr_max.py:332
+        CUA = gram_dev(Ud, Ad, kp_ua, kind=self._spec.kind, extra=self._spec.extra, ld=P)  # (n, P) contiguous, kernel_sr_max.py:332
         self._CUA = CUA
         # K(X, Y) as the GEMM's left operand: (K = npad rows) x (m = npad columns), zero padding
         Kmat = dv.zeros(npad, npad)
-        gram_dev(Xd, Yd, self._spec.params_for(Xd, Yd), kind=self._spec.kind, extra=self._spec.extra, out=Kmat, ld=npad)
+        gram_dev(Xd, Yd, kp_xy, kind=self._spec.kind, extra=self._spec.extra, out=Kmat, ld=npad)
         logger.debug("Computing value functions.")
-        vf = dv.empty(max(T, 1), n)
         ldbm = -(-P // 128) * 128
         Bm = dv.empty(npad, ldbm)
         Cm = dv.empty(npad, ldbm)
         Den = dv.empty(npad, ldbm)
-        st = dv.stream()
-        prob = PROBLEM_CODE[self.problem]
         # vf[T-1] = 1_target(Y) first (kernel_sr_max.py:59): the first pack below reads it
         _lib.call("socks_srmax_step", dv.ptr(Cm), ldbm, 0, 0, n, P, 1, 0, dv.ptr(Yd), d, dv.ptr(self._tubes), prob, T,
                   dv.ptr(vf), n, 1, st)
@@ -150,8 +164,15 @@ class KernelMaximalSR:
         if kparams is None:
             sharded_bandwidth_guard(self._spec)
             kparams = self._spec.params_for(self._Xd, pts)
-        # all rows at once: r = 0 normaliser, r = 1..T-1 time steps 0..T-2
-        R = Th
+        if self._spec.kind == 0:  # one enqueue for the whole test set (csrc/compose.cu: socks_srmax_predict)
+            chunk = min(self.predict_chunk, -(-m // 128) * 128)
+            wk = self._cached_work(_lib.load().socks_srmax_predict_work_bytes(n, P, Th, chunk))
+            _lib.call("socks_srmax_predict", dv.ptr(self._Xd), dv.ptr(self._w), dv.ptr(self._vf), n, dv.ptr(self._CUA), n, d,
+                      P, float(kparams[0]), int(kparams[1]), dv.ptr(pts), m, dv.ptr(self._tubes), prob, Th, dv.ptr(out),
+                      out.stride(0), dv.ptr(wk), chunk, st)
+            return out
+        # other kernel families: the same steps with the family Gram builder
+        R = Th  # all rows at once: r = 0 normaliser, r = 1..T-1 time steps 0..T-2
         ldbm = -(-R * P // 128) * 128
         Bm = dv.empty(npad, ldbm)
         _lib.call("socks_srmax_pack", dv.ptr(self._CUA), n, P, dv.ptr(self._w), dv.ptr(self._vf), n, 0, 0, R, dv.ptr(Bm),
@@ -169,6 +190,13 @@ class KernelMaximalSR:
             _lib.call("socks_srmax_step", dv.ptr(Cm), ldbm, 0, 0, cnt, P, R, 0, dv.ptr(p), d, dv.ptr(self._tubes), prob,
                       Th, dv.ptr(out[:, s:]), out.stride(0), 1, st)
         return out
+
+    def _cached_work(self, nbytes):
+        need = (int(nbytes) + 7) // 8 + 2
+        t = self.__dict__.get("_work")
+        if t is None or t.numel() < need:
+            t = self.__dict__["_work"] = dv.work(nbytes)
+        return t
 
     @property
     def X(self):

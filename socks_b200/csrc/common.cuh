@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include "../../include/socks_b200.h"
+#include "../../include/socks_b200_dev.h"
 
 namespace socks {
 

@@ -15,7 +15,59 @@ import os
 import torch
 import torch.distributed as dist
 
-__all__ = ["init_from_env", "shard_bounds", "broadcast_state", "gather_columns", "predict_sharded"]
+__all__ = ["init_from_env", "shard_bounds", "broadcast_state", "gather_columns", "predict_sharded", "SocksComm"]
+
+
+class SocksComm:
+    """The library's own NCCL communicator (csrc/compose.cu: socks_ctx_* / socks_comm_init / socks_bcast /
+    socks_allgather): what a non-torch binder of the C ABI uses for the path's two collectives.  torch.distributed is
+    only the rendezvous here (it carries the 128-byte NCCL unique id from rank 0 to the others)."""
+
+    def __init__(self):
+        import ctypes
+
+        from socks_b200 import _lib
+
+        self._lib, self._ct = _lib, ctypes
+        self.rank, self.world = _rank(), _world()
+        self.ctx = ctypes.c_void_p()
+        _lib.call("socks_ctx_create", torch.cuda.current_device(), ctypes.byref(self.ctx))
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (ctypes.c_char * 128)()
+            _lib.call("socks_comm_unique_id", buf)
+            ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        if self.world > 1:
+            dev_id = ident.cuda() if dist.get_backend() == "nccl" else ident
+            dist.broadcast(dev_id, src=0)
+            ident = dev_id.cpu()
+        raw = (ctypes.c_char * 128).from_buffer_copy(bytes(ident.numpy().tobytes()))
+        _lib.call("socks_comm_init", self.ctx, self.rank, self.world, raw)
+
+    def broadcast_state(self, tensors, src=0):
+        """In-place broadcast of every tensor of the dict on the context stream; returns the bytes sent."""
+        torch.cuda.current_stream().synchronize()  # the tensors were produced on torch's stream
+        nbytes = 0
+        for key in sorted(tensors):
+            t = tensors[key]
+            assert t.is_contiguous()
+            self._lib.call("socks_bcast", self.ctx, t.data_ptr(), t.numel() * t.element_size(), src)
+            nbytes += t.numel() * t.element_size()
+        self._lib.call("socks_ctx_synchronize", self.ctx)
+        return nbytes
+
+    def allgather(self, local):
+        """(world * local.numel(),) tensor of every rank's contiguous buffer, rank-major."""
+        torch.cuda.current_stream().synchronize()
+        out = torch.empty(self.world * local.numel(), dtype=local.dtype, device=local.device)
+        self._lib.call("socks_allgather", self.ctx, local.data_ptr(), out.data_ptr(), local.numel() * local.element_size())
+        self._lib.call("socks_ctx_synchronize", self.ctx)
+        return out
+
+    def close(self):
+        if self.ctx:
+            self._lib.call("socks_ctx_destroy", self.ctx)
+            self.ctx = None
 
 
 def init_from_env(backend=None):

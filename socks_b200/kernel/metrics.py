@@ -142,17 +142,18 @@ def sqdist_dev(Xd, Yd, squared=True):
 
 def _median_sqdist(Xd, Yd, squared=True):
     """np.median of the (squared) distance matrix (metrics.py:130-131, :199-200): mean of the two middle order
-    statistics for an even count.  Distances come from the CUDA kernel; torch.kthvalue only selects."""
+    statistics for an even count, by radix select on the device (csrc/compose.cu: socks_median_sq_dist)."""
     if Xd.shape[0] * Yd.shape[0] * 8 > MEDIAN_BYTES_LIMIT:
         raise ValueError(f"sigma=None takes the median of the full {Xd.shape[0]} x {Yd.shape[0]} distance matrix "
                          "(metrics.py:130-131), which does not fit the device workspace limit; pass an explicit sigma.")
-    D = sqdist_dev(Xd, Yd, squared).reshape(-1)
-    cnt = D.numel()
-    hi = torch.kthvalue(D, cnt // 2 + 1).values
-    if cnt % 2:
-        return float(hi)
-    lo = torch.kthvalue(D, cnt // 2).values
-    return float((lo + hi) / 2)  # same rounding as numpy's mean of the two middle values
+    n, d = Xd.shape
+    m = Yd.shape[0]
+    lib = _lib.load()
+    wk = dv.work(lib.socks_median_work_bytes(n, m))
+    res = dv.empty(1)
+    _lib.call("socks_median_sq_dist", dv.ptr(Xd), n, dv.ptr(Yd), m, d, 1 if squared else 0, dv.ptr(wk), dv.ptr(res),
+              dv.stream())
+    return float(res.item())
 
 
 MEDIAN_BYTES_LIMIT = 16 << 30  # largest distance matrix the median heuristic may materialise on the device

@@ -9,13 +9,15 @@ import pytest
 from conftest import ROOT
 from socks_b200 import _lib
 
-HEADER = os.path.join(ROOT, "include", "socks_b200.h")
+HEADERS = [os.path.join(ROOT, "include", "socks_b200.h"), os.path.join(ROOT, "include", "socks_b200_dev.h")]
 
 
-def _declared():
-    src = open(HEADER).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(socks_[a-z0-9_]+)\s*\(", src)))
+def _declared(headers=HEADERS):
+    names = set()
+    for h in headers:
+        src = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
+        names |= set(re.findall(r"\b(socks_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
@@ -26,6 +28,12 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in socks_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in socks_b200/_lib.py"
     assert set(_lib.SIGNATURES) == set(names)
+    # the product header carries no probe / tuning exports
+    product = _declared(HEADERS[:1])
+    assert not [n for n in product if "probe" in n or "_dev_" in n or n == "socks_potrf_inv_set_block"]
+    for composite in ("socks_sr_fit", "socks_srmax_fit", "socks_srmax_predict", "socks_fwd_scores", "socks_median_sq_dist",
+                      "socks_ctx_create", "socks_ctx_destroy", "socks_comm_init", "socks_bcast", "socks_allgather"):
+        assert composite in product
 
 
 def test_version_and_padding():

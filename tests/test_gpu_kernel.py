@@ -334,3 +334,45 @@ def test_kernel_family_rejections():
     with pytest.raises(np.linalg.LinAlgError):
         regularized_inverse(np.array([[1.0, 0.0], [0.0, 2.0], [3.0, 1.0]]), regularization_param=1e-9,
                             kernel_fn=partial(polynomial_kernel, degree=1, coef0=-5.0))
+
+
+@pytest.mark.parametrize("n,m,d,squared", [(37, 23, 3, True), (40, 40, 2, False), (301, 7, 4, True), (1, 1, 2, True),
+                                            (2000, 1500, 2, True)])
+def test_median_select_matches_numpy(n, m, d, squared):
+    """socks_median_sq_dist (radix select of both middle order statistics) against np.median of the oracle's matrix:
+    the sigma=None bandwidth of metrics.py:130-131 / :199-200, bit for bit."""
+    torch, dv, _lib, mt = _mods()
+    rng = np.random.default_rng(n + m)
+    X, Y = rng.standard_normal((n, d)), rng.standard_normal((m, d))
+    if n == 40:
+        Y = X.copy()  # zeros on the diagonal take part in the median (test_kernel.py:102-115)
+    D = orc.sq_dist(X, Y)
+    want = np.median(D if squared else np.sqrt(D))
+    got = mt._median_sqdist(dv.to_dev(X), dv.to_dev(Y), squared=squared)
+    assert got == want or abs(got - want) <= 4 * np.finfo(float).eps * want  # sqrt: device vs numpy rounding
+
+
+def test_context_workspace_and_stream():
+    import ctypes
+
+    torch, dv, _lib, mt = _mods()
+    lib = _lib.load()
+    ctx = ctypes.c_void_p()
+    _lib.call("socks_ctx_create", torch.cuda.current_device(), ctypes.byref(ctx))
+    assert lib.socks_ctx_stream(ctx)
+    p1, p2, p3 = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    _lib.call("socks_ctx_workspace", ctx, 1 << 20, ctypes.byref(p1))
+    _lib.call("socks_ctx_workspace", ctx, 1 << 10, ctypes.byref(p2))   # smaller: same arena
+    assert p1.value and p1.value == p2.value
+    _lib.call("socks_ctx_workspace", ctx, 1 << 22, ctypes.byref(p3))   # larger: reallocated
+    assert p3.value
+    # a Gram matrix computed on the context's stream into the context's workspace
+    X = dv.to_dev(np.arange(4.0).reshape(2, 2))
+    torch.cuda.synchronize()
+    _lib.call("socks_gram_rbf", dv.ptr(X), 2, dv.ptr(X), 2, 2, -2.0, 1, None, p3, 2, lib.socks_ctx_stream(ctx))
+    _lib.call("socks_ctx_synchronize", ctx)
+    K = torch.empty(4, dtype=torch.float64, device="cuda")
+    _lib.call("socks_copy2d", K.data_ptr(), 32, p3, 32, 32, 1, 3, None)
+    torch.cuda.synchronize()
+    assert np.allclose(K.cpu().numpy().reshape(2, 2), [[1.0, np.exp(-4.0)], [np.exp(-4.0), 1.0]])
+    _lib.call("socks_ctx_destroy", ctx)
