@@ -241,6 +241,19 @@ int socks_fwd_weights(const double* X, int64_t n, int d, double scale, int divid
  * occurrence on ties (gym_socks/algorithms/control/common.py:96-100, 166-174). idx_dev: device int. */
 int socks_argmin_masked(const double* C, const double* D, int P, int* idx_dev, socks_stream_t stream);
 
+/* ---- Linear system identification: gym_socks/algorithms/identification/kernel_linear_id.py:133-181 ------ */
+
+/* C (p x q, row stride ldc) = A^T B for tall-skinny A (n x p) and B (n x q), p, q <= 64: Z^T Z and Z^T Y of the primal
+ * normal equations (:144-145) in one pass over the samples.  Deterministic (fixed 2048-row chunks summed in order). */
+int64_t socks_atb_small_work_bytes(int64_t n, int p, int q);
+int socks_atb_small(const double* A, int64_t lda, int p, const double* B, int64_t ldb, int q, int64_t n, double* C,
+                    int64_t ldc, double* work, socks_stream_t stream);
+
+/* out[i][j] = sum_k A[i][k] T[j][k] (+ sum_k B[i][k] U[j][k] if U != NULL), i < r, j < m:
+ * state_matrix @ T.T + input_matrix @ U.T (:173-181). */
+int socks_linear_map(const double* A, int lda, int dx, const double* B, int ldb, int du, int r, const double* T,
+                     const double* U, int64_t m, double* out, int64_t ldout, socks_stream_t stream);
+
 /* ---- Composite entry points: one enqueue per algorithm step of the reference's classes ------------------ */
 
 /* KernelSR.fit after the inverse (kernel_sr.py:286-309): B = diag(w) K(X,Y) resident in `work`, in-place recursion into

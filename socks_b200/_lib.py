@@ -57,6 +57,9 @@ SIGNATURES = {
     "socks_gemv_t": (_I, [_P, _L, _L, _L, _P, _L, _I, _P, _L, _P, _P]),
     "socks_fwd_weights": (_I, [_P, _L, _I, _D, _I, _P, _P, _L, _I, _P, _L, _P]),
     "socks_argmin_masked": (_I, [_P, _P, _I, _P, _P]),
+    "socks_atb_small_work_bytes": (_L, [_L, _I, _I]),
+    "socks_atb_small": (_I, [_P, _L, _I, _P, _L, _I, _L, _P, _L, _P, _P]),
+    "socks_linear_map": (_I, [_P, _I, _I, _P, _I, _I, _I, _P, _P, _L, _P, _L, _P]),
     "socks_sr_fit_work_bytes": (_L, [_L]),
     "socks_sr_fit": (_I, [_P, _P, _P, _L, _I, _D, _I, _P, _I, _I, _P, _L, _P, _P, _P]),
     "socks_srmax_fit_work_bytes": (_L, [_L, _I]),

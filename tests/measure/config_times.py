@@ -84,8 +84,27 @@ def c3(n=5000, P_grid=(25, 40), T=20):
         dt, act = wall(lambda: pol(time=t, state=state))
         ts.append(dt)
         state = state + 0.05  # any state: the cost of a call does not depend on it
+    # where a call's time goes: the user's cost_fn on the host (part of the reference API, kernel_control_fwd.py:225) and
+    # the device work of socks_fwd_policy (CUDA events around the enqueue, inputs already staged)
+    tc = []
+    for t in range(T):
+        t0 = time.perf_counter()
+        np.array(pol.cost_fn(time=t), dtype=np.float32)
+        tc.append(time.perf_counter() - t0)
+    td = []
+    for t in range(T):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        pol._enqueue(t, state, policy=True)
+        e1.record()
+        torch.cuda.synchronize()
+        td.append(e0.elapsed_time(e1) * 1e-3)
     return {"N": n, "P": len(A), "T": T, "train_s": t_train, "call_s_median": float(np.median(ts)),
-            "call_s_max": float(np.max(ts)), "reference_call_flops": 2.0 * n * n * len(A)}
+            "call_s_max": float(np.max(ts)), "host_cost_fn_s_median": float(np.median(tc)),
+            "enqueue_to_done_s_median": float(np.median(td)),
+            "call_minus_cost_fn_s": float(np.median(ts) - np.median(tc)),
+            "hbm_floor_s": 8.0 * n * n / 6546.2e9, "reference_call_flops": 2.0 * n * n * len(A)}
 
 
 def c4(n=40000):
