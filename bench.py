@@ -279,7 +279,16 @@ def run_ours(args):
     else:
         alg.allocate_state(n, d)
     if world > 1:  # fit state broadcast over NCCL/NVLink: the only collective on the path
-        fit_info["broadcast_bytes"] = broadcast_state(alg.state_tensors(), src=0)
+        try:  # the library's own communicator (socks_comm_init / socks_bcast); torch.distributed is the rendezvous
+            from socks_b200.distributed import SocksComm
+
+            comm = SocksComm()
+            fit_info["broadcast_bytes"] = comm.broadcast_state(alg.state_tensors(), src=0)
+            fit_info["broadcast_via"] = "socks_bcast (libsocksb200 -> NCCL)"
+            comm.close()
+        except Exception as e:  # plumbing only: same bytes through torch.distributed
+            fit_info["broadcast_bytes"] = broadcast_state(alg.state_tensors(), src=0)
+            fit_info["broadcast_via"] = f"torch.distributed ({type(e).__name__}: {e})"[:160]
 
     peaks = {}
     try:
