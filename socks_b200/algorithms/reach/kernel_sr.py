@@ -146,7 +146,15 @@ class KernelSR:
 
     _keep_factors = True  # `.W` stays available; set False to free L and M right after fit
 
-    predict_chunks = 4  # D2H of chunk c overlaps the kernel of chunk c+1 (only for large M)
+    # How predict() returns the (T, M) result to the host, measured on B200 (profiles/r2_e2e_small.json):
+    #   M < 100 000: ONE launch whose finish kernel stores straight into the pinned host buffer (zero-copy over PCIe);
+    #   M >= 100 000: two column blocks, the device-to-host copy of block 1 overlapping the kernel of block 2.
+    predict_chunks = None       # None: automatic; an int forces that many column blocks (and disables direct stores)
+    predict_direct_host = None  # None: automatic; True / False forces
+
+    @staticmethod
+    def _chunks_for(m):
+        return 2 if m >= 100000 else 1
 
     def predict(self, T):
         """Host in, host out (`kernel_sr.py:311-344`): (m, d) points -> (time_horizon, m) float64 ndarray."""
@@ -160,23 +168,41 @@ class KernelSR:
         src = torch.from_numpy(pts_h)
         pts = src.to(dv.device(), non_blocking=src.is_pinned())
         host, finish = dv.host_pool.get(Th, m)
+        kparams = self._kparams_for(pts)  # once for the whole call (sigma=None: median over K(X,T))
+        direct = self.predict_direct_host
+        if direct is None:
+            direct = self.predict_chunks is None and m < 100000
+        if direct and self._spec.kind == 0:
+            # pinned host memory is device-addressable (UVA): the finish kernel's coalesced row stores go over PCIe as
+            # posted writes, no copy is enqueued at all
+            for s in range(0, m, self.max_launch_points):
+                e = min(m, s + self.max_launch_points)
+                self._predict_launch(pts[s:e], host.data_ptr() + 8 * s, m, kparams)
+            torch.cuda.current_stream().synchronize()
+            return finish()
         out = self._cached("out", (Th, m))
-        nchunks = self.predict_chunks if m >= 65536 else 1
+        nchunks = self.predict_chunks or self._chunks_for(m)
         chunk = -(-(-(-m // nchunks)) // 256) * 256
         cs = dv.copy_stream()
-        kparams = self._kparams_for(pts)  # once for the whole call (sigma=None: median over K(X,T))
         for s in range(0, m, chunk):
             e = min(m, s + chunk)
             self._predict_into(pts[s:e], out[:, s:e], kparams)
-            ev = torch.cuda.Event()
+            ev = self._event(s // chunk)
             ev.record()
-            with torch.cuda.stream(cs):
-                cs.wait_event(ev)
-                # Th row segments of this column block -> pinned host, one strided enqueue
-                _lib.call("socks_copy2d", host.data_ptr() + 8 * s, 8 * m, out.data_ptr() + 8 * s, 8 * out.stride(0),
-                          8 * (e - s), Th, 2, cs.cuda_stream)
+            cs.wait_event(ev)
+            # Th row segments of this column block -> pinned host, one strided enqueue on the copy stream
+            _lib.call("socks_copy2d", host.data_ptr() + 8 * s, 8 * m, out.data_ptr() + 8 * s, 8 * out.stride(0),
+                      8 * (e - s), Th, 2, cs.cuda_stream)
         cs.synchronize()
         return finish()
+
+    def _event(self, i):
+        import torch
+
+        evs = self.__dict__.setdefault("_events", [])
+        while len(evs) <= i:
+            evs.append(torch.cuda.Event())
+        return evs[i]
 
     def predict_dev(self, pts, kparams=None):
         """Device in, device out: (m, d) test points -> (time_horizon, m) safety probabilities."""
@@ -226,14 +252,19 @@ class KernelSR:
             return
         if self._spec.kind != 0:
             return self._predict_materialised(pts, out, kparams)
+        self._predict_launch(pts, dv.ptr(out), out.stride(0), kparams)
+
+    def _predict_launch(self, pts, out_ptr, ldout, kparams):
+        if self._spec.kind != 0:
+            raise NotImplementedError("direct host stores are implemented for the fused RBF predict only")
+        m = pts.shape[0]
         scale, divide = kparams
         pack = self._packed(kparams)
         nbytes = _lib.load().socks_sr_predict_packed_work_bytes(self._n, m)
         work = self._cached("work", ((nbytes + 7) // 8 + 2,))
-        _lib.call("socks_sr_predict_packed", dv.ptr(pack), dv.ptr(self._Xd), self._n, self._d, float(scale),
-                  int(divide), dv.ptr(pts), m, dv.ptr(self._tubes), PROBLEM_CODE[self.problem],
-                  int(self.time_horizon), dv.ptr(out), out.stride(0), dv.ptr(work), int(self.predict_variant),
-                  dv.stream())
+        _lib.call("socks_sr_predict_packed", dv.ptr(pack), dv.ptr(self._Xd), self._n, self._d, float(scale), int(divide),
+                  dv.ptr(pts), m, dv.ptr(self._tubes), PROBLEM_CODE[self.problem], int(self.time_horizon), int(out_ptr),
+                  int(ldout), dv.ptr(work), int(self.predict_variant), dv.stream())
 
     def _predict_materialised(self, pts, out, kparams):
         """Kernel families other than RBF (abel, and sklearn's linear / polynomial / laplacian): the fused predict
