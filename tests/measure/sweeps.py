@@ -2,10 +2,16 @@
 wall time vs sample size, test-set size, time horizon, dimensionality and number of actions, with the reference's
 defaults (d=2, N=1000, M=1000, T=10, sigma=0.1, lambda=1, THT, sklearn rbf_kernel(gamma=1/(2 sigma^2));
 `benchmarks/kernel_sr/baseline.py:26-34,127-146`, `benchmarks/kernel_sr_max/baseline.py:33`, sweeps
-`benchmarks/*/plot_*_vs_time.py:19`).  Timed region as in the reference: tube construction + fit + predict, one
-warm-up discarded, median of 5 repeats; host arrays in, host array out.  The CPU column is the oracle port.
+`benchmarks/*/plot_*_vs_time.py:19`).  Timed region as in the reference: tube construction + fit + predict; host arrays
+in, host array out.  Repeats follow the reference's own rule (`benchmarks/experiment_matrix.py:44-62,224-255`): one
+discarded warm-up, then at least 3 and at most 32 runs, stopping early as soon as `sample_mean` reports the last run
+OUTSIDE the 95 % normal interval of the runs so far (that is the rule as the reference codes it: `if callback_result is
+False or len(results) >= max_iter: return`); the mean, the median and the number of runs are reported.  The CPU column is
+the oracle port (run once).
 
-Usage (on a B200): python tests/measure/sweeps.py [out.json] [--no-cpu]"""
+Usage (on a B200): python tests/measure/sweeps.py [out.json] [--no-cpu]
+M-sweep on 1..8 GPUs (test points sharded, fit on rank 0, NCCL broadcast + gather):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/measure/sweeps.py --msweep [out.json]"""
 import json
 import os
 import sys
@@ -26,16 +32,40 @@ SIGMA, LAM = 0.1, 1.0
 DEF = dict(d=2, n=1000, m=1000, T=10, P=100)
 
 
-def timed(fn, reps=5):
-    fn()
-    ts = []
-    for _ in range(reps):
+def sample_mean(results, alpha=0.95):
+    """The reference's callback (benchmarks/experiment_matrix.py:224-255): True if the last result lies inside the
+    `alpha` normal interval around the mean of all results so far (sample standard deviation)."""
+    from scipy import stats
+
+    results = np.asarray(results)
+    last, mu, sigma = results[-1], results.mean(), results.std(ddof=1)
+    lo, hi = stats.norm.interval(alpha, loc=mu, scale=sigma)
+    return bool(last >= lo and last < hi)
+
+
+def reference_repeats(run_once, min_iter=3, max_iter=32, warmup=True, callback=sample_mean):
+    """`_result_accumulator` of benchmarks/experiment_matrix.py:17-62, with run_once() -> seconds."""
+    if warmup:
+        run_once()
+    results = []
+    while True:
+        results.append(run_once())
+        if len(results) >= min_iter:
+            cb = callback(results) if callback is not None else False
+            if cb is False or len(results) >= max_iter:
+                return results
+
+
+def timed(fn):
+    def once():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         fn()
         torch.cuda.synchronize()
-        ts.append(time.perf_counter() - t0)
-    return float(np.median(ts))
+        return time.perf_counter() - t0
+
+    ts = reference_repeats(once)
+    return {"mean": float(np.mean(ts)), "median": float(np.median(ts)), "runs": len(ts)}
 
 
 def run_sr(n, m, T, d, cpu):
@@ -48,7 +78,8 @@ def run_sr(n, m, T, d, cpu):
         return kernel_sr(S, pts, time_horizon=T, constraint_tube=ct, target_tube=tt, problem="THT",
                          regularization_param=LAM, kernel_fn=partial(sk_rbf, gamma=1 / (2 * SIGMA ** 2)))
 
-    out = {"gpu_s": timed(gpu)}
+    t = timed(gpu)
+    out = {"gpu_s": t["median"], "gpu_s_mean": t["mean"], "runs": t["runs"]}
     if cpu:
         def cpu_fn():
             ct, tt = syn.integrator_tubes(T, d)
@@ -72,7 +103,8 @@ def run_srmax(n, m, T, P, cpu):
         return kernel_sr_max(S, A, pts, time_horizon=T, constraint_tube=ct, target_tube=tt, problem="THT",
                              regularization_param=LAM, kernel_fn=partial(sk_rbf, gamma=1 / (2 * SIGMA ** 2)))
 
-    out = {"gpu_s": timed(gpu)}
+    t = timed(gpu)
+    out = {"gpu_s": t["median"], "gpu_s_mean": t["mean"], "runs": t["runs"]}
     if cpu:
         def cpu_fn():
             ct, tt = syn.integrator_tubes(T, d)
@@ -84,7 +116,66 @@ def run_srmax(n, m, T, P, cpu):
     return out
 
 
+def msweep():
+    """Wall time of tubes + fit + predict vs test-set size on WORLD_SIZE GPUs (the reference's M-sweep,
+    benchmarks/kernel_sr/plot_test_sample_size_vs_time.py:19, extended past its 1 500 points): rank 0 fits, the fitted
+    state is broadcast, every rank predicts its contiguous block, the blocks are gathered on the device."""
+    import torch.distributed as dist
+
+    from socks_b200 import _device as dv
+    from socks_b200.algorithms.reach.kernel_sr import KernelSR
+    from socks_b200.distributed import broadcast_state, gather_columns, init_from_env, shard_bounds
+
+    rank, world, local = init_from_env()
+    outp = [a for a in sys.argv[1:] if a.endswith(".json")]
+    res = {"gpus": world, "repeat_rule": "experiment_matrix.py:44-62 (warm-up + 3..32 runs, sample_mean callback)", "rows": []}
+    for n in (1000, 20000):
+        X, U, Y = syn.integrator_sample(n, dim=2, seed=0)
+        for m in (1000, 10000, 100000, 1000000):
+            pts_h = syn.uniform_points(m, 2, seed=1)
+            lo, hi = shard_bounds(m, world, rank)
+            T = 10
+
+            def run():
+                ct, tt = syn.integrator_tubes(T, 2)
+                alg = KernelSR(time_horizon=T, constraint_tube=ct, target_tube=tt, problem="THT", regularization_param=LAM,
+                               kernel_fn=partial(sk_rbf, gamma=1 / (2 * SIGMA ** 2)))
+                alg._validate_params(None)
+                alg._keep_factors = False
+                if rank == 0:
+                    alg.fit_arrays(X, Y)
+                else:
+                    alg.allocate_state(n, 2)
+                broadcast_state(alg.state_tensors(), src=0)
+                local_out = alg.predict_dev(dv.to_dev(pts_h[lo:hi]))
+                return gather_columns(local_out, m) if world > 1 else local_out
+
+            def once():
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                run()
+                torch.cuda.synchronize()
+                dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+                if world > 1:
+                    dist.all_reduce(dt, op=dist.ReduceOp.MAX)  # every rank sees the same time => the same stopping point
+                return float(dt)
+
+            ts = reference_repeats(once)
+            row = {"N": n, "M": m, "T": T, "s_mean": float(np.mean(ts)), "s_median": float(np.median(ts)), "runs": len(ts)}
+            if rank == 0:
+                print(json.dumps(row), flush=True)
+            res["rows"].append(row)
+    if rank == 0 and outp:
+        json.dump(res, open(outp[0], "w"), indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
+    if "--msweep" in sys.argv:
+        return msweep()
     cpu = "--no-cpu" not in sys.argv
     outp = [a for a in sys.argv[1:] if a.endswith(".json")]
     res = {"defaults": DEF, "sigma": SIGMA, "lambda": LAM, "problem": "THT", "kernel_sr": {}, "kernel_sr_max": {}}

@@ -152,3 +152,28 @@ def test_host_pool_never_reuses_a_live_result(monkeypatch):
     gc.collect()
     t4, _ = pool.get(3, 4)
     assert t4 is t1
+
+
+def test_sweep_repeat_rule_follows_the_reference():
+    """tests/measure/sweeps.py repeats like benchmarks/experiment_matrix.py:44-62: one warm-up, >= 3 runs, <= 32 runs, and
+    it stops as soon as `sample_mean` (:224-255) reports the last run outside the 95 % interval of the runs so far."""
+    import importlib.util
+    import os
+
+    from conftest import ROOT
+
+    spec = importlib.util.spec_from_file_location("sweeps", os.path.join(ROOT, "tests", "measure", "sweeps.py"))
+    sw = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sw)
+    calls = []
+
+    def const():
+        calls.append(1)
+        return 1.0 + 1e-6 * (len(calls) % 2)  # always inside the interval: runs to max_iter
+
+    assert len(sw.reference_repeats(const)) == 32 and len(calls) == 33  # + the discarded warm-up
+    seq = iter([1.0, 1.02, 0.98, 1.01, 1.0, 0.99, 5.0, 1.0, 1.0])
+    out = sw.reference_repeats(lambda: next(seq), warmup=False)
+    assert out[-1] == 5.0 and len(out) == 7  # the outlier ends the repeats, as the reference codes it
+    assert sw.sample_mean([1.0, 1.01, 0.99, 1.0]) is True and sw.sample_mean([1.0, 1.01, 0.99, 1.0, 1.0, 1.0, 3.0]) is False
+    assert len(sw.reference_repeats(lambda: 1.0, min_iter=3, max_iter=5, warmup=False, callback=None)) == 3
