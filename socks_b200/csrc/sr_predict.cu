@@ -155,6 +155,47 @@ __device__ __forceinline__ void sp_store_partials(const double (&acc)[Q][2][2], 
     }
 }
 
+// ---- per-column finish shared by the in-kernel reduction of the factored pass and the finish kernel of the direct pass
+struct FinishArgs {
+    int* counters;          // one arrival counter per point tile (zeroed before the launch)
+    int* list;              // [0] = count, [1..] = flagged columns
+    const double* tubes;
+    double* out;
+    int64_t ldout;
+    double kmul;
+    int problem, T, t0, R, write_last, build_list;
+};
+
+// sum[0] = normaliser, sum[r] = numerator of step t0 + r - 1.  After a factored pass the column only stands if no factor
+// could have over/underflowed and its un-scaled normaliser is >= 1e-280 (see the header); otherwise it is queued for the
+// direct form.  Also writes out[T-1] = 1_target (kernel_sr.py:57) when write_last.
+template <int ROWS>
+__device__ __forceinline__ void finish_column(const double (&sum)[ROWS], int64_t j, const double* __restrict__ p, int d,
+                                              const double* __restrict__ hdr, const FinishArgs& fa) {
+    if (fa.write_last)
+        fa.out[(int64_t)(fa.T - 1) * fa.ldout + j] = in_box(p, fa.tubes + (int64_t)(fa.T - 1) * 4 * d, 1, d) ? 1.0 : 0.0;
+    if (fa.R <= 1) return;
+    const double den = sum[0];
+    double q2 = 0.0;
+    for (int k = 0; k < d; ++k) {
+        const double t = p[k] - hdr[2 + k];
+        q2 = fma(t, t, q2);
+    }
+    const double g = -fa.kmul;
+    bool ok = (g * q2 < SP_RANGE) && (2.0 * g * sqrt(q2 * hdr[1]) < SP_RANGE);
+    ok = ok && (den * exp(fa.kmul * q2) >= 1e-280) && (den < INFINITY);  // false for NaN
+    if (!ok) {
+        if (fa.build_list) fa.list[1 + atomicAdd(fa.list, 1)] = (int)j;
+        return;
+    }
+#pragma unroll
+    for (int r = 1; r < ROWS; ++r)
+        if (r < fa.R) {
+            const int t = fa.t0 + r - 1;
+            fa.out[(int64_t)t * fa.ldout + j] = sr_step(p, fa.tubes + (int64_t)t * 4 * d, d, fa.problem, sum[r] / den);
+        }
+}
+
 // ---- factored form ------------------------------------------------------------------------------------------
 // CTA = WARPS warps x (8 Q) points x one 2048-sample split.  Lane (lq = lane/4, lr = lane%4) evaluates sample
 // s = 4 ks + lr against the points {8 q + lq}: exactly the B-fragment layout of mma.m8n8k4.
@@ -164,14 +205,21 @@ template <int D, int WARPS, int MINB, int Q, bool HI, int U>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     sr_predict_fast_kernel(const double* __restrict__ Xc, const double* __restrict__ coefF, int64_t n_pad,
                            const double* __restrict__ pts, int64_t m, const double* __restrict__ hdr, double pscale,
-                           int force_direct, double* __restrict__ part, int64_t ldp) {
+                           int force_direct, double* __restrict__ part, FinishArgs fa) {
     if (force_direct || hdr[0] == 0.0) return;  // launch-uniform: the direct kernel handles this launch
     __shared__ __align__(16) double sx[2][SP_TS * D];
     __shared__ __align__(16) double sc[2][SP_TS * SR_CP];
     __shared__ double etbl[EXP_TBL2];
+    __shared__ int s_last;
+    constexpr int TW = WARPS * Q * 8;     // points per CTA
+    constexpr int ROWS = HI ? 16 : 8;      // coefficient rows carried
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lq = lane >> 2, lr = lane & 3;
-    const int64_t pbase = (int64_t)blockIdx.x * (WARPS * Q * 8) + warp * (Q * 8);
+    // blockIdx.x = sample split (fastest: the CTAs of one point tile are scheduled together, so the tile's partial
+    // sums are still in L2 when its last CTA reduces them), blockIdx.y = point tile
+    const int split = blockIdx.x, nsplit = gridDim.x;
+    const int64_t tile = blockIdx.y;
+    const int64_t pbase = tile * TW + warp * (Q * 8);
     exp_table2_init(etbl, tid, WARPS * 32);  // visible after the first __syncthreads of the main loop
 
     double ps[Q][D];
@@ -194,7 +242,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     double kD1;
     asm("mov.f64 %0, 0d3F362E42FEFA39EF;" : "=d"(kD1));
     const char* etb = reinterpret_cast<const char*>(etbl);
-    const int tile0 = blockIdx.y * (SP_SPLIT / SP_TS);
+    const int tile0 = split * (SP_SPLIT / SP_TS);
     const int tile1 = min((int)(n_pad / SP_TS), tile0 + SP_SPLIT / SP_TS);
     sp_load_stage<D>(sx[0], sc[0], Xc, coefF, n_pad, (int64_t)tile0 * SP_TS, tid, WARPS * 32);
     cp_async_commit();
@@ -257,7 +305,43 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             cp += U * 4 * SR_CP;
         }
     }
-    sp_store_partials<Q>(acc, part, ldp, pbase, m, lq, lr);
+    // ---- epilogue: this split's partial sums -> part[tile][split][ROWS][TW]; the LAST CTA of the tile to arrive sums the
+    // splits in index order (deterministic, independent of arrival order), divides, applies the step and writes the
+    // result rows.  Nothing but the result leaves the chip: the partials are read back from L2 and then discarded.
+    double* tpart = part + (tile * nsplit + split) * (int64_t)(ROWS * TW);
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+        for (int h = 0; h < (HI ? 2 : 1); ++h)
+            *reinterpret_cast<double2*>(tpart + (lq + 8 * h) * TW + warp * (Q * 8) + q * 8 + 2 * lr) =
+                make_double2(acc[q][h][0], acc[q][h][1]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(fa.counters + tile, 1) == nsplit - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const double* tbase = part + tile * nsplit * (int64_t)(ROWS * TW);
+    for (int col = tid; col < TW; col += WARPS * 32) {
+        const int64_t j = tile * TW + col;
+        if (j >= m) continue;
+        double sum[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) sum[r] = 0.0;
+        for (int sp = 0; sp < nsplit; ++sp) {
+            const double* src = tbase + (int64_t)sp * (ROWS * TW) + col;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) sum[r] += __ldcg(src + r * TW);
+        }
+        finish_column<ROWS>(sum, j, pts + j * D, D, hdr, fa);
+    }
+    __syncthreads();  // every thread has read its columns: the tile's partials are dead
+    {
+        const char* base = reinterpret_cast<const char*>(tbase);
+        const int lines = nsplit * ROWS * TW * 8 / 128;
+        for (int l = tid; l < lines; l += WARPS * 32)
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + (int64_t)l * 128) : "memory");
+    }
 }
 
 // ---- direct form (whole launch): distance by differences + table exp with IEEE range handling ---------------
@@ -333,15 +417,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     sp_store_partials<Q>(acc, part, ldp, pbase, m, lq, lr);
 }
 
-// ---- finish: sum the splits in order, divide by the normaliser row, apply the FHT/THT step -----------------
-// Also writes out[T-1] = 1_target(pts) (kernel_sr.py:57) when write_last, and -- after a factored pass -- decides
-// per column whether the factored value stands (see the header); the others go to list[] for sr_predict_cols.
+// ---- finish of the DIRECT pass: sum the splits in order, divide by the normaliser row, apply the FHT/THT step;
+// also out[T-1] = 1_target(pts) (kernel_sr.py:57) when write_last.  (The factored pass finishes inside its own kernel.)
 __global__ void sr_predict_finish_kernel(const double* __restrict__ part, int64_t ldp, int splits, int64_t m, int R,
                                          int t0, const double* __restrict__ pts, int d,
                                          const double* __restrict__ tubes, int problem, int T,
-                                         const double* __restrict__ hdr, double kmul, int force_direct, int write_last,
-                                         int build_list, int* __restrict__ list, double* __restrict__ out,
-                                         int64_t ldout) {
+                                         const double* __restrict__ hdr, int force_direct, int write_last,
+                                         double* __restrict__ out, int64_t ldout) {
+    if (!force_direct && hdr[0] != 0.0) return;  // launch-uniform: the factored kernel already wrote the result
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
     const double* p = pts + j * d;
@@ -350,20 +433,6 @@ __global__ void sr_predict_finish_kernel(const double* __restrict__ part, int64_
     if (R <= 1) return;
     double den = 0.0;
     for (int s = 0; s < splits; ++s) den += part[(int64_t)s * 16 * ldp + j];
-    if (!force_direct && hdr[0] != 0.0) {
-        double q2 = 0.0;
-        for (int k = 0; k < d; ++k) {
-            const double t = p[k] - hdr[2 + k];
-            q2 = fma(t, t, q2);
-        }
-        const double g = -kmul;
-        bool ok = (g * q2 < SP_RANGE) && (2.0 * g * sqrt(q2 * hdr[1]) < SP_RANGE);
-        ok = ok && (den * exp(kmul * q2) >= 1e-280) && (den < INFINITY);  // false for NaN
-        if (!ok) {
-            if (build_list) list[1 + atomicAdd(list, 1)] = (int)j;
-            return;
-        }
-    }
     for (int r = 1; r < R; ++r) {
         double num = 0.0;
         for (int s = 0; s < splits; ++s) num += part[((int64_t)s * 16 + r) * ldp + j];
@@ -501,8 +570,9 @@ static inline PackView pack_view(const double* pack, int64_t n, int d, int T) {
 }
 static inline int predict_splits(int64_t n) { return (int)ceil_div(sp_npad(n), SP_SPLIT); }
 static inline int64_t predict_part_doubles(int64_t n, int64_t m) {
-    return (int64_t)predict_splits(n) * 16 * round_up(m, 2);
+    return (int64_t)predict_splits(n) * 16 * round_up(m, 256);  // whole point tiles: [tile][split][rows][tile width]
 }
+static inline int64_t predict_counter_ints(int64_t m) { return ceil_div(m, 64) + 2; }
 
 // CTA shape per launch: fewer warps per CTA when there are few point tiles, so that every SM still receives
 // >= ~24 (tile, split) items and the last, partially filled wave is short.  The shape changes which warp evaluates a
@@ -514,17 +584,17 @@ static inline bool small_tiles(int64_t m, int splits, int pts_per_cta) {
 template <int D>
 static void launch_tensor(const PackView& v, const double* X, int64_t n, const double* pts, int64_t m, double kmul,
                           int b, int R, int force_direct, int shape, double* part, int64_t ldp, int splits,
-                          cudaStream_t st) {
+                          const FinishArgs& fa, cudaStream_t st) {
     constexpr int Q = (D <= 4) ? 4 : 2;
     const double* cf = v.coefF + (int64_t)b * v.n_pad * SR_CP;
     const double* ce = v.coefE + (int64_t)b * v.n_pad * SR_CP;
     const double pscale = -2.0 * kmul * (2048.0 / 0.693147180559945309417232121458176568);
     const bool small = shape == 2 || (shape == 0 && small_tiles(m, splits, 8 * Q * 8));
 #define SOCKS_FAST_LAUNCH(W, MB, HI, U)                                                                              \
-    sr_predict_fast_kernel<D, W, MB, Q, HI, U><<<dim3((unsigned)ceil_div(m, W * Q * 8), (unsigned)splits), W * 32, 0, st>>>( \
-        v.Xc, cf, v.n_pad, pts, m, v.hdr, pscale, force_direct, part, ldp)
+    sr_predict_fast_kernel<D, W, MB, Q, HI, U><<<dim3((unsigned)splits, (unsigned)ceil_div(m, W * Q * 8)), W * 32, 0, st>>>( \
+        v.Xc, cf, v.n_pad, pts, m, v.hdr, pscale, force_direct, part, fa)
     // 8 warps x 2 CTAs/SM (unroll 2) and 4 warps x 4 CTAs/SM (unroll 4): best of the shape sweep in
-    // profiles/r2_predict_sweep.json (all shapes within 4 %)
+    // profiles/r2_predict_shape_sweep.json (all shapes within 4 %)
     if (small) {
         if (R > 8) SOCKS_FAST_LAUNCH(4, 4, true, 4); else SOCKS_FAST_LAUNCH(4, 4, false, 4);
     } else {
@@ -566,7 +636,7 @@ extern "C" int socks_sr_pack(const double* X, const double* w, const double* vf,
 }
 
 extern "C" int64_t socks_sr_predict_packed_work_bytes(int64_t n, int64_t m) {
-    return (predict_part_doubles(n, m) + (m + 4) / 2 + 4) * 8;  // partial sums + int list[1 + m]
+    return (predict_part_doubles(n, m) + (predict_counter_ints(m) + m + 4) / 2 + 4 + 16) * 8;  // partials, counters, list
 }
 
 extern "C" int socks_sr_predict_packed(const double* pack, const double* X, int64_t n, int d, double scale,
@@ -605,13 +675,16 @@ extern "C" int socks_sr_predict_packed(const double* pack, const double* X, int6
         SOCKS_CHECK_LAUNCH();
         return SOCKS_OK;
     }
-    double* part = work;
-    int* list = reinterpret_cast<int*>(work + predict_part_doubles(n, m));
+    // partial sums, 128-byte aligned (whole L2 lines are discarded after the in-kernel reduction)
+    double* part = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(work) + 127) & ~(uintptr_t)127);
+    int* counters = reinterpret_cast<int*>(part + predict_part_doubles(n, m));  // one per point tile, then the list
+    const int64_t nctr = predict_counter_ints(m);
+    int* list = counters + nctr;  // list[0] = number of flagged columns
     const int64_t ldp = round_up(m, 2);
     const int splits = predict_splits(n);
     const int force_direct = (variant == 2);
     const int shape = variant == 3 ? 1 : (variant == 4 ? 2 : 0);
-    if (variant != 1) SOCKS_CUDA(cudaMemsetAsync(list, 0, sizeof(int), st));
+    SOCKS_CHECK_ARG(ceil_div(m, 64) <= 65535, 8);  // point tiles ride on gridDim.y
     for (int b = 0; b < v.nblk; ++b) {
         const int t0 = b * (SOCKS_SR_ROWS - 1);
         const int R = ((T - 1 - t0 < SOCKS_SR_ROWS - 1) ? (T - 1 - t0) : (SOCKS_SR_ROWS - 1)) + 1;
@@ -631,9 +704,12 @@ extern "C" int socks_sr_predict_packed(const double* pack, const double* X, int6
             SOCKS_CHECK_LAUNCH();
             continue;
         }
+        // arrival counters of this launch (and, once, the flagged-column count)
+        SOCKS_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * (size_t)(nctr + (b == 0 ? 1 : 0)), st));
+        const FinishArgs fa{counters, list, tubes, out, ldout, kmul, problem, T, t0, R, b == 0, b == 0};
 #define SOCKS_PRED_CASE(DD)                                                                                    \
     case DD:                                                                                                   \
-        launch_tensor<DD>(v, X, n, pts, m, kmul, b, R, force_direct, shape, part, ldp, splits, st);            \
+        launch_tensor<DD>(v, X, n, pts, m, kmul, b, R, force_direct, shape, part, ldp, splits, fa, st);        \
         break;
         switch (d) {
             SOCKS_PRED_CASE(1) SOCKS_PRED_CASE(2) SOCKS_PRED_CASE(3) SOCKS_PRED_CASE(4)
@@ -642,7 +718,7 @@ extern "C" int socks_sr_predict_packed(const double* pack, const double* X, int6
 #undef SOCKS_PRED_CASE
         SOCKS_CHECK_LAUNCH();
         sr_predict_finish_kernel<<<gm, 256, 0, st>>>(part, ldp, splits, m, R, t0, pts, d, tubes, problem, T, v.hdr,
-                                                     kmul, force_direct, b == 0, b == 0, list, out, ldout);
+                                                     force_direct, b == 0, out, ldout);
         SOCKS_CHECK_LAUNCH();
     }
     if (variant != 1 && !force_direct) {
