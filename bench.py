@@ -257,7 +257,8 @@ def run_ours(args):
         small = syn.integrator_sample(512, d, seed=9)
         KernelSR(time_horizon=3, constraint_tube=ct, target_tube=tt, problem=PROBLEM,
                  regularization_param=1e-3).fit_arrays(small[0], small[2])  # module load / attribute warm-up
-        torch.cuda.synchronize()
+        alg.fit_arrays(X, Y)  # one discarded warm-up at full size, as the reference's harness does
+        torch.cuda.synchronize()  # (benchmarks/experiment_matrix.py:44-46): first-touch cudaMalloc of the 3.2 GB buffers
         dv.stage_marks = []
         alg.fit_arrays(X, Y)
         torch.cuda.synchronize()

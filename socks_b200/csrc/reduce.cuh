@@ -17,7 +17,9 @@ constexpr int CR_COLS = CR_THREADS * 2;
 constexpr int CR_MAX_SPLITS = 64;
 
 // tri != 0: Bm is lower triangular by 128-tiles; column j only reads rows >= 128*floor(j/128).
-template <bool SQUARE>
+// WITH_SUM: the same pass also accumulates the UNWEIGHTED column sums (V = 1) into the partials of "row vector" z = 1
+// (gridDim.z must be 1): the normaliser of kernel_sr.py:45 rides on the first GEMV pass instead of costing its own.
+template <bool SQUARE, bool WITH_SUM = false>
 __global__ void __launch_bounds__(CR_THREADS)
     colreduce_kernel(const double* __restrict__ Bm, int64_t n, int64_t m, int64_t ldb, const double* __restrict__ V,
                      int64_t ldv, double* __restrict__ part, int64_t ldpart, int tri, int vec_ok) {
@@ -32,7 +34,7 @@ __global__ void __launch_bounds__(CR_THREADS)
     const bool has1 = (j0 + 1 < m);
     const bool pair = vec_ok && has1;
     const double* p = Bm + j0;
-    double a0 = 0.0, a1 = 0.0;
+    double a0 = 0.0, a1 = 0.0, s0 = 0.0, s1 = 0.0;
     int64_t i = r0;
     for (; i + 8 <= r1; i += 8) {
         double2 x[8];
@@ -56,6 +58,10 @@ __global__ void __launch_bounds__(CR_THREADS)
                 a0 = fma(x[u].x, vv[u], a0);
                 a1 = fma(x[u].y, vv[u], a1);
             }
+            if (WITH_SUM) {  // same association as the V = 1 pass (fma(x, 1, s) == s + x)
+                s0 += x[u].x;
+                s1 += x[u].y;
+            }
         }
     }
     for (; i < r1; ++i) {
@@ -68,10 +74,19 @@ __global__ void __launch_bounds__(CR_THREADS)
             a0 = fma(x0, vv, a0);
             a1 = fma(x1, vv, a1);
         }
+        if (WITH_SUM) {
+            s0 += x0;
+            s1 += x1;
+        }
     }
     double* q = part + ((int64_t)blockIdx.z * splits + blockIdx.y) * ldpart + j0;
     q[0] = a0;
     if (has1) q[1] = a1;
+    if (WITH_SUM) {
+        double* qs = part + ((int64_t)splits + blockIdx.y) * ldpart + j0;
+        qs[0] = s0;
+        if (has1) qs[1] = s1;
+    }
 }
 
 // y[z][j] = sum_s part[z][s][j]
@@ -98,13 +113,14 @@ inline int colreduce_splits(int64_t n, int64_t m) {
 inline int64_t colreduce_ldpart(int64_t m) { return round_up(m, 2); }
 
 // Launch part = reduce(...). part must hold R * CR_MAX_SPLITS * ldpart doubles. Returns splits used.
-template <bool SQUARE>
+template <bool SQUARE, bool WITH_SUM = false>
 inline int colreduce_launch(const double* Bm, int64_t n, int64_t m, int64_t ldb, const double* V, int64_t ldv, int R,
                             double* part, int tri, cudaStream_t st) {
     const int splits = colreduce_splits(n, m);
     const int vec_ok = (ldb % 2 == 0) && ((reinterpret_cast<uintptr_t>(Bm) & 15) == 0);
     dim3 grid((unsigned)ceil_div(m, CR_COLS), (unsigned)splits, (unsigned)R);
-    colreduce_kernel<SQUARE><<<grid, CR_THREADS, 0, st>>>(Bm, n, m, ldb, V, ldv, part, colreduce_ldpart(m), tri, vec_ok);
+    colreduce_kernel<SQUARE, WITH_SUM><<<grid, CR_THREADS, 0, st>>>(Bm, n, m, ldb, V, ldv, part, colreduce_ldpart(m), tri,
+                                                                   vec_ok);
     return splits;
 }
 

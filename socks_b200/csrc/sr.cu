@@ -22,15 +22,26 @@ __global__ void sr_init_kernel(const double* __restrict__ pts, int64_t m, int d,
     out[(int64_t)(T - 1) * ldout + j] = in_box(pts + j * d, tube, 1, d) ? 1.0 : 0.0;
 }
 
-// out_t[j] = step(pts_j, (sum_s part[s][j]) / den[j])       (kernel_sr.py:62-63 after `normalize`)
+// out_t[j] = step(pts_j, (sum_s part[s][j]) / den[j])       (kernel_sr.py:62-63 after `normalize`).
+// den_part != NULL: the pass also produced the unweighted column sums (partials at den_part): den[j] is formed here,
+// stored for the following steps and used at once.
 __global__ void sr_finish_step_kernel(const double* __restrict__ part, int64_t ldpart, int splits,
-                                      const double* __restrict__ den, const double* __restrict__ pts, int64_t m, int d,
+                                      double* __restrict__ den, const double* __restrict__ den_part,
+                                      const double* __restrict__ pts, int64_t m, int d,
                                       const double* __restrict__ tube_t, int problem, double* __restrict__ out_t) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
     double a = 0.0;
     for (int s = 0; s < splits; ++s) a += part[(int64_t)s * ldpart + j];
-    out_t[j] = sr_step(pts + j * d, tube_t, d, problem, a / den[j]);
+    double dj;
+    if (den_part) {
+        dj = 0.0;
+        for (int s = 0; s < splits; ++s) dj += den_part[(int64_t)s * ldpart + j];
+        den[j] = dj;
+    } else {
+        dj = den[j];
+    }
+    out_t[j] = sr_step(pts + j * d, tube_t, d, problem, a / dj);
 }
 
 // q[r][i] = z[r][i] * exp(-gamma |X_i - s|^2)     (kernel_control_fwd.py:220-222: CXT * ...)
@@ -115,15 +126,16 @@ extern "C" int socks_sr_recursion(const double* B, int64_t n, int64_t m, int64_t
     sr_init_kernel<<<gb, 256, 0, st>>>(pts, m, d, tubes, T, out, ldout);
     SOCKS_CHECK_LAUNCH();
     if (T == 1) return SOCKS_OK;
-    int splits = colreduce_launch<false>(B, n, m, ldb, nullptr, 0, 1, part, 0, st);
-    SOCKS_CHECK_LAUNCH();
-    colreduce_finish_kernel<<<dim3(gb, 1), 256, 0, st>>>(part, ldp, splits, m, den, ldp);
-    SOCKS_CHECK_LAUNCH();
+    // T-1 passes over B in total: the normaliser (column sums of B, `normalize` of kernel_sr.py:45) is accumulated by the
+    // first GEMV pass from the same loads
     for (int t = T - 2; t >= 0; --t) {
-        splits = colreduce_launch<false>(B, n, m, ldb, vf + (int64_t)(t + 1) * ldvf, 0, 1, part, 0, st);
+        const bool first = (t == T - 2);
+        const int splits = first ? colreduce_launch<false, true>(B, n, m, ldb, vf + (int64_t)(t + 1) * ldvf, 0, 1, part, 0, st)
+                                 : colreduce_launch<false>(B, n, m, ldb, vf + (int64_t)(t + 1) * ldvf, 0, 1, part, 0, st);
         SOCKS_CHECK_LAUNCH();
-        sr_finish_step_kernel<<<gb, 256, 0, st>>>(part, ldp, splits, den, pts, m, d, tubes + (int64_t)t * 4 * d,
-                                                  problem, out + (int64_t)t * ldout);
+        sr_finish_step_kernel<<<gb, 256, 0, st>>>(part, ldp, splits, den, first ? part + (int64_t)splits * ldp : nullptr,
+                                                  pts, m, d, tubes + (int64_t)t * 4 * d, problem,
+                                                  out + (int64_t)t * ldout);
         SOCKS_CHECK_LAUNCH();
     }
     return SOCKS_OK;
