@@ -507,6 +507,7 @@ static Lookahead* lookahead_for_device(int* rc_out) {
     return &l;
 }
 
+static int g_potrf_tail = 1;   // 1: half-width block columns over the last 4 NB columns
 static int g_potrf_nb = 1024;  // block-column width of the look-ahead factorisation (multiple of 128; 0 = pure recursion)
 
 // inv(L) from its diagonal-block inverses: the merges M21 = -(M22 L21) M11 of the block recursion, in post-order
@@ -537,8 +538,14 @@ static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, i
     Lookahead* la = lookahead_for_device(&rc);
     if (!la) return rc;
     CholCtx c1{s1}, c2{la->s2};
+    // block-column boundaries: NB wide, but half as wide over the last 4 NB columns -- there the trailing update is
+    // shorter than the critical path of a block (leaves + small GEMMs), so shorter blocks shorten what is exposed
     std::vector<int64_t> bnd;
-    for (int64_t o = 0; o < np; o += NB) bnd.push_back(o);
+    const int64_t tail = g_potrf_tail ? std::max<int64_t>(0, np - 4 * NB) : np;
+    for (int64_t o = 0; o < np;) {
+        bnd.push_back(o);
+        o += (o >= tail && NB >= 2 * LF) ? NB / 2 : NB;
+    }
     bnd.push_back(np);
     const int nb = (int)bnd.size() - 1;
     std::vector<Merge> merges;
@@ -707,7 +714,11 @@ extern "C" int socks_potrf_inv(double* G, int64_t n, int64_t ldg, double* M, int
 // Returns the previous value.  Tuning / measurement knob (tools/run_potrf.py); not thread-safe against running calls.
 extern "C" int socks_potrf_inv_set_block(int nb) {
     const int old = g_potrf_nb;
-    if (nb >= 0 && nb % LF == 0) g_potrf_nb = nb;
+    if (nb < 0) {  // -1 / -2: switch the half-width tail off / on (measurement)
+        g_potrf_tail = (nb == -2);
+        return old;
+    }
+    if (nb % LF == 0) g_potrf_nb = nb;
     return old;
 }
 

@@ -44,3 +44,21 @@ shapes = [(0, 1, 10112, 10112, 9984, 1), (0, 0, 10112, 9984, 9984, 0), (0, 1, 25
 for ta, tb, m, n, K, lower in shapes:
     for cfg in cfgs:
         print(json.dumps(run(ta, tb, m, n, K, lower, cfg)), flush=True)
+
+if len(sys.argv) > 1 and sys.argv[1] == "lookahead":
+    # shapes of socks_potrf_inv's look-ahead factorisation at N = 20 000 (block columns of 1024)
+    print("# rank-1024 trailing updates (lower-only SYRK), column updates, panels (B upper-clipped), merges")
+    for m in (19072, 15104, 10112, 5120, 2048):
+        r = run(0, 1, m, m, 1024, 1, 0)
+        r["what"] = "trailing update A22 -= L21 L21^T"
+        print(json.dumps(r), flush=True)
+    for m in (19072, 10112, 2048):
+        r = run(0, 1, m, 1024, 1024, 0, 0)
+        r["what"] = "next-block-column update / panel-shaped GEMM"
+        print(json.dumps(r), flush=True)
+    for n1 in (1024, 2048, 4096, 10112):
+        for flags, name in ((1, "T = M22 L21 (A lower: k <= m)"), (4, "M21 = -T M11 (B: k >= n)")):
+            r = run(0, 0, n1, n1, n1, 0, 0, flags=flags)
+            r["tflops_triangular"] = r["tflops"] / 2  # about half of the k-range is clipped
+            r["what"] = name
+            print(json.dumps(r), flush=True)

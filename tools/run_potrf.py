@@ -23,6 +23,10 @@ if what == "sweep":
     mt.Factorization(dv.to_dev(X[:3000]), (-50.0, 0), 1.0 / 3000)  # warm-up: module load, smem attributes, streams
     out = []
     for nb in [int(a) for a in sys.argv[3].split(",")] if len(sys.argv) > 3 else (0, 512, 1024, 1536, 2048):
+        tail = 1
+        if nb >= 100000:  # e.g. 101024: block 1024 without the half-width tail
+            tail, nb = 0, nb - 100000
+        lib.socks_potrf_inv_set_block(-2 if tail else -1)
         old = lib.socks_potrf_inv_set_block(nb)
         ts = []
         for rep in range(3):
@@ -35,7 +39,8 @@ if what == "sweep":
             del fac
         lib.socks_potrf_inv_set_block(old)
         t = min(ts)
-        rec = {"N": n, "block": nb, "potrf_inv_s": t, "tflops": 2 * npad ** 3 / 3 / t / 1e12, "all_s": ts}
+        lib.socks_potrf_inv_set_block(-2)
+        rec = {"N": n, "block": nb, "half_width_tail": bool(tail), "potrf_inv_s": t, "tflops": 2 * npad ** 3 / 3 / t / 1e12, "all_s": ts}
         print(json.dumps(rec), flush=True)
         out.append(rec)
     if len(sys.argv) > 4:
