@@ -376,3 +376,43 @@ def test_context_workspace_and_stream():
     torch.cuda.synchronize()
     assert np.allclose(K.cpu().numpy().reshape(2, 2), [[1.0, np.exp(-4.0)], [np.exp(-4.0), 1.0]])
     _lib.call("socks_ctx_destroy", ctx)
+
+
+def test_composite_sr_entry_points_match_the_wrappers():
+    """socks_sr_fit and socks_sr_predict (pack + predict in one call, arbitrary 16-byte aligned workspace) called directly
+    through ctypes give the bits KernelSR gives; predict()'s host paths (direct pinned-host stores, overlapped column
+    blocks, forced block counts) agree bit for bit."""
+    torch, dv, _lib, mt = _mods()
+    from functools import partial
+
+    from socks_b200 import synthetic as syn
+    from socks_b200.algorithms.reach.common import PROBLEM_CODE, pack_tubes
+    from socks_b200.algorithms.reach.kernel_sr import KernelSR
+
+    lib = _lib.load()
+    n, T, d, m = 777, 9, 2, 5001
+    X, U, Y = syn.integrator_sample(n, d, seed=4)
+    pts_h = syn.uniform_points(m, d, seed=5, low=-1.05, high=1.05)
+    ct, tt = syn.integrator_tubes(T, d)
+    alg = KernelSR(time_horizon=T, constraint_tube=ct, target_tube=tt, problem="FHT",
+                   kernel_fn=partial(mt.rbf_kernel, sigma=0.15), regularization_param=1e-4)
+    alg.fit_arrays(X, Y)
+    Xd, Yd, pts = dv.to_dev(X), dv.to_dev(Y), dv.to_dev(pts_h)
+    tubes = pack_tubes(ct, tt, T, d)
+    scale = -2 * 0.15 ** 2
+    vf = dv.empty(T, n)
+    wk = dv.work(lib.socks_sr_fit_work_bytes(n))
+    _lib.call("socks_sr_fit", dv.ptr(Xd), dv.ptr(Yd), dv.ptr(alg._w), n, d, scale, 1, dv.ptr(tubes), PROBLEM_CODE["FHT"], T,
+              dv.ptr(vf), n, None, dv.ptr(wk), dv.stream())
+    assert torch.equal(vf, alg._vf)
+    out = dv.empty(T, m)
+    work = dv.work(lib.socks_sr_predict_work_bytes(n, m) + 64)
+    for off in (0, 16, 48):  # the entry point only requires 16-byte alignment
+        _lib.call("socks_sr_predict", dv.ptr(Xd), dv.ptr(alg._w), dv.ptr(vf), n, n, d, scale, 1, dv.ptr(pts), m,
+                  dv.ptr(tubes), PROBLEM_CODE["FHT"], T, dv.ptr(out), m, work.data_ptr() + off, 0, dv.stream())
+        assert torch.equal(out, alg.predict_dev(pts))
+    ref = alg.predict(pts_h)
+    assert np.array_equal(ref, out.cpu().numpy())
+    for chunks, direct in ((1, False), (3, False), (None, True), (None, False)):
+        alg.predict_chunks, alg.predict_direct_host = chunks, direct
+        assert np.array_equal(alg.predict(pts_h), ref)
