@@ -15,7 +15,7 @@ per rank) is measured in the same run and reported under "weak".
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 `--impl reference` times the UNMODIFIED reference (`gym_socks.algorithms.reach.kernel_sr.KernelSR`, imported from
-/root/reference or from the verbatim copy oracle/vendor_ref.py leaves in oracle/_ref) on the host cores: one reference
+/root/reference or from the verbatim archive oracle/vendor_ref.py leaves in oracle/_ref) on the host cores: one reference
 fit at full N (untimed, reported), then `predict` on a bounded sample of the same test points per step.  It never
 touches the CUDA library.  If the reference cannot be imported, the numpy oracle port is timed instead
 (`cpu_baseline.kind: "port"`).
