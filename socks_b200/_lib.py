@@ -81,6 +81,7 @@ SIGNATURES = {
     "socks_bcast": (_I, [_P, _P, _L, _I]),
     "socks_allgather": (_I, [_P, _P, _P, _L]),
     "socks_dev_potf2_phases": (_I, [_P, _L, _P, _P, _P, _P]),
+    "socks_dev_i8gemm_check": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "socks_probe_fp64": (_I, [_I, _I, _P, _I, _P]),
 }
 
