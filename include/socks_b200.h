@@ -278,6 +278,18 @@ int socks_srmax_predict(const double* X, const double* w, const double* vf, int6
                         int problem, int T, double* out, int64_t ldout, double* work, int64_t chunk,
                         socks_stream_t stream);
 
+/* The same predict with the contraction on the INTEGER tensor cores (tcgen05.mma kind::i8, TMEM accumulators): both
+ * operands are split into `slices` (6..8) unsigned 7-bit digits and every digit product is an exact int8 GEMM
+ * (Ozaki splitting); sums of non-negative terms, recombined in fp64: relative error of num and den ~ 2^(-7 slices) K.
+ * Points whose smallest normaliser is below tau * 2^(e_0) (far from every sample: the fixed-point digits of K(x,p) carry
+ * too few significant bits there) are NOT trustworthy: their indices are appended to flagged[1..], flagged[0] = count
+ * (device ints, 1 + m entries), and the caller recomputes them with socks_srmax_predict.  work: 1024-byte aligned. */
+int64_t socks_srmax_predict_i8_work_bytes(int64_t n, int P, int T, int64_t chunk, int slices);
+int socks_srmax_predict_i8(const double* X, const double* w, const double* vf, int64_t ldvf, const double* CUA, int64_t n,
+                           int d, int P, double scale, int divide, const double* pts, int64_t m, const double* tubes,
+                           int problem, int T, double* out, int64_t ldout, void* work, int64_t chunk, int slices,
+                           double tau, int* flagged, socks_stream_t stream);
+
 /* KernelControlFwd.__call__ (kernel_control_fwd.py:217-232): scores[r][a] = c_r^T W (K(X,s) * CUA)[:, a] for the R <= 2
  * row vectors c (float32-rounded cost / constraint values as float64, row stride ldc); W = inv(G) (n x n, ld ldw);
  * scores is R x P contiguous.  socks_fwd_policy adds the heuristic selection of control/common.py:96-100,166-174

@@ -35,6 +35,11 @@ class KernelMaximalSR:
     `regularization_param` precedes `kernel_fn` here (:231-232)."""
 
     predict_chunk = 8192  # test points per GEMM (multiple of 128)
+    # Contraction engine of predict: "i8" = Ozaki splitting on the integer tensor cores (tcgen05.mma kind::i8, csrc/ozaki.cu;
+    # exact digit products, num/den good to ~1e-11), with the FP64 DMMA GEMM for the points it flags; "f64" = DMMA only.
+    predict_engine = "i8"
+    predict_slices = 8
+    predict_tau = 1e-3
 
     def __init__(self, time_horizon=None, constraint_tube=None, target_tube=None, problem="THT",
                  regularization_param=None, kernel_fn=None, batch_size=None, verbose=False, *args, **kwargs):
@@ -164,6 +169,8 @@ class KernelMaximalSR:
         if kparams is None:
             sharded_bandwidth_guard(self._spec)
             kparams = self._spec.params_for(self._Xd, pts)
+        if self._spec.kind == 0 and self.predict_engine == "i8" and d <= 8 and Th >= 2 and kparams[0] < 0:
+            return self._predict_i8(pts, out, kparams)
         if self._spec.kind == 0:  # one enqueue for the whole test set (csrc/compose.cu: socks_srmax_predict)
             chunk = min(self.predict_chunk, -(-m // 128) * 128)
             wk = self._cached_work(_lib.load().socks_srmax_predict_work_bytes(n, P, Th, chunk))
@@ -189,6 +196,36 @@ class KernelMaximalSR:
             _lib.call("socks_gemm_tn", dv.ptr(Kmat), mc, dv.ptr(Bm), ldbm, dv.ptr(Cm), ldbm, mc, ldbm, npad, st)
             _lib.call("socks_srmax_step", dv.ptr(Cm), ldbm, 0, 0, cnt, P, R, 0, dv.ptr(p), d, dv.ptr(self._tubes), prob,
                       Th, dv.ptr(out[:, s:]), out.stride(0), 1, st)
+        return out
+
+    def _predict_i8(self, pts, out, kparams):
+        """Integer tensor-core contraction (socks_srmax_predict_i8) + FP64 recomputation of the points it flags."""
+        import torch
+
+        m, Th = pts.shape[0], int(self.time_horizon)
+        n, d, P = self._n, self._d, self._P
+        lib, st, prob = _lib.load(), dv.stream(), PROBLEM_CODE[self.problem]
+        chunk = min(self.predict_chunk, -(-m // 128) * 128)
+        S = int(self.predict_slices)
+        nbytes = lib.socks_srmax_predict_i8_work_bytes(n, P, Th, chunk, S)
+        wk = self._cached_work(nbytes + 2048)
+        base = (wk.data_ptr() + 1023) // 1024 * 1024
+        flagged = torch.empty(m + 1, dtype=torch.int32, device=pts.device)
+        _lib.call("socks_srmax_predict_i8", dv.ptr(self._Xd), dv.ptr(self._w), dv.ptr(self._vf), n, dv.ptr(self._CUA), n, d,
+                  P, float(kparams[0]), int(kparams[1]), dv.ptr(pts), m, dv.ptr(self._tubes), prob, Th, dv.ptr(out),
+                  out.stride(0), base, chunk, S, float(self.predict_tau), dv.ptr(flagged), st)
+        cnt = int(flagged[0].item())
+        self.last_flagged = cnt
+        if cnt:  # far-away points: the exact FP64 path, scattered back into their columns
+            idx = flagged[1:1 + cnt].long()
+            sub = pts.index_select(0, idx).contiguous()
+            tmp = dv.empty(Th, cnt)
+            c2 = min(self.predict_chunk, -(-cnt // 128) * 128)
+            w2 = dv.work(lib.socks_srmax_predict_work_bytes(n, P, Th, c2))
+            _lib.call("socks_srmax_predict", dv.ptr(self._Xd), dv.ptr(self._w), dv.ptr(self._vf), n, dv.ptr(self._CUA), n, d,
+                      P, float(kparams[0]), int(kparams[1]), dv.ptr(sub), cnt, dv.ptr(self._tubes), prob, Th, dv.ptr(tmp),
+                      tmp.stride(0), dv.ptr(w2), c2, st)
+            out.index_copy_(1, idx, tmp)
         return out
 
     def _cached_work(self, nbytes):

@@ -2,6 +2,10 @@
 // Phase-1 check kernel: C (M x N, int32) = A (M x K, int8, K contiguous) * B (N x K, int8, K contiguous)^T, one CTA per
 // 128 x 64 tile, one MMA (K = 32) per staged K-block.  Validates the descriptor / layout conventions of umma.cuh against
 // an exact integer reference (tools/i8gemm_check.py) before anything is built on them.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+
 #include "umma.cuh"
 
 namespace socks {
@@ -82,4 +86,390 @@ extern "C" int socks_dev_i8gemm_check(const void* A, const void* B, void* C, int
         (const int8_t*)A, (const int8_t*)B, (int32_t*)C, M, N, K, variant);
     SOCKS_CHECK_LAUNCH();
     return SOCKS_OK;
+}
+
+// =====================================================================================================================
+// KernelMaximalSR.predict on the integer tensor cores (Ozaki splitting; gym_socks/algorithms/reach/kernel_sr_max.py:65-72).
+//
+// The contraction  Cm[j][c] = sum_i K(x_i, p_j) * Bm[i][c],  Bm[i][(r,a)] = coef_r[i] CUA[i][a]  (1.5e13 flop at C2) only
+// feeds ratios num/den of sums of NON-NEGATIVE terms that must be good to ~1e-9, so it does not need the FP64 pipe: both
+// operands are split error-free into S unsigned 7-bit digits,
+//     K_ij = sum_s a_s 2^(-7(s+1)),   Bm_ic / 2^(e_r) = sum_t b_t 2^(-7(t+1))      (e_r: exponent of max_i coef_r[i]),
+// and every digit product A_s^T B_t is an EXACT int8 x int8 -> int32 GEMM on tcgen05.mma kind::i8.  Products with
+// s + t = g share one TMEM accumulator; groups g >= S are dropped (below 2^(-7(S+2)) K 127^2 of the scale); the
+// epilogue converts the S accumulators to fp64 and recombines sum_g 2^(-7(g+2)) G_g * 2^(e_r).  CTA tile 128 points x 64
+// columns, S accumulators of 64 TMEM columns (S = 8: all 512), K-block = 32 samples = one MMA per digit pair;
+// int32 is exact for 8192 samples (9 * 8192 * 128 * 127 < 2^31), so the epilogue runs once per 256 K-blocks.
+// Warp roles: warps 0-3 epilogue (TMEM lane = point row), warp 4 = one thread issuing two bulk async copies per stage
+// (the producers write both operands in the exact shared-memory stage layout, so a stage is two contiguous blocks),
+// warp 5 = one thread issuing S(S+1)/2 MMAs per stage; full/empty mbarriers per stage, acc_full/acc_empty per chunk.
+// Points whose normaliser is too small for the fixed-point operand (far from every sample) are listed for the FP64 path.
+namespace socks {
+
+constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KB = 32;
+constexpr int OZ_A_BYTES = OZ_BM * OZ_KB, OZ_B_BYTES = OZ_BN * OZ_KB;
+constexpr int OZ_KCHUNK = 256;  // K-blocks per int32 accumulation chunk
+constexpr int OZ_THREADS = 192;
+
+template <int S>
+struct OzCfg {
+    static constexpr int STAGE_BYTES = S * (OZ_A_BYTES + OZ_B_BYTES);
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (2 * STAGES + 2) * 8 + 16;
+};
+
+template <int S>
+__device__ __forceinline__ void oz_digits(double v01, uint32_t (&dig)[S]) {
+    // v01 in [0, 1]: q = round(v 2^(7S)); leading digit unmasked (v = 1 gives 128), the others 7 bits
+    const long long q = __double2ll_rn(v01 * (double)(1ll << (7 * S)));
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const unsigned d = (unsigned)(q >> (7 * (S - 1 - s)));
+        dig[s] = (s == 0) ? (d & 0xFFu) : (d & 0x7Fu);
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+    srmax_ozaki_kernel(const uint8_t* __restrict__ Aop, const uint8_t* __restrict__ Bop, double* __restrict__ Cm, int64_t ldc,
+                       int kblocks, const double* __restrict__ colscale) {
+    using Cfg = OzCfg<S>;
+    extern __shared__ __align__(1024) uint8_t oz_smem[];
+    uint8_t* stage_base = oz_smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(oz_smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty = full + Cfg::STAGES;
+    uint64_t* acc_full = empty + Cfg::STAGES;
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ctile = blockIdx.x, ptile = blockIdx.y;
+    if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
+    if (tid == 32) {
+        for (int i = 0; i < Cfg::STAGES; ++i) {
+            umma::mbar_init(full + i, 1);
+            umma::mbar_init(empty + i, 1);
+        }
+        umma::mbar_init(acc_full, 1);
+        umma::mbar_init(acc_empty, 128);
+        umma::mbar_fence_init();
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int nchunks = (kblocks + OZ_KCHUNK - 1) / OZ_KCHUNK;
+
+    if (warp == 4) {
+        if (lane == 0) {  // ---- loader: one stage = S slices of A (128 x 32 B) + S slices of B (64 x 32 B)
+            const uint8_t* a_src = Aop + (int64_t)ptile * kblocks * (S * OZ_A_BYTES);
+            const uint8_t* b_src = Bop + (int64_t)ctile * kblocks * (S * OZ_B_BYTES);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int st = kb % Cfg::STAGES, round = kb / Cfg::STAGES;
+                if (round > 0) umma::mbar_wait(empty + st, (uint32_t)(round - 1) & 1u);
+                uint8_t* sa = stage_base + st * Cfg::STAGE_BYTES;
+                umma::mbar_arrive_expect_tx(full + st, Cfg::STAGE_BYTES);
+                umma::bulk_g2s(sa, a_src + (int64_t)kb * (S * OZ_A_BYTES), S * OZ_A_BYTES, full + st);
+                umma::bulk_g2s(sa + S * OZ_A_BYTES, b_src + (int64_t)kb * (S * OZ_B_BYTES), S * OZ_B_BYTES, full + st);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {  // ---- MMA issuer
+            const uint32_t idesc = umma::idesc_i8(OZ_BM, OZ_BN, 0, 0);  // unsigned digits
+            for (int kc = 0; kc < nchunks; ++kc) {
+                if (kc > 0) {
+                    umma::mbar_wait(acc_empty, (uint32_t)(kc - 1) & 1u);
+                    umma::tc_fence_after();
+                }
+                const int kb0 = kc * OZ_KCHUNK, kb1 = min(kblocks, kb0 + OZ_KCHUNK);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const int st = kb % Cfg::STAGES, round = kb / Cfg::STAGES;
+                    umma::mbar_wait(full + st, (uint32_t)round & 1u);
+                    umma::tc_fence_after();
+                    const uint32_t sa = umma::smem_u32(stage_base + st * Cfg::STAGE_BYTES), sb = sa + S * OZ_A_BYTES;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        const uint64_t da = umma::smem_desc_kmajor_noswizzle(sa + s * OZ_A_BYTES, 128, 256);
+#pragma unroll
+                        for (int t = 0; t + s < S; ++t) {
+                            const uint64_t db = umma::smem_desc_kmajor_noswizzle(sb + t * OZ_B_BYTES, 128, 256);
+                            // s = 0 touches every group first: it overwrites at the start of an accumulation chunk
+                            umma::mma_i8(tmem + (uint32_t)((s + t) * OZ_BN), da, db, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma::mma_commit(empty + st);  // the stage is free once these MMAs have read it
+                }
+                umma::mma_commit(acc_full);
+            }
+        }
+    } else {  // ---- epilogue: thread = point row; int32 groups -> fp64, recombine, scale, store / accumulate
+        const int64_t row = (int64_t)ptile * OZ_BM + tid;
+        for (int kc = 0; kc < nchunks; ++kc) {
+            umma::mbar_wait(acc_full, (uint32_t)kc & 1u);
+            umma::tc_fence_after();
+            for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+                double v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.0;
+#pragma unroll
+                for (int g = S - 1; g >= 0; --g) {  // smallest weights first
+                    uint32_t u[16];
+                    umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * OZ_BN + c0), u);
+                    umma::tmem_ld_wait();
+                    const double pw = __longlong_as_double((long long)(1023 - 7 * (g + 2)) << 52);  // 2^(-7(g+2))
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fma((double)(int)u[i], pw, v[i]);
+                }
+                double* dst = Cm + row * ldc + (int64_t)ctile * OZ_BN + c0;
+                const double* cs = colscale + (int64_t)ctile * OZ_BN + c0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const double x = v[i] * cs[i];
+                    dst[i] = kc ? dst[i] + x : x;
+                }
+            }
+            umma::tc_fence_before();
+            umma::mbar_arrive(acc_empty);
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+// ---- operand producers: both write the shared-memory stage layout directly -----------------------------------------
+// Aop[ptile][kb][s][core layout of 128 points x 32 samples]: digits of K(x_i, p_j) (direct form, CUDA exp).
+template <int D, int S>
+__global__ void __launch_bounds__(128)
+    oz_slice_points_kernel(const double* __restrict__ X, int64_t n, const double* __restrict__ pts, int64_t m, double kmul,
+                           uint8_t* __restrict__ Aop, int kblocks) {
+    __shared__ double sx[512 * D];
+    const int r = threadIdx.x;
+    const int64_t ptile = blockIdx.y, j = ptile * OZ_BM + r;
+    const int kbase = blockIdx.x * 16;
+    for (int e = threadIdx.x; e < 512 * D; e += 128) {
+        const int64_t i = (int64_t)kbase * 32 + e / D;
+        sx[e] = (i < n) ? X[i * D + e % D] : 0.0;
+    }
+    __syncthreads();
+    double p[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) p[k] = pts[min(j, m - 1) * D + k];
+    const bool live_j = j < m;
+    for (int kbl = 0; kbl < 16; ++kbl) {
+        const int kb = kbase + kbl;
+        if (kb >= kblocks) break;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t words[S][4];
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) words[s][q] = 0;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int li = kbl * 32 + c * 16 + e;
+                const int64_t i = (int64_t)kbase * 32 + li;
+                double d2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    const double t = p[k] - sx[li * D + k];
+                    d2 = fma(t, t, d2);
+                }
+                const double kv = (live_j && i < n) ? exp(d2 * kmul) : 0.0;
+                uint32_t dig[S];
+                oz_digits<S>(kv, dig);
+#pragma unroll
+                for (int s = 0; s < S; ++s) words[s][e >> 2] |= dig[s] << (8 * (e & 3));
+            }
+            uint8_t* dst = Aop + (((int64_t)ptile * kblocks + kb) * S) * OZ_A_BYTES + core_offset(r, c);
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                *reinterpret_cast<uint4*>(dst + (int64_t)s * OZ_A_BYTES) =
+                    make_uint4(words[s][0], words[s][1], words[s][2], words[s][3]);
+        }
+    }
+}
+
+// rowscale[r] = 2^(e_r) >= max_i coef_r[i], inv[r] = 2^(-e_r); coef_0 = w, coef_r = vf[r] * w (srmax_pack's rows)
+__global__ void oz_rowscale_kernel(const double* __restrict__ w, const double* __restrict__ vf, int64_t ldvf, int64_t n,
+                                   double* __restrict__ rowscale, double* __restrict__ inv) {
+    __shared__ double sm[256];
+    const int r = blockIdx.x;
+    double mx = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) mx = fmax(mx, r == 0 ? w[i] : vf[(int64_t)r * ldvf + i] * w[i]);
+    sm[threadIdx.x] = mx;
+    __syncthreads();
+    for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + off]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double m0 = sm[0];
+        const int e = (m0 > 0.0 && m0 < INFINITY) ? ilogb(m0) + 1 : 0;
+        rowscale[r] = ldexp(1.0, e);
+        inv[r] = ldexp(1.0, -e);
+    }
+}
+
+__global__ void oz_colscale_kernel(const double* __restrict__ rowscale, int P, int T, int64_t ld, double* __restrict__ colscale) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ld) return;
+    colscale[c] = (c < (int64_t)T * P) ? rowscale[c / P] : 0.0;
+}
+
+// Bop[ctile][kb][t][core layout of 64 columns x 32 samples]: digits of coef_r[i] CUA[i][a] / 2^(e_r).
+template <int S>
+__global__ void __launch_bounds__(64)
+    oz_slice_coef_kernel(const double* __restrict__ CUA, int64_t n, int P, const double* __restrict__ w,
+                         const double* __restrict__ vf, int64_t ldvf, int T, const double* __restrict__ inv,
+                         uint8_t* __restrict__ Bop, int kblocks) {
+    const int col = threadIdx.x;
+    const int64_t ctile = blockIdx.y, c = ctile * OZ_BN + col;
+    const bool live_c = c < (int64_t)T * P;
+    const int r = live_c ? (int)(c / P) : 0, a = live_c ? (int)(c % P) : 0;
+    const double sc = inv[r];
+    const int kbase = blockIdx.x * 16;
+    for (int kbl = 0; kbl < 16; ++kbl) {
+        const int kb = kbase + kbl;
+        if (kb >= kblocks) break;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            uint32_t words[S][4];
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) words[s][q] = 0;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int64_t i = (int64_t)kb * 32 + ch * 16 + e;
+                double v = 0.0;
+                if (live_c && i < n) {
+                    const double coef = (r == 0) ? w[i] : vf[(int64_t)r * ldvf + i] * w[i];
+                    v = fmin(coef * CUA[i * P + a] * sc, 1.0);
+                }
+                uint32_t dig[S];
+                oz_digits<S>(v, dig);
+#pragma unroll
+                for (int s = 0; s < S; ++s) words[s][e >> 2] |= dig[s] << (8 * (e & 3));
+            }
+            uint8_t* dst = Bop + (((int64_t)ctile * kblocks + kb) * S) * OZ_B_BYTES + core_offset(col, ch);
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                *reinterpret_cast<uint4*>(dst + (int64_t)s * OZ_B_BYTES) =
+                    make_uint4(words[s][0], words[s][1], words[s][2], words[s][3]);
+        }
+    }
+}
+
+// Points whose smallest normaliser den[a] = Cm[j][a] is below `tau` of the operand scale are queued for the FP64 path
+// (list[0] = count, list[1..] = global point indices): there the fixed-point digits no longer carry ~1e-9 relative.
+__global__ void oz_flag_kernel(const double* __restrict__ Cm, int64_t ldc, int64_t m, int P, const double* __restrict__ rowscale,
+                               double tau, int64_t j0, int* __restrict__ list) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= m) return;
+    double mn = INFINITY;
+    for (int a = lane; a < P; a += 32) mn = fmin(mn, Cm[j * ldc + a]);
+    for (int off = 16; off > 0; off >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+    if (lane == 0 && !(mn >= tau * rowscale[0])) list[1 + atomicAdd(list, 1)] = (int)(j0 + j);
+}
+
+static inline int64_t pad_to(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+template <int S>
+static int oz_configure() {
+    static std::atomic<bool> done[SOCKS_MAX_DEVICES];
+    int dev = 0;
+    SOCKS_CUDA(cudaGetDevice(&dev));
+    const bool tracked = dev >= 0 && dev < SOCKS_MAX_DEVICES;
+    if (tracked && done[dev].load(std::memory_order_acquire)) return SOCKS_OK;
+    SOCKS_CUDA(cudaFuncSetAttribute(srmax_ozaki_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<S>::SMEM_BYTES));
+    if (tracked) done[dev].store(true, std::memory_order_release);
+    return SOCKS_OK;
+}
+
+template <int S>
+static int srmax_predict_i8_impl(const double* X, const double* w, const double* vf, int64_t ldvf, const double* CUA,
+                                 int64_t n, int d, int P, double kmul, const double* pts, int64_t m, const double* tubes,
+                                 int problem, int T, double* out, int64_t ldout, uint8_t* work, int64_t chunk, double tau,
+                                 int* list, cudaStream_t st) {
+    int rc = oz_configure<S>();
+    if (rc) return rc;
+    const int kblocks = (int)(pad_to(n, OZ_KB) / OZ_KB);
+    const int64_t ldbm = pad_to((int64_t)T * P, 128), ctiles = ldbm / OZ_BN;
+    const int64_t mc = pad_to(std::min(chunk, m), OZ_BM), ptiles = mc / OZ_BM;
+    uint8_t* Bop = work;
+    uint8_t* Aop = Bop + pad_to(ctiles * kblocks * (int64_t)S * OZ_B_BYTES, 1024);
+    double* Cm = reinterpret_cast<double*>(Aop + pad_to(ptiles * kblocks * (int64_t)S * OZ_A_BYTES, 1024));
+    double* rowscale = Cm + mc * ldbm;
+    double* inv = rowscale + pad_to(T, 2);
+    double* colscale = inv + pad_to(T, 2);
+    oz_rowscale_kernel<<<T, 256, 0, st>>>(w, vf, ldvf, n, rowscale, inv);
+    oz_colscale_kernel<<<(unsigned)ceil_div(ldbm, 256), 256, 0, st>>>(rowscale, P, T, ldbm, colscale);
+    oz_slice_coef_kernel<S><<<dim3((unsigned)ceil_div(kblocks, 16), (unsigned)ctiles), 64, 0, st>>>(CUA, n, P, w, vf, ldvf, T, inv,
+                                                                                              Bop, kblocks);
+    SOCKS_CHECK_LAUNCH();
+    SOCKS_CUDA(cudaMemsetAsync(list, 0, sizeof(int), st));
+    for (int64_t s0 = 0; s0 < m; s0 += mc) {
+        const int64_t cnt = std::min(mc, m - s0), pt = ceil_div(cnt, OZ_BM);
+        const double* p = pts + s0 * d;
+        const dim3 gs((unsigned)ceil_div(kblocks, 16), (unsigned)pt);
+#define SOCKS_OZ_CASE(DD)                                                                              \
+    case DD:                                                                                           \
+        oz_slice_points_kernel<DD, S><<<gs, 128, 0, st>>>(X, n, p, cnt, kmul, Aop, kblocks);           \
+        break;
+        switch (d) {
+            SOCKS_OZ_CASE(1) SOCKS_OZ_CASE(2) SOCKS_OZ_CASE(3) SOCKS_OZ_CASE(4)
+            SOCKS_OZ_CASE(5) SOCKS_OZ_CASE(6) SOCKS_OZ_CASE(7) SOCKS_OZ_CASE(8)
+        }
+#undef SOCKS_OZ_CASE
+        SOCKS_CHECK_LAUNCH();
+        srmax_ozaki_kernel<S><<<dim3((unsigned)ctiles, (unsigned)pt), OZ_THREADS, OzCfg<S>::SMEM_BYTES, st>>>(
+            Aop, Bop, Cm, ldbm, kblocks, colscale);
+        SOCKS_CHECK_LAUNCH();
+        oz_flag_kernel<<<(unsigned)ceil_div(cnt, 8), 256, 0, st>>>(Cm, ldbm, cnt, P, rowscale, tau, s0, list);
+        SOCKS_CHECK_LAUNCH();
+        rc = socks_srmax_step(Cm, ldbm, nullptr, 0, cnt, P, T, 0, p, d, tubes, problem, T, out + s0, ldout, 1,
+                              (socks_stream_t)st);
+        if (rc) return rc;
+    }
+    return SOCKS_OK;
+}
+
+}  // namespace socks
+
+extern "C" int64_t socks_srmax_predict_i8_work_bytes(int64_t n, int P, int T, int64_t chunk, int slices) {
+    const int64_t kblocks = pad_to(n, OZ_KB) / OZ_KB, ldbm = pad_to((int64_t)T * P, 128), mc = pad_to(chunk, OZ_BM);
+    return pad_to((ldbm / OZ_BN) * kblocks * slices * OZ_B_BYTES, 1024) + pad_to((mc / OZ_BM) * kblocks * slices * OZ_A_BYTES, 1024) +
+           (mc * ldbm + 2 * pad_to(T, 2) + ldbm) * 8 + 1024;
+}
+
+extern "C" int socks_srmax_predict_i8(const double* X, const double* w, const double* vf, int64_t ldvf, const double* CUA,
+                                      int64_t n, int d, int P, double scale, int divide, const double* pts, int64_t m,
+                                      const double* tubes, int problem, int T, double* out, int64_t ldout, void* work,
+                                      int64_t chunk, int slices, double tau, int* flagged, socks_stream_t stream) {
+    SOCKS_CHECK_ARG(X && w && vf && CUA, 1);
+    SOCKS_CHECK_ARG(n >= 1, 6);
+    SOCKS_CHECK_ARG(d >= 1 && d <= 8, 7);
+    SOCKS_CHECK_ARG(P >= 1, 8);
+    SOCKS_CHECK_ARG(scale == scale && (!divide || scale != 0.0), 9);
+    SOCKS_CHECK_ARG(m >= 0 && m < ((int64_t)1 << 31), 12);
+    SOCKS_CHECK_ARG(T >= 2, 15);
+    SOCKS_CHECK_ARG(ldout >= m, 17);
+    SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 1023) == 0, 18);
+    SOCKS_CHECK_ARG(chunk >= 1, 19);
+    SOCKS_CHECK_ARG(slices >= 6 && slices <= 8, 20);
+    SOCKS_CHECK_ARG(tau >= 0.0, 21);
+    SOCKS_CHECK_ARG(flagged != nullptr, 22);
+    if (m == 0) return SOCKS_OK;
+    SOCKS_CHECK_ARG(pts != nullptr && out != nullptr, 11);
+    const double kmul = divide ? 1.0 / scale : scale;
+    SOCKS_CHECK_ARG(kmul < 0.0, 9);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* wk = reinterpret_cast<uint8_t*>(work);
+    switch (slices) {
+        case 6: return srmax_predict_i8_impl<6>(X, w, vf, ldvf, CUA, n, d, P, kmul, pts, m, tubes, problem, T, out, ldout, wk, chunk, tau, flagged, st);
+        case 7: return srmax_predict_i8_impl<7>(X, w, vf, ldvf, CUA, n, d, P, kmul, pts, m, tubes, problem, T, out, ldout, wk, chunk, tau, flagged, st);
+        default: return srmax_predict_i8_impl<8>(X, w, vf, ldvf, CUA, n, d, P, kmul, pts, m, tubes, problem, T, out, ldout, wk, chunk, tau, flagged, st);
+    }
 }
