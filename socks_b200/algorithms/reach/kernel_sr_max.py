@@ -38,8 +38,8 @@ class KernelMaximalSR:
     # Contraction engine of predict: "i8" = Ozaki splitting on the integer tensor cores (tcgen05.mma kind::i8, csrc/ozaki.cu;
     # exact digit products, num/den good to ~1e-11), with the FP64 DMMA GEMM for the points it flags; "f64" = DMMA only.
     predict_engine = "i8"
-    predict_slices = 8
-    predict_tau = 1e-3
+    predict_slices = 7   # 49-bit fixed point: |num, den error| ~ 4e-12 of the operand scale at N = 20 000 (measured)
+    predict_tau = 1e-2   # points with min_a den[a] < tau * scale go to the FP64 path (relative error there > ~4e-10)
 
     def __init__(self, time_horizon=None, constraint_tube=None, target_tube=None, problem="THT",
                  regularization_param=None, kernel_fn=None, batch_size=None, verbose=False, *args, **kwargs):

@@ -353,3 +353,38 @@ def test_kernel_sr_other_kernel_families(family):
     want = orc.sr_recursion(pts, w, cpu(X, pts), T, ct, tt, vf, "FHT")
     assert np.max(np.abs(alg.value_functions - vf)) <= TOL
     assert np.max(np.abs(alg.predict(pts) - want)) <= TOL
+
+
+@pytest.mark.parametrize("slices", [6, 7, 8])
+def test_kernel_sr_max_int8_engine_matches_fp64_engine(slices):
+    """KernelMaximalSR.predict: Ozaki digit splitting on the integer tensor cores (tcgen05.mma kind::i8, csrc/ozaki.cu)
+    against the FP64 DMMA contraction and the oracle; ragged sizes (N, M, T*P not multiples of the tiles), several
+    chunks, points far from the data (flagged -> recomputed in FP64, NaN columns where numpy has them)."""
+    _, _, KernelMaximalSR, _, _, rbf = _api()
+    n, T, P = 1237, 7, 37
+    X, U, Y = syn.integrator_sample(n, seed=81)
+    rng = np.random.default_rng(82)
+    near = syn.uniform_points(1500, seed=83, low=-1.05, high=1.05)
+    far = np.stack([np.linspace(1.2, 60.0, 61), rng.uniform(-1, 1, 61)], axis=1)  # progressively far, then underflow
+    pts = np.concatenate([near, far])
+    A = np.linspace(-1, 1, P).reshape(-1, 1)
+    ct, tt = syn.integrator_tubes(T)
+    alg = KernelMaximalSR(time_horizon=T, constraint_tube=ct, target_tube=tt, problem="THT",
+                          kernel_fn=partial(rbf, sigma=0.1), regularization_param=1.0)
+    alg.fit_arrays(X, U, Y, A)
+    alg.predict_engine = "f64"
+    want = alg.predict(pts)
+    o = orc.KernelMaximalSROracle(T, ct, tt, "THT", 0.1, 1.0).fit(X, U, Y, A)
+    with np.errstate(all="ignore"):
+        ref = o.predict(pts)
+    alg.predict_engine, alg.predict_slices, alg.predict_chunk = "i8", slices, 512
+    got = alg.predict(pts)
+    assert alg.last_flagged >= 30  # the far points were not trusted to the fixed-point operand
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(want)
+    tol = {6: 2e-9, 7: 2e-10, 8: 1e-11}[slices]
+    assert np.max(np.abs(got[ok] - want[ok])) <= tol
+    assert np.max(np.abs(got[ok] - ref[ok])) <= TOL
+    # flagged points come from the FP64 path itself: identical bits
+    idx = np.arange(1500, len(pts))[-20:]
+    assert np.array_equal(got[:, idx], want[:, idx], equal_nan=True)
