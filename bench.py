@@ -474,7 +474,15 @@ def maximal_sr_extra(n, m, T, d, ct, tt, X, U, Y, pts, P=100):
     cols = -(-T * P // 128) * 128
     res = {"P": P, "fit_s": t_fit, "predict_s": t_pred, "points_per_s": m / t_pred,
            "predict_gemm_tflops": 2.0 * npad * m * cols / t_pred / 1e12,
-           "note": "predict = one DMMA GEMM K(X,pts)^T [diag(coef_r) CUA]_r per chunk of test points + fused max/step"}
+           "engine": f"{alg.predict_engine} ({alg.predict_slices} slices)" if alg.predict_engine == "i8" else "f64",
+           "flagged_points": getattr(alg, "last_flagged", None),
+           "note": "predict = K(X,pts)^T [diag(coef_r) CUA]_r per chunk of test points + fused max/step; engine i8: Ozaki "
+                   "digit splitting, exact int8 products on tcgen05.mma kind::i8 (predict_gemm_tflops is then the "
+                   "fp64-EQUIVALENT rate of the contraction), FP64 DMMA for flagged points"}
+    alg.predict_engine = "f64"
+    alg.predict_dev(pts[:16384])
+    t64, _ = timed(lambda: alg.predict_dev(pts))
+    res["predict_s_f64_engine"] = t64
     del alg, out
     torch.cuda.empty_cache()
     return res
