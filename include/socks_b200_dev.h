@@ -21,6 +21,12 @@ int socks_dev_potf2_phases(double* A, int64_t lda, double* dinv, int* info_dev, 
  * N % 64 == 0, K % 32 == 0.  variant swaps the descriptor's leading / stride byte offsets (layout-convention probe). */
 int socks_dev_i8gemm_check(const void* A, const void* B, void* C, int M, int N, int K, int variant,
                            socks_stream_t stream);
+/* FP64-equivalent C (m x n) -= A (m x K) B (n x K)^T on the integer tensor cores (Ozaki scheme: 7 balanced base-256
+ * digits per operand, 28 exact int8 GEMMs on tcgen05.mma kind::i8, fp64 recombination); m, n % 128 == 0, K % 32 == 0,
+ * K <= 16384; syrk != 0: B = A.  The factorisation's trailing updates run through the same kernels. */
+int64_t socks_dev_ozaki_gemm_work_bytes(int64_t m, int64_t n, int64_t K);
+int socks_dev_ozaki_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t m,
+                            int64_t n, int64_t K, int syrk, int lower_only, void* work, socks_stream_t stream);
 /* Block-column width of socks_potrf_inv's look-ahead factorisation (see socks_b200.h); returns the previous value. */
 int socks_potrf_inv_set_block(int nb);
 

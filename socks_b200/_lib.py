@@ -84,6 +84,8 @@ SIGNATURES = {
     "socks_allgather": (_I, [_P, _P, _P, _L]),
     "socks_dev_potf2_phases": (_I, [_P, _L, _P, _P, _P, _P]),
     "socks_dev_i8gemm_check": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "socks_dev_ozaki_gemm_work_bytes": (_L, [_L, _L, _L]),
+    "socks_dev_ozaki_gemm_nt": (_I, [_P, _L, _P, _L, _P, _L, _L, _L, _L, _I, _I, _P, _P]),
     "socks_probe_fp64": (_I, [_I, _I, _P, _I, _P]),
 }
 

@@ -473,3 +473,269 @@ extern "C" int socks_srmax_predict_i8(const double* X, const double* w, const do
         default: return srmax_predict_i8_impl<8>(X, w, vf, ldvf, CUA, n, d, P, kmul, pts, m, tubes, problem, T, out, ldout, wk, chunk, tau, flagged, st);
     }
 }
+
+// =====================================================================================================================
+// FP64-equivalent GEMM on the integer tensor cores (Ozaki scheme) for the factorisation's trailing updates:
+//     C (m x n) -= A (m x K) * B (n x K)^T,   A, B, C fp64 row-major.
+// Each row of an operand is scaled by 2^(-e_row) (e_row = exponent of its largest magnitude) and written as S = 7
+// BALANCED base-256 digits d in [-128, 127] (int8): v 2^(-e) 2^54 = sum_s d_s 256^(6-s), exactly.  Digit products are
+// exact int8 x int8 -> int32 GEMMs (|sum| <= 7 K 2^14 < 2^31 for K <= 16384); products with s + t = g share a TMEM
+// accumulator and carry the weight 2^(-12 - 8g); groups g >= 7 (< 2^(-68) K 2^14 of |a|_max |b|_max per entry, i.e.
+// below the rounding error K u |a||b| of an fp64 GEMM for K <= 2^14) are dropped.  The result is normwise as accurate
+// as DGEMM; 28 int8 GEMMs replace one fp64 GEMM.  Operand digits live in 128-row tiles of the shared-memory stage
+// layout: Dop[tile][kb][s][128 rows x 32 B core-matrix layout].
+namespace socks {
+
+constexpr int OG_S = 7;
+
+// exps[row] = 2^(e) with 2^(e-1) <= max_k |P[row][k]| < 2^e (1 for an all-zero row); one warp per row.
+__global__ void oz_rowscale_rows_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t ld,
+                                        double* __restrict__ scale) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const double* p = P + r * ld;
+    double mx = 0.0;
+    for (int64_t k = lane * 2; k < K; k += 64) {
+        const double2 v = *reinterpret_cast<const double2*>(p + k);
+        mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+    }
+    for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if (lane == 0) scale[r] = (mx > 0.0 && mx < INFINITY) ? ldexp(1.0, ilogb(mx) + 1) : 1.0;
+}
+
+// Balanced base-256 digits of q (|q| < 2^54): q = sum_s d_s 256^(6-s), d_s in [-128, 127] (d_0 in [-64, 64]).
+__device__ __forceinline__ void oz_signed_digits(long long q, uint32_t (&dig)[OG_S]) {
+#pragma unroll
+    for (int s = OG_S - 1; s > 0; --s) {
+        const int d = (int)(signed char)(q & 0xFF);
+        dig[s] = (uint32_t)(d & 0xFF);
+        q = (q - d) >> 8;  // exact: q - d is a multiple of 256
+    }
+    dig[0] = (uint32_t)((int)q & 0xFF);
+}
+
+// Dop[rtile][kb][s][core layout]: digits of P[row][k] / scale[row]; thread = row of the tile, 16 kblocks per CTA.
+__global__ void __launch_bounds__(128)
+    oz_slice_rows_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t ld, const double* __restrict__ scale,
+                         uint8_t* __restrict__ Dop, int kblocks) {
+    const int r = threadIdx.x;
+    const int64_t rtile = blockIdx.y, row = rtile * OZ_BM + r;
+    const bool live = row < rows;
+    const double inv = live ? (0x1p54 / scale[row]) : 0.0;  // exact power of two; |q| < 2^54 keeps the top digit in [-64, 64]
+    const double* p = P + (live ? row : 0) * ld;
+    const int kb0 = blockIdx.x * 16;
+    for (int kbl = 0; kbl < 16; ++kbl) {
+        const int kb = kb0 + kbl;
+        if (kb >= kblocks) break;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t words[OG_S][4];
+#pragma unroll
+            for (int s = 0; s < OG_S; ++s)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) words[s][q] = 0;
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+                const int64_t k = (int64_t)kb * 32 + c * 16 + e;
+                double2 v = make_double2(0.0, 0.0);
+                if (live && k + 1 < K) v = *reinterpret_cast<const double2*>(p + k);
+                else if (live && k < K) v.x = p[k];
+                uint32_t d0[OG_S], d1[OG_S];
+                oz_signed_digits(__double2ll_rn(v.x * inv), d0);
+                oz_signed_digits(__double2ll_rn(v.y * inv), d1);
+#pragma unroll
+                for (int s = 0; s < OG_S; ++s) words[s][e >> 2] |= (d0[s] << (8 * (e & 3))) | (d1[s] << (8 * ((e + 1) & 3)));
+            }
+            uint8_t* dst = Dop + (((int64_t)rtile * kblocks + kb) * OG_S) * OZ_A_BYTES + core_offset(r, c);
+#pragma unroll
+            for (int s = 0; s < OG_S; ++s)
+                *reinterpret_cast<uint4*>(dst + (int64_t)s * OZ_A_BYTES) =
+                    make_uint4(words[s][0], words[s][1], words[s][2], words[s][3]);
+        }
+    }
+}
+
+struct OgCfg {
+    static constexpr int STAGE_BYTES = OG_S * (OZ_A_BYTES + OZ_B_BYTES);
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (2 * STAGES + 2) * 8 + 16;
+};
+
+// C[m0 + i][n0 + j] -= sa[i] sb[j] sum_g 2^(-12 - 8g) G_g[i][j];  CTA = 128 rows x 64 columns; the B-side operand is the
+// `half`-th 64-row half of 128-row tile n0/128 of Bop.
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+    oz_gemm_nt_kernel(const uint8_t* __restrict__ Aop, const double* __restrict__ sa, const uint8_t* __restrict__ Bop,
+                      const double* __restrict__ sb, double* __restrict__ C, int64_t ldc, int kblocks, int lower_only) {
+    constexpr int S = OG_S;
+    using Cfg = OgCfg;
+    const int ctile = blockIdx.x, ptile = blockIdx.y;
+    if (lower_only && (int64_t)ctile * OZ_BN > (int64_t)ptile * OZ_BM + (OZ_BM - 1)) return;
+    extern __shared__ __align__(1024) uint8_t oz_smem[];
+    uint8_t* stage_base = oz_smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(oz_smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty = full + Cfg::STAGES;
+    uint64_t* acc_full = empty + Cfg::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
+    if (tid == 32) {
+        for (int i = 0; i < Cfg::STAGES; ++i) {
+            umma::mbar_init(full + i, 1);
+            umma::mbar_init(empty + i, 1);
+        }
+        umma::mbar_init(acc_full, 1);
+        umma::mbar_fence_init();
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (warp == 4) {
+        if (lane == 0) {
+            const uint8_t* a_src = Aop + (int64_t)ptile * kblocks * (S * OZ_A_BYTES);
+            const uint8_t* b_src = Bop + (int64_t)(ctile >> 1) * kblocks * (S * OZ_A_BYTES) + (ctile & 1) * OZ_B_BYTES;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int st = kb % Cfg::STAGES, round = kb / Cfg::STAGES;
+                if (round > 0) umma::mbar_wait(empty + st, (uint32_t)(round - 1) & 1u);
+                uint8_t* sA = stage_base + st * Cfg::STAGE_BYTES;
+                uint8_t* sB = sA + S * OZ_A_BYTES;
+                umma::mbar_arrive_expect_tx(full + st, Cfg::STAGE_BYTES);
+                umma::bulk_g2s(sA, a_src + (int64_t)kb * (S * OZ_A_BYTES), S * OZ_A_BYTES, full + st);
+#pragma unroll
+                for (int t = 0; t < S; ++t)  // the 64-row half of each 128-row digit block
+                    umma::bulk_g2s(sB + t * OZ_B_BYTES, b_src + ((int64_t)kb * S + t) * OZ_A_BYTES, OZ_B_BYTES, full + st);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc = umma::idesc_i8(OZ_BM, OZ_BN, 1, 1);  // signed digits
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int st = kb % Cfg::STAGES, round = kb / Cfg::STAGES;
+                umma::mbar_wait(full + st, (uint32_t)round & 1u);
+                umma::tc_fence_after();
+                const uint32_t sA = umma::smem_u32(stage_base + st * Cfg::STAGE_BYTES), sB = sA + S * OZ_A_BYTES;
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    const uint64_t da = umma::smem_desc_kmajor_noswizzle(sA + s * OZ_A_BYTES, 128, 256);
+#pragma unroll
+                    for (int t = 0; t + s < S; ++t) {
+                        const uint64_t db = umma::smem_desc_kmajor_noswizzle(sB + t * OZ_B_BYTES, 128, 256);
+                        umma::mma_i8(tmem + (uint32_t)((s + t) * OZ_BN), da, db, idesc, (kb > 0 || s > 0) ? 1u : 0u);
+                    }
+                }
+                umma::mma_commit(empty + st);
+            }
+            umma::mma_commit(acc_full);
+        }
+    } else {
+        const int64_t row = (int64_t)ptile * OZ_BM + tid;
+        const double sr = sa[row];
+        umma::mbar_wait(acc_full, 0u);
+        umma::tc_fence_after();
+        for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+            double v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.0;
+#pragma unroll
+            for (int g = S - 1; g >= 0; --g) {
+                uint32_t u[16];
+                umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * OZ_BN + c0), u);
+                umma::tmem_ld_wait();
+                const double pw = __longlong_as_double((long long)(1023 - 12 - 8 * g) << 52);  // 2^(-12 - 8g)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fma((double)(int)u[i], pw, v[i]);
+            }
+            double* dst = C + row * ldc + (int64_t)ctile * OZ_BN + c0;
+            const double* cs = sb + (int64_t)ctile * OZ_BN + c0;
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                double2 c = *reinterpret_cast<double2*>(dst + i);
+                c.x -= sr * cs[i] * v[i];
+                c.y -= sr * cs[i + 1] * v[i + 1];
+                *reinterpret_cast<double2*>(dst + i) = c;
+            }
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+static int og_configure() {
+    static std::atomic<bool> done[SOCKS_MAX_DEVICES];
+    int dev = 0;
+    SOCKS_CUDA(cudaGetDevice(&dev));
+    const bool tracked = dev >= 0 && dev < SOCKS_MAX_DEVICES;
+    if (tracked && done[dev].load(std::memory_order_acquire)) return SOCKS_OK;
+    SOCKS_CUDA(cudaFuncSetAttribute(oz_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OgCfg::SMEM_BYTES));
+    if (tracked) done[dev].store(true, std::memory_order_release);
+    return SOCKS_OK;
+}
+
+// Digits + row scales of a (rows x K) fp64 operand; rows are padded to whole 128-row tiles with zeros.
+int64_t ozaki_operand_bytes(int64_t rows, int64_t K) {
+    const int64_t rt = pad_to(rows, OZ_BM) / OZ_BM, kb = pad_to(K, OZ_KB) / OZ_KB;
+    return pad_to(rt * kb * OG_S * OZ_A_BYTES, 1024) + pad_to(rt * OZ_BM * 8, 1024);
+}
+int ozaki_slice_operand(const double* P, int64_t rows, int64_t K, int64_t ld, uint8_t* buf, cudaStream_t st) {
+    const int64_t rt = pad_to(rows, OZ_BM) / OZ_BM;
+    const int kb = (int)(pad_to(K, OZ_KB) / OZ_KB);
+    double* scale = reinterpret_cast<double*>(buf + pad_to(rt * kb * OG_S * OZ_A_BYTES, 1024));
+    oz_rowscale_rows_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(P, rows, K, ld, scale);
+    oz_slice_rows_kernel<<<dim3((unsigned)ceil_div(kb, 16), (unsigned)rt), 128, 0, st>>>(P, rows, K, ld, scale, buf, kb);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("ozaki_slice_operand: %s", cudaGetErrorString(e));
+        return SOCKS_ECUDA;
+    }
+    return SOCKS_OK;
+}
+// C (m x n) -= A B^T from sliced operands (row offsets in units of 128 rows into each operand buffer).
+int ozaki_gemm_nt_sliced(const uint8_t* abuf, int64_t a_rows_total, int64_t a_tile0, const uint8_t* bbuf, int64_t b_rows_total,
+                         int64_t b_tile0, int64_t K, double* C, int64_t ldc, int64_t m, int64_t n, int lower_only,
+                         cudaStream_t st) {
+    int rc = og_configure();
+    if (rc) return rc;
+    const int kb = (int)(pad_to(K, OZ_KB) / OZ_KB);
+    const int64_t art = pad_to(a_rows_total, OZ_BM) / OZ_BM, brt = pad_to(b_rows_total, OZ_BM) / OZ_BM;
+    const double* sa = reinterpret_cast<const double*>(abuf + pad_to(art * kb * OG_S * OZ_A_BYTES, 1024)) + a_tile0 * OZ_BM;
+    const double* sb = reinterpret_cast<const double*>(bbuf + pad_to(brt * kb * OG_S * OZ_A_BYTES, 1024)) + b_tile0 * OZ_BM;
+    const uint8_t* aop = abuf + a_tile0 * (int64_t)kb * OG_S * OZ_A_BYTES;
+    const uint8_t* bop = bbuf + b_tile0 * (int64_t)kb * OG_S * OZ_A_BYTES;
+    oz_gemm_nt_kernel<<<dim3((unsigned)(n / OZ_BN), (unsigned)(m / OZ_BM)), OZ_THREADS, OgCfg::SMEM_BYTES, st>>>(
+        aop, sa, bop, sb, C, ldc, kb, lower_only);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("ozaki_gemm_nt: %s", cudaGetErrorString(e));
+        return SOCKS_ECUDA;
+    }
+    return SOCKS_OK;
+}
+
+}  // namespace socks
+
+extern "C" int64_t socks_dev_ozaki_gemm_work_bytes(int64_t m, int64_t n, int64_t K) {
+    return ozaki_operand_bytes(m, K) + ozaki_operand_bytes(n, K) + 2048;
+}
+
+// C (m x n, ldc) -= A (m x K, lda) B (n x K, ldb)^T through the integer tensor cores; m, n multiples of 128, K of 32,
+// K <= 16384.  syrk != 0: B is A (sliced once), lower_only as in socks_gemm_f64.  work: 1024-byte aligned.
+extern "C" int socks_dev_ozaki_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                                       int64_t m, int64_t n, int64_t K, int syrk, int lower_only, void* work,
+                                       socks_stream_t stream) {
+    SOCKS_CHECK_ARG(A != nullptr && lda >= K && lda % 2 == 0, 1);
+    SOCKS_CHECK_ARG(syrk || (B != nullptr && ldb >= K && ldb % 2 == 0), 3);
+    SOCKS_CHECK_ARG(C != nullptr && ldc >= n && ldc % 2 == 0, 5);
+    SOCKS_CHECK_ARG(m > 0 && m % 128 == 0, 7);
+    SOCKS_CHECK_ARG(n > 0 && n % 128 == 0 && (!syrk || n == m), 8);
+    SOCKS_CHECK_ARG(K > 0 && K % 32 == 0 && K <= 16384, 9);
+    SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 1023) == 0, 12);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* abuf = reinterpret_cast<uint8_t*>(work);
+    uint8_t* bbuf = syrk ? abuf : abuf + ozaki_operand_bytes(m, K);
+    int rc = ozaki_slice_operand(A, m, K, lda, abuf, st);
+    if (rc) return rc;
+    if (!syrk && (rc = ozaki_slice_operand(B, n, K, ldb, bbuf, st))) return rc;
+    return ozaki_gemm_nt_sliced(abuf, m, 0, bbuf, syrk ? m : n, 0, K, C, ldc, m, n, lower_only, st);
+}
