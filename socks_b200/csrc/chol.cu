@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "gemm_f64.cuh"
+#include "ozaki.cuh"
 #include "reduce.cuh"
 
 namespace socks {
@@ -507,6 +508,7 @@ static Lookahead* lookahead_for_device(int* rc_out) {
     return &l;
 }
 
+static int g_potrf_ozaki = 1;  // 1: trailing updates on the integer tensor cores (csrc/ozaki.cu), 0: FP64 DMMA GEMM
 static int g_potrf_tail = 1;   // 1: half-width block columns over the last 4 NB columns
 static int g_potrf_nb = 1024;  // block-column width of the look-ahead factorisation (multiple of 128; 0 = pure recursion)
 
@@ -532,11 +534,22 @@ static void run_merge(CholCtx& cx, double* M, int64_t ldm, const int64_t* bnd, c
     cx.note(gemm_f64<false, false>(work, n1, M11, ldm, M21, ldm, n2, n1, n1, -1.0, 0.0, GEMM_B_K_GE_N, 0, cx.st));
 }
 
+static inline int64_t trtri_scratch_doubles(int64_t np) {
+    if (np <= LF) return 2;
+    const int64_t n1 = split_point(np);
+    return n1 * (np - n1);
+}
+// digits of one block-column panel (np x NB) for the integer tensor-core trailing updates, after the merge scratch
+static inline int64_t potrf_digit_bytes(int64_t np) { return ozaki_operand_bytes(np, 2048) + 2048; }
+
 static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, int64_t np, double* work, int* info,
                                bool keep_l, cudaStream_t s1, int64_t NB) {
     int rc;
     Lookahead* la = lookahead_for_device(&rc);
     if (!la) return rc;
+    uint8_t* digits = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(work + trtri_scratch_doubles(np)) + 1023) & ~(uintptr_t)1023);
+    const bool use_ozaki = g_potrf_ozaki && NB <= 2048;
     CholCtx c1{s1}, c2{la->s2};
     // block-column boundaries: NB wide, but half as wide over the last 4 NB columns -- there the trailing update is
     // shorter than the critical path of a block (leaves + small GEMMs), so shorter blocks shorten what is exposed
@@ -579,11 +592,21 @@ static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, i
         const double* L21 = M + (k0 + bk) * ldm + k0;
         double* A22 = A + (k0 + bk) * lda + (k0 + bk);
         // next block column first (rows rem x cols b1), then the rest of the trailing lower triangle
-        c1.note(gemm_f64<false, true>(L21, ldm, L21, ldm, A22, lda, rem, b1, bk, -1.0, 1.0, 0, 1, s1));
-        c1.note(cudaEventRecord(la->ev_col, s1));
-        if (rem > b1)
-            c1.note(gemm_f64<false, true>(L21 + b1 * ldm, ldm, L21 + b1 * ldm, ldm, A22 + b1 * lda + b1, lda, rem - b1,
-                                          rem - b1, bk, -1.0, 1.0, 0, 1, s1));
+        if (use_ozaki) {
+            // A22 -= L21 L21^T on the integer tensor cores: the panel is split into digits once, both updates read them
+            if ((rc = ozaki_slice_operand(L21, rem, bk, ldm, digits, s1))) return rc;
+            if ((rc = ozaki_gemm_nt_sliced(digits, rem, 0, digits, rem, 0, bk, A22, lda, rem, b1, 1, s1))) return rc;
+            c1.note(cudaEventRecord(la->ev_col, s1));
+            if (rem > b1 && (rc = ozaki_gemm_nt_sliced(digits, rem, b1 / LF, digits, rem, b1 / LF, bk, A22 + b1 * lda + b1,
+                                                       lda, rem - b1, rem - b1, 1, s1)))
+                return rc;
+        } else {
+            c1.note(gemm_f64<false, true>(L21, ldm, L21, ldm, A22, lda, rem, b1, bk, -1.0, 1.0, 0, 1, s1));
+            c1.note(cudaEventRecord(la->ev_col, s1));
+            if (rem > b1)
+                c1.note(gemm_f64<false, true>(L21 + b1 * ldm, ldm, L21 + b1 * ldm, ldm, A22 + b1 * lda + b1, lda, rem - b1,
+                                              rem - b1, bk, -1.0, 1.0, 0, 1, s1));
+        }
     }
     // join, then the large merges (most of the inverse's flops: machine-filling GEMMs) in post-order on the caller's stream
     c2.note(cudaEventRecord(la->ev_panel, la->s2));
@@ -620,8 +643,8 @@ extern "C" int64_t socks_potrf_work_bytes(int64_t n) { return socks_padded_dim(n
 extern "C" int64_t socks_trtri_work_bytes(int64_t n) {
     const int64_t np = socks_padded_dim(n);
     if (np <= LF) return 16;
-    const int64_t n1 = split_point(np), n2 = np - n1;
-    return n1 * n2 * 8;
+    // merge scratch T (n2 x n1) + the digit form of one block-column panel (socks_potrf_inv's integer tensor-core updates)
+    return trtri_scratch_doubles(np) * 8 + potrf_digit_bytes(np);
 }
 
 extern "C" int64_t socks_reduce_work_bytes(int64_t cols) { return 2 * CR_MAX_SPLITS * colreduce_ldpart(cols) * 8; }
@@ -714,8 +737,9 @@ extern "C" int socks_potrf_inv(double* G, int64_t n, int64_t ldg, double* M, int
 // Returns the previous value.  Tuning / measurement knob (tools/run_potrf.py); not thread-safe against running calls.
 extern "C" int socks_potrf_inv_set_block(int nb) {
     const int old = g_potrf_nb;
-    if (nb < 0) {  // -1 / -2: switch the half-width tail off / on (measurement)
-        g_potrf_tail = (nb == -2);
+    if (nb < 0) {  // -1 / -2: half-width tail off / on; -3 / -4: FP64 DMMA / integer tensor-core trailing updates
+        if (nb >= -2) g_potrf_tail = (nb == -2);
+        else g_potrf_ozaki = (nb == -4);
         return old;
     }
     if (nb % LF == 0) g_potrf_nb = nb;

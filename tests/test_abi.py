@@ -45,7 +45,7 @@ def test_version_and_padding():
     assert lib.socks_padded_dim(20000) == 20096
     assert lib.socks_potrf_work_bytes(1000) == 1024 * 128 * 8
     assert lib.socks_trtri_work_bytes(100) == 16
-    assert lib.socks_trtri_work_bytes(1000) == 512 * 512 * 8
+    assert lib.socks_trtri_work_bytes(1000) >= 512 * 512 * 8  # merge scratch + the digit form of one block-column panel
     assert lib.socks_sr_predict_work_bytes(20000, 250000) >= (20000 * 20 + 10 * 16 * 250000) * 8
 
 

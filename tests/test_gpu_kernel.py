@@ -160,14 +160,18 @@ def test_potrf_inv_lookahead_matches_recursion_and_numpy(n, nb, keep_l):
     res = {}
     old = lib.socks_potrf_inv_set_block(nb)
     try:
-        for mode, block in (("lookahead", nb), ("recursion", 0)):
+        for mode, block in (("lookahead", nb), ("lookahead_dmma", nb), ("recursion", 0)):
             lib.socks_potrf_inv_set_block(block)
+            lib.socks_potrf_inv_set_block(-3 if mode == "lookahead_dmma" else -4)  # trailing updates: FP64 DMMA / int8
             fac = mt.factorize(X, None, mt.RBFSpec(sigma=0.2), 1e-4, keep_l=keep_l)
             fac.check()
             res[mode] = (np.tril(fac.inverse_factor()[:n, :n].cpu().numpy()), fac.diag().cpu().numpy(),
                          np.tril(fac.L[:n, :n].cpu().numpy()) if keep_l else None)
     finally:
         lib.socks_potrf_inv_set_block(old)
+        lib.socks_potrf_inv_set_block(-4)
+    Md, wd, _ = res["lookahead_dmma"]
+    assert np.linalg.norm(res["lookahead"][0] - Md) / np.linalg.norm(Md) <= 100 * cond * 2.0 ** -53
     M, w, L = res["lookahead"]
     M0, w0, L0 = res["recursion"]
     Lref = np.linalg.cholesky(G)
