@@ -509,6 +509,7 @@ static Lookahead* lookahead_for_device(int* rc_out) {
 }
 
 static int g_potrf_ozaki = 1;  // 1: trailing updates on the integer tensor cores (csrc/ozaki.cu), 0: FP64 DMMA GEMM
+static int g_potrf_ozaki_merge = 1;  // 1: the large merges of inv(L) on the integer tensor cores as well
 static int g_potrf_tail = 1;   // 1: half-width block columns over the last 4 NB columns
 static int g_potrf_nb = 1024;  // block-column width of the look-ahead factorisation (multiple of 128; 0 = pure recursion)
 
@@ -525,11 +526,31 @@ static void plan_merges(int lo, int hi, std::vector<Merge>& out) {
     plan_merges(mid, hi, out);
     out.push_back(Merge{lo, mid, hi});
 }
-static void run_merge(CholCtx& cx, double* M, int64_t ldm, const int64_t* bnd, const Merge& g, double* work) {
+// digits == nullptr: FP64 DMMA GEMMs.  Otherwise both products run on the integer tensor cores (csrc/ozaki.cu) when
+// their digit operands fit in `digit_bytes`; the triangular structure is clipped exactly as the DMMA GEMM clips it.
+static void run_merge(CholCtx& cx, double* M, int64_t ldm, const int64_t* bnd, const Merge& g, double* work,
+                      uint8_t* digits = nullptr, int64_t digit_bytes = 0) {
     const int64_t o1 = bnd[g.lo], o2 = bnd[g.mid], n1 = bnd[g.mid] - bnd[g.lo], n2 = bnd[g.hi] - bnd[g.mid];
     double* M11 = M + o1 * ldm + o1;
     double* M21 = M + o2 * ldm + o1;  // holds L21
     double* M22 = M + o2 * ldm + o2;
+    const int64_t kmax = std::max(n1, n2);
+    if (digits && ozaki_operand_bytes(n2, kmax) + ozaki_operand_bytes(n1, kmax) <= digit_bytes) {
+        int rc = SOCKS_OK;
+        // T = M22 L21: A = rows of M22 (lower triangular), B = columns of L21, K = n2
+        uint8_t* da = digits;
+        uint8_t* db = digits + ozaki_operand_bytes(n2, n2);
+        if (!rc) rc = ozaki_slice_operand(M22, n2, n2, ldm, 0, 1, da, cx.st);
+        if (!rc) rc = ozaki_slice_operand(M21, n1, n2, ldm, 1, 0, db, cx.st);
+        if (!rc) rc = ozaki_gemm_nt_sliced(da, n2, 0, db, n1, 0, n2, work, n1, n2, n1, 0, 1, 1, 0, cx.st);
+        // M21 = -T M11: A = rows of T, B = columns of M11 (zero above the diagonal: k >= j), K = n1
+        db = digits + ozaki_operand_bytes(n2, n1);
+        if (!rc) rc = ozaki_slice_operand(work, n2, n1, n1, 0, 0, da, cx.st);
+        if (!rc) rc = ozaki_slice_operand(M11, n1, n1, ldm, 1, 2, db, cx.st);
+        if (!rc) rc = ozaki_gemm_nt_sliced(da, n2, 0, db, n1, 0, n1, M21, ldm, n2, n1, 0, 2, 0, 1, cx.st);
+        if (rc) cx.note(cudaErrorUnknown);
+        return;
+    }
     cx.note(gemm_f64<false, false>(M22, ldm, M21, ldm, work, n1, n2, n1, n2, 1.0, 0.0, GEMM_A_K_LE_M, 0, cx.st));
     cx.note(gemm_f64<false, false>(work, n1, M11, ldm, M21, ldm, n2, n1, n1, -1.0, 0.0, GEMM_B_K_GE_N, 0, cx.st));
 }
@@ -540,7 +561,11 @@ static inline int64_t trtri_scratch_doubles(int64_t np) {
     return n1 * (np - n1);
 }
 // digits of one block-column panel (np x NB) for the integer tensor-core trailing updates, after the merge scratch
-static inline int64_t potrf_digit_bytes(int64_t np) { return ozaki_operand_bytes(np, 2048) + 2048; }
+// ... and the two digit operands of the largest merge (rows n1 + n2 <= np, K <= max(n1, n2) <= np/2 + 2 block columns)
+static inline int64_t potrf_digit_bytes(int64_t np) {
+    const int64_t kmax = std::min<int64_t>(np, np / 2 + 2048);
+    return std::max(ozaki_operand_bytes(np, 2048), 2 * ozaki_operand_bytes((np + 1) / 2 + 2048, kmax)) + 2048;
+}
 
 static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, int64_t np, double* work, int* info,
                                bool keep_l, cudaStream_t s1, int64_t NB) {
@@ -594,11 +619,11 @@ static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, i
         // next block column first (rows rem x cols b1), then the rest of the trailing lower triangle
         if (use_ozaki) {
             // A22 -= L21 L21^T on the integer tensor cores: the panel is split into digits once, both updates read them
-            if ((rc = ozaki_slice_operand(L21, rem, bk, ldm, digits, s1))) return rc;
-            if ((rc = ozaki_gemm_nt_sliced(digits, rem, 0, digits, rem, 0, bk, A22, lda, rem, b1, 1, s1))) return rc;
+            if ((rc = ozaki_slice_operand(L21, rem, bk, ldm, 0, 0, digits, s1))) return rc;
+            if ((rc = ozaki_gemm_nt_sliced(digits, rem, 0, digits, rem, 0, bk, A22, lda, rem, b1, 1, 0, 0, 0, s1))) return rc;
             c1.note(cudaEventRecord(la->ev_col, s1));
             if (rem > b1 && (rc = ozaki_gemm_nt_sliced(digits, rem, b1 / LF, digits, rem, b1 / LF, bk, A22 + b1 * lda + b1,
-                                                       lda, rem - b1, rem - b1, 1, s1)))
+                                                       lda, rem - b1, rem - b1, 1, 0, 0, 0, s1)))
                 return rc;
         } else {
             c1.note(gemm_f64<false, true>(L21, ldm, L21, ldm, A22, lda, rem, b1, bk, -1.0, 1.0, 0, 1, s1));
@@ -612,7 +637,9 @@ static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, i
     c2.note(cudaEventRecord(la->ev_panel, la->s2));
     c1.note(cudaStreamWaitEvent(s1, la->ev_panel, 0));
     for (const Merge& g : merges)
-        if (g.hi - g.lo > kSmallMerge) run_merge(c1, M, ldm, bnd.data(), g, work);
+        if (g.hi - g.lo > kSmallMerge)
+            run_merge(c1, M, ldm, bnd.data(), g, work, (use_ozaki && g_potrf_ozaki_merge) ? digits : nullptr,
+                      potrf_digit_bytes(np) - 1024);
     const cudaError_t err = (c1.err != cudaSuccess) ? c1.err : c2.err;
     if (err != cudaSuccess) {
         set_error("socks_potrf_inv: CUDA call failed: %s", cudaGetErrorString(err));
@@ -737,9 +764,11 @@ extern "C" int socks_potrf_inv(double* G, int64_t n, int64_t ldg, double* M, int
 // Returns the previous value.  Tuning / measurement knob (tools/run_potrf.py); not thread-safe against running calls.
 extern "C" int socks_potrf_inv_set_block(int nb) {
     const int old = g_potrf_nb;
-    if (nb < 0) {  // -1 / -2: half-width tail off / on; -3 / -4: FP64 DMMA / integer tensor-core trailing updates
+    if (nb < 0) {  // -1 / -2: half-width tail off / on; -3 / -4: FP64 DMMA / integer tensor-core trailing updates;
+                   // -5 / -6: large merges of the inverse on FP64 DMMA / on the integer tensor cores
         if (nb >= -2) g_potrf_tail = (nb == -2);
-        else g_potrf_ozaki = (nb == -4);
+        else if (nb >= -4) g_potrf_ozaki = (nb == -4);
+        else g_potrf_ozaki_merge = (nb == -6);
         return old;
     }
     if (nb % LF == 0) g_potrf_nb = nb;

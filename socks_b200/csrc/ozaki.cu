@@ -488,20 +488,55 @@ namespace socks {
 
 constexpr int OG_S = 7;
 
-// exps[row] = 2^(e) with 2^(e-1) <= max_k |P[row][k]| < 2^e (1 for an all-zero row); one warp per row.
-__global__ void oz_rowscale_rows_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t ld,
+// Structure masks (128-tile granularity, as everywhere in chol.cu: tiles beyond the block diagonal hold garbage):
+//   OZ_TRI_K_LE_ROW  operand row r only has entries for k <  128 (floor(r/128) + 1)   (lower-triangular A: k <= row)
+//   OZ_TRI_K_GE_ROW  operand row r only has entries for k >= 128 floor(r/128)         (B(k, j) = 0 for k < j)
+enum OzTri : int { OZ_TRI_NONE = 0, OZ_TRI_K_LE_ROW = 1, OZ_TRI_K_GE_ROW = 2 };
+
+__device__ __forceinline__ bool oz_in_range(int tri, int64_t r, int64_t k) {
+    if (tri == OZ_TRI_K_LE_ROW) return k < (r / 128 + 1) * 128;
+    if (tri == OZ_TRI_K_GE_ROW) return k >= (r / 128) * 128;
+    return true;
+}
+
+// Operand element (r, k): P[r][k] (TRANS = false) or P[k][r] (TRANS = true: the operand is the transpose of a row-major
+// K x rows matrix, i.e. the B of an "NN" product).
+// scale[r] = 2^(e) with 2^(e-1) <= max_k |op(r, k)| < 2^e (1 for an all-zero row).
+__global__ void oz_rowscale_rows_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t ld, int tri,
                                         double* __restrict__ scale) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= rows) return;
     const double* p = P + r * ld;
     double mx = 0.0;
-    for (int64_t k = lane * 2; k < K; k += 64) {
-        const double2 v = *reinterpret_cast<const double2*>(p + k);
-        mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
-    }
+    for (int64_t k = lane; k < K; k += 32)
+        if (oz_in_range(tri, r, k)) mx = fmax(mx, fabs(p[k]));
     for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
     if (lane == 0) scale[r] = (mx > 0.0 && mx < INFINITY) ? ldexp(1.0, ilogb(mx) + 1) : 1.0;
+}
+// transposed operand: thread = operand row (= column of P, coalesced across threads), blockIdx.y = 256-sample K chunk;
+// the maxima are combined as integers (non-negative doubles order like their bit patterns), then turned into scales.
+__global__ void oz_colmax_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t ld, int tri,
+                                 unsigned long long* __restrict__ mxbits) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int64_t k0 = (int64_t)blockIdx.y * 256, k1 = min(K, k0 + 256);
+    double mx = 0.0;
+    for (int64_t k = k0; k < k1; ++k)
+        if (oz_in_range(tri, r, k)) mx = fmax(mx, fabs(P[k * ld + r]));
+    if (mx > 0.0) atomicMax(mxbits + r, (unsigned long long)__double_as_longlong(mx));
+}
+__global__ void oz_scale_from_max_kernel(double* __restrict__ scale, int64_t rows) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const double mx = scale[r];
+    scale[r] = (mx > 0.0 && mx < INFINITY) ? ldexp(1.0, ilogb(mx) + 1) : 1.0;
+}
+// K-blocks of operand tile `rtile` that a clipped GEMM reads (the others are neither written nor read)
+__device__ __forceinline__ bool oz_kb_live(int tri, int64_t rtile, int kb) {
+    if (tri == OZ_TRI_K_LE_ROW) return kb < (rtile + 1) * (OZ_BM / OZ_KB);
+    if (tri == OZ_TRI_K_GE_ROW) return kb >= rtile * (OZ_BM / OZ_KB);
+    return true;
 }
 
 // Balanced base-256 digits of q (|q| < 2^54): q = sum_s d_s 256^(6-s), d_s in [-128, 127] (d_0 in [-64, 64]).
@@ -515,19 +550,20 @@ __device__ __forceinline__ void oz_signed_digits(long long q, uint32_t (&dig)[OG
     dig[0] = (uint32_t)((int)q & 0xFF);
 }
 
-// Dop[rtile][kb][s][core layout]: digits of P[row][k] / scale[row]; thread = row of the tile, 16 kblocks per CTA.
+// Dop[rtile][kb][s][core layout]: digits of op(row, k) / scale[row]; thread = operand row of the tile, 16 kblocks per CTA.
+template <bool TRANS>
 __global__ void __launch_bounds__(128)
-    oz_slice_rows_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t ld, const double* __restrict__ scale,
-                         uint8_t* __restrict__ Dop, int kblocks) {
+    oz_slice_rows_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t ld, int tri,
+                         const double* __restrict__ scale, uint8_t* __restrict__ Dop, int kblocks) {
     const int r = threadIdx.x;
     const int64_t rtile = blockIdx.y, row = rtile * OZ_BM + r;
     const bool live = row < rows;
     const double inv = live ? (0x1p54 / scale[row]) : 0.0;  // exact power of two; |q| < 2^54 keeps the top digit in [-64, 64]
-    const double* p = P + (live ? row : 0) * ld;
     const int kb0 = blockIdx.x * 16;
     for (int kbl = 0; kbl < 16; ++kbl) {
         const int kb = kb0 + kbl;
         if (kb >= kblocks) break;
+        if (!oz_kb_live(tri, rtile, kb)) continue;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             uint32_t words[OG_S][4];
@@ -536,16 +572,14 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) words[s][q] = 0;
 #pragma unroll
-            for (int e = 0; e < 16; e += 2) {
+            for (int e = 0; e < 16; ++e) {
                 const int64_t k = (int64_t)kb * 32 + c * 16 + e;
-                double2 v = make_double2(0.0, 0.0);
-                if (live && k + 1 < K) v = *reinterpret_cast<const double2*>(p + k);
-                else if (live && k < K) v.x = p[k];
-                uint32_t d0[OG_S], d1[OG_S];
-                oz_signed_digits(__double2ll_rn(v.x * inv), d0);
-                oz_signed_digits(__double2ll_rn(v.y * inv), d1);
+                double v = 0.0;
+                if (live && k < K && oz_in_range(tri, row, k)) v = TRANS ? P[k * ld + row] : P[row * ld + k];
+                uint32_t d[OG_S];
+                oz_signed_digits(__double2ll_rn(v * inv), d);
 #pragma unroll
-                for (int s = 0; s < OG_S; ++s) words[s][e >> 2] |= (d0[s] << (8 * (e & 3))) | (d1[s] << (8 * ((e + 1) & 3)));
+                for (int s = 0; s < OG_S; ++s) words[s][e >> 2] |= d[s] << (8 * (e & 3));
             }
             uint8_t* dst = Dop + (((int64_t)rtile * kblocks + kb) * OG_S) * OZ_A_BYTES + core_offset(r, c);
 #pragma unroll
@@ -562,21 +596,30 @@ struct OgCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (2 * STAGES + 2) * 8 + 16;
 };
 
-// C[m0 + i][n0 + j] -= sa[i] sb[j] sum_g 2^(-12 - 8g) G_g[i][j];  CTA = 128 rows x 64 columns; the B-side operand is the
-// `half`-th 64-row half of 128-row tile n0/128 of Bop.
+// C[m0 + i][n0 + j] (op)= sa[i] sb[j] sum_g 2^(-12 - 8g) G_g[i][j];  CTA = 128 rows x 64 columns; the B-side operand is
+// the `half`-th 64-row half of 128-row tile n0/128 of Bop.  mode: 0 C -= AB^T, 1 C = AB^T, 2 C = -AB^T.
+// tri_a / tri_b clip the K range per tile exactly like GEMM_A_K_LE_M / GEMM_B_K_GE_N of gemm_f64.cuh.  int32 stays exact
+// for OG_KCHUNK K-blocks; longer products are accumulated chunk by chunk in fp64 through C.
+constexpr int OG_KCHUNK = 512;  // 16 384 samples: 7 * 16384 * 2^14 < 2^31
+
 __global__ void __launch_bounds__(OZ_THREADS, 1)
     oz_gemm_nt_kernel(const uint8_t* __restrict__ Aop, const double* __restrict__ sa, const uint8_t* __restrict__ Bop,
-                      const double* __restrict__ sb, double* __restrict__ C, int64_t ldc, int kblocks, int lower_only) {
+                      const double* __restrict__ sb, double* __restrict__ C, int64_t ldc, int kblocks, int lower_only,
+                      int mode, int tri_a, int tri_b) {
     constexpr int S = OG_S;
     using Cfg = OgCfg;
     const int ctile = blockIdx.x, ptile = blockIdx.y;
     if (lower_only && (int64_t)ctile * OZ_BN > (int64_t)ptile * OZ_BM + (OZ_BM - 1)) return;
+    int kb_lo = 0, kb_hi = kblocks;
+    if (tri_a) kb_hi = min(kb_hi, (ptile + 1) * (OZ_BM / OZ_KB));            // A(i, k) = 0 for k beyond row tile i
+    if (tri_b) kb_lo = max(kb_lo, ((ctile * OZ_BN) / OZ_BM) * (OZ_BM / OZ_KB));  // B(k, j) = 0 for k before column tile j
     extern __shared__ __align__(1024) uint8_t oz_smem[];
     uint8_t* stage_base = oz_smem;
     uint64_t* full = reinterpret_cast<uint64_t*>(oz_smem + Cfg::STAGES * Cfg::STAGE_BYTES);
     uint64_t* empty = full + Cfg::STAGES;
     uint64_t* acc_full = empty + Cfg::STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
     if (tid == 32) {
@@ -585,18 +628,21 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
             umma::mbar_init(empty + i, 1);
         }
         umma::mbar_init(acc_full, 1);
+        umma::mbar_init(acc_empty, 128);
         umma::mbar_fence_init();
     }
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    const int nk = max(kb_hi - kb_lo, 0);
+    const int nchunks = (nk + OG_KCHUNK - 1) / OG_KCHUNK;
     if (warp == 4) {
         if (lane == 0) {
             const uint8_t* a_src = Aop + (int64_t)ptile * kblocks * (S * OZ_A_BYTES);
             const uint8_t* b_src = Bop + (int64_t)(ctile >> 1) * kblocks * (S * OZ_A_BYTES) + (ctile & 1) * OZ_B_BYTES;
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int st = kb % Cfg::STAGES, round = kb / Cfg::STAGES;
+            for (int it = 0; it < nk; ++it) {
+                const int kb = kb_lo + it, st = it % Cfg::STAGES, round = it / Cfg::STAGES;
                 if (round > 0) umma::mbar_wait(empty + st, (uint32_t)(round - 1) & 1u);
                 uint8_t* sA = stage_base + st * Cfg::STAGE_BYTES;
                 uint8_t* sB = sA + S * OZ_A_BYTES;
@@ -610,51 +656,68 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     } else if (warp == 5) {
         if (lane == 0) {
             const uint32_t idesc = umma::idesc_i8(OZ_BM, OZ_BN, 1, 1);  // signed digits
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int st = kb % Cfg::STAGES, round = kb / Cfg::STAGES;
-                umma::mbar_wait(full + st, (uint32_t)round & 1u);
-                umma::tc_fence_after();
-                const uint32_t sA = umma::smem_u32(stage_base + st * Cfg::STAGE_BYTES), sB = sA + S * OZ_A_BYTES;
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    const uint64_t da = umma::smem_desc_kmajor_noswizzle(sA + s * OZ_A_BYTES, 128, 256);
-#pragma unroll
-                    for (int t = 0; t + s < S; ++t) {
-                        const uint64_t db = umma::smem_desc_kmajor_noswizzle(sB + t * OZ_B_BYTES, 128, 256);
-                        umma::mma_i8(tmem + (uint32_t)((s + t) * OZ_BN), da, db, idesc, (kb > 0 || s > 0) ? 1u : 0u);
-                    }
+            for (int kc = 0; kc < nchunks; ++kc) {
+                if (kc > 0) {
+                    umma::mbar_wait(acc_empty, (uint32_t)(kc - 1) & 1u);
+                    umma::tc_fence_after();
                 }
-                umma::mma_commit(empty + st);
+                const int it0 = kc * OG_KCHUNK, it1 = min(nk, it0 + OG_KCHUNK);
+                for (int it = it0; it < it1; ++it) {
+                    const int st = it % Cfg::STAGES, round = it / Cfg::STAGES;
+                    umma::mbar_wait(full + st, (uint32_t)round & 1u);
+                    umma::tc_fence_after();
+                    const uint32_t sA = umma::smem_u32(stage_base + st * Cfg::STAGE_BYTES), sB = sA + S * OZ_A_BYTES;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        const uint64_t da = umma::smem_desc_kmajor_noswizzle(sA + s * OZ_A_BYTES, 128, 256);
+#pragma unroll
+                        for (int t = 0; t + s < S; ++t) {
+                            const uint64_t db = umma::smem_desc_kmajor_noswizzle(sB + t * OZ_B_BYTES, 128, 256);
+                            umma::mma_i8(tmem + (uint32_t)((s + t) * OZ_BN), da, db, idesc, (it > it0 || s > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma::mma_commit(empty + st);
+                }
+                umma::mma_commit(acc_full);
             }
-            umma::mma_commit(acc_full);
         }
     } else {
         const int64_t row = (int64_t)ptile * OZ_BM + tid;
         const double sr = sa[row];
-        umma::mbar_wait(acc_full, 0u);
-        umma::tc_fence_after();
-        for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
-            double v[16];
+        if (nchunks == 0 && mode != 0) {  // empty K range: the product is zero
+            double* dst = C + row * ldc + (int64_t)ctile * OZ_BN;
+            for (int i = 0; i < OZ_BN; ++i) dst[i] = 0.0;
+        }
+        for (int kc = 0; kc < nchunks; ++kc) {
+            umma::mbar_wait(acc_full, (uint32_t)kc & 1u);
+            umma::tc_fence_after();
+            const bool overwrite = (mode != 0) && kc == 0;
+            const double sgn = (mode == 1) ? 1.0 : -1.0;
+            for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+                double v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0.0;
+                for (int i = 0; i < 16; ++i) v[i] = 0.0;
 #pragma unroll
-            for (int g = S - 1; g >= 0; --g) {
-                uint32_t u[16];
-                umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * OZ_BN + c0), u);
-                umma::tmem_ld_wait();
-                const double pw = __longlong_as_double((long long)(1023 - 12 - 8 * g) << 52);  // 2^(-12 - 8g)
+                for (int g = S - 1; g >= 0; --g) {
+                    uint32_t u[16];
+                    umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * OZ_BN + c0), u);
+                    umma::tmem_ld_wait();
+                    const double pw = __longlong_as_double((long long)(1023 - 12 - 8 * g) << 52);  // 2^(-12 - 8g)
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = fma((double)(int)u[i], pw, v[i]);
+                    for (int i = 0; i < 16; ++i) v[i] = fma((double)(int)u[i], pw, v[i]);
+                }
+                double* dst = C + row * ldc + (int64_t)ctile * OZ_BN + c0;
+                const double* cs = sb + (int64_t)ctile * OZ_BN + c0;
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    double2 c = overwrite ? make_double2(0.0, 0.0) : *reinterpret_cast<double2*>(dst + i);
+                    c.x += sgn * (sr * cs[i] * v[i]);
+                    c.y += sgn * (sr * cs[i + 1] * v[i + 1]);
+                    *reinterpret_cast<double2*>(dst + i) = c;
+                }
             }
-            double* dst = C + row * ldc + (int64_t)ctile * OZ_BN + c0;
-            const double* cs = sb + (int64_t)ctile * OZ_BN + c0;
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-                double2 c = *reinterpret_cast<double2*>(dst + i);
-                c.x -= sr * cs[i] * v[i];
-                c.y -= sr * cs[i + 1] * v[i + 1];
-                *reinterpret_cast<double2*>(dst + i) = c;
-            }
+            umma::tc_fence_before();
+            umma::mbar_arrive(acc_empty);
         }
     }
     umma::tc_fence_before();
@@ -678,12 +741,23 @@ int64_t ozaki_operand_bytes(int64_t rows, int64_t K) {
     const int64_t rt = pad_to(rows, OZ_BM) / OZ_BM, kb = pad_to(K, OZ_KB) / OZ_KB;
     return pad_to(rt * kb * OG_S * OZ_A_BYTES, 1024) + pad_to(rt * OZ_BM * 8, 1024);
 }
-int ozaki_slice_operand(const double* P, int64_t rows, int64_t K, int64_t ld, uint8_t* buf, cudaStream_t st) {
+// trans == 0: operand(r, k) = P[r][k];  trans != 0: operand(r, k) = P[k][r].  tri: OzTri mask of the operand.
+int ozaki_slice_operand(const double* P, int64_t rows, int64_t K, int64_t ld, int trans, int tri, uint8_t* buf,
+                        cudaStream_t st) {
     const int64_t rt = pad_to(rows, OZ_BM) / OZ_BM;
     const int kb = (int)(pad_to(K, OZ_KB) / OZ_KB);
     double* scale = reinterpret_cast<double*>(buf + pad_to(rt * kb * OG_S * OZ_A_BYTES, 1024));
-    oz_rowscale_rows_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(P, rows, K, ld, scale);
-    oz_slice_rows_kernel<<<dim3((unsigned)ceil_div(kb, 16), (unsigned)rt), 128, 0, st>>>(P, rows, K, ld, scale, buf, kb);
+    const dim3 gs((unsigned)ceil_div(kb, 16), (unsigned)rt);
+    if (trans) {
+        cudaMemsetAsync(scale, 0, (size_t)rt * OZ_BM * 8, st);
+        oz_colmax_kernel<<<dim3((unsigned)ceil_div(rows, 128), (unsigned)ceil_div(K, 256)), 128, 0, st>>>(
+            P, rows, K, ld, tri, reinterpret_cast<unsigned long long*>(scale));
+        oz_scale_from_max_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, st>>>(scale, rows);
+        oz_slice_rows_kernel<true><<<gs, 128, 0, st>>>(P, rows, K, ld, tri, scale, buf, kb);
+    } else {
+        oz_rowscale_rows_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(P, rows, K, ld, tri, scale);
+        oz_slice_rows_kernel<false><<<gs, 128, 0, st>>>(P, rows, K, ld, tri, scale, buf, kb);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("ozaki_slice_operand: %s", cudaGetErrorString(e));
@@ -691,10 +765,10 @@ int ozaki_slice_operand(const double* P, int64_t rows, int64_t K, int64_t ld, ui
     }
     return SOCKS_OK;
 }
-// C (m x n) -= A B^T from sliced operands (row offsets in units of 128 rows into each operand buffer).
+// C (m x n) (op)= A B^T from sliced operands (tile offsets in units of 128 operand rows); mode 0: -=, 1: =, 2: = -.
 int ozaki_gemm_nt_sliced(const uint8_t* abuf, int64_t a_rows_total, int64_t a_tile0, const uint8_t* bbuf, int64_t b_rows_total,
-                         int64_t b_tile0, int64_t K, double* C, int64_t ldc, int64_t m, int64_t n, int lower_only,
-                         cudaStream_t st) {
+                         int64_t b_tile0, int64_t K, double* C, int64_t ldc, int64_t m, int64_t n, int lower_only, int mode,
+                         int tri_a, int tri_b, cudaStream_t st) {
     int rc = og_configure();
     if (rc) return rc;
     const int kb = (int)(pad_to(K, OZ_KB) / OZ_KB);
@@ -704,7 +778,7 @@ int ozaki_gemm_nt_sliced(const uint8_t* abuf, int64_t a_rows_total, int64_t a_ti
     const uint8_t* aop = abuf + a_tile0 * (int64_t)kb * OG_S * OZ_A_BYTES;
     const uint8_t* bop = bbuf + b_tile0 * (int64_t)kb * OG_S * OZ_A_BYTES;
     oz_gemm_nt_kernel<<<dim3((unsigned)(n / OZ_BN), (unsigned)(m / OZ_BM)), OZ_THREADS, OgCfg::SMEM_BYTES, st>>>(
-        aop, sa, bop, sb, C, ldc, kb, lower_only);
+        aop, sa, bop, sb, C, ldc, kb, lower_only, mode, tri_a, tri_b);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("ozaki_gemm_nt: %s", cudaGetErrorString(e));
@@ -729,13 +803,13 @@ extern "C" int socks_dev_ozaki_gemm_nt(const double* A, int64_t lda, const doubl
     SOCKS_CHECK_ARG(C != nullptr && ldc >= n && ldc % 2 == 0, 5);
     SOCKS_CHECK_ARG(m > 0 && m % 128 == 0, 7);
     SOCKS_CHECK_ARG(n > 0 && n % 128 == 0 && (!syrk || n == m), 8);
-    SOCKS_CHECK_ARG(K > 0 && K % 32 == 0 && K <= 16384, 9);
+    SOCKS_CHECK_ARG(K > 0 && K % 32 == 0, 9);
     SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 1023) == 0, 12);
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* abuf = reinterpret_cast<uint8_t*>(work);
     uint8_t* bbuf = syrk ? abuf : abuf + ozaki_operand_bytes(m, K);
-    int rc = ozaki_slice_operand(A, m, K, lda, abuf, st);
+    int rc = ozaki_slice_operand(A, m, K, lda, 0, 0, abuf, st);
     if (rc) return rc;
-    if (!syrk && (rc = ozaki_slice_operand(B, n, K, ldb, bbuf, st))) return rc;
-    return ozaki_gemm_nt_sliced(abuf, m, 0, bbuf, syrk ? m : n, 0, K, C, ldc, m, n, lower_only, st);
+    if (!syrk && (rc = ozaki_slice_operand(B, n, K, ldb, 0, 0, bbuf, st))) return rc;
+    return ozaki_gemm_nt_sliced(abuf, m, 0, bbuf, syrk ? m : n, 0, K, C, ldc, m, n, lower_only, 0, 0, 0, st);
 }

@@ -185,6 +185,39 @@ def test_potrf_inv_lookahead_matches_recursion_and_numpy(n, nb, keep_l):
     assert np.max(np.abs(w - w0) / w0) <= 100 * cond * 2.0 ** -53
 
 
+@pytest.mark.parametrize("m,n,K,syrk,lower", [(256, 128, 96, False, False), (384, 384, 1024, True, True),
+                                              (128, 192, 16384 + 64, False, False), (256, 64, 32, False, False)])
+def test_ozaki_gemm_is_fp64_accurate(m, n, K, syrk, lower):
+    """C -= A B^T on the integer tensor cores (7 balanced base-256 digits, tcgen05.mma kind::i8; csrc/ozaki.cu) against
+    float64 with operands spanning 12 decades per row; K > 16384 exercises the chunked int32 accumulation."""
+    torch, dv, _lib, mt = _mods()
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(m + n + K)
+    A = torch.randn(m, K, dtype=torch.float64, device="cuda", generator=g)
+    A = A * torch.pow(10.0, torch.empty(m, 1, dtype=torch.float64, device="cuda").uniform_(-6, 6, generator=g))
+    B = A if syrk else torch.randn(n, K, dtype=torch.float64, device="cuda", generator=g)
+    C0 = torch.randn(m, n, dtype=torch.float64, device="cuda", generator=g)
+    C = C0.clone()
+    wk = dv.work(lib.socks_dev_ozaki_gemm_work_bytes(m, n, K) + 2048)
+    base = (wk.data_ptr() + 1023) // 1024 * 1024
+    _lib.call("socks_dev_ozaki_gemm_nt", A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), n, m, n, K, 1 if syrk else 0,
+              1 if lower else 0, base, dv.stream())
+    torch.cuda.synchronize()
+    A_, B_, C0_, C_ = A.cpu().numpy(), B.cpu().numpy(), C0.cpu().numpy(), C.cpu().numpy()
+    ref = C0_ - (A_.astype(np.longdouble) @ B_.T.astype(np.longdouble)).astype(np.float64)
+    # error model of the digit scheme: operands are truncated at 2^-54 of their ROW maximum and digit pairs with
+    # s + t >= 7 are dropped (<= 6 * 2^-54 per sample, worst case), so the bound is relative to K * rowmax(A) * rowmax(B)
+    # (worst case 12 * 2^-53 of it) -- plus the rounding of C itself.  Measured: ~1e-17 of it (signs are random).
+    bound = K * np.abs(A_).max(axis=1)[:, None] * np.abs(B_).max(axis=1)[None, :]
+    err = (np.abs(C_ - ref) - 2.0 ** -53 * np.abs(ref)) / bound
+    if lower:  # only 128 x 64 tiles touching the lower triangle are written
+        i, j = np.indices((m, n))
+        keep = (j // 64) * 64 <= (i // 128) * 128 + 127
+        assert np.array_equal(C_[~keep], C0_[~keep])
+        err = err[keep]
+    assert err.max() < 2.0 ** -53
+
+
 def test_not_positive_definite_reports():
     torch, dv, _lib, mt = _mods()
     n = 130
