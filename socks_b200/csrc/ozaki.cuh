@@ -17,4 +17,7 @@ int ozaki_gemm_nt_sliced(const uint8_t* abuf, int64_t a_rows_total, int64_t a_ti
                          int64_t b_tile0, int64_t K, double* C, int64_t ldc, int64_t m, int64_t n, int lower_only, int mode,
                          int tri_a, int tri_b, cudaStream_t st);
 
+// 1: persistent launch (one CTA per SM), 0: one CTA per tile
+extern int g_og_persistent;
+
 }  // namespace socks
