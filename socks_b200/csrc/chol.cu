@@ -768,8 +768,7 @@ extern "C" int socks_potrf_inv_set_block(int nb) {
                    // -5 / -6: large merges of the inverse on FP64 DMMA / on the integer tensor cores
         if (nb >= -2) g_potrf_tail = (nb == -2);
         else if (nb >= -4) g_potrf_ozaki = (nb == -4);
-        else if (nb >= -6) g_potrf_ozaki_merge = (nb == -6);
-        else g_og_persistent = (nb == -8);  // -7 / -8: integer GEMM launched one CTA per tile / persistent
+        else g_potrf_ozaki_merge = (nb == -6);
         return old;
     }
     if (nb % LF == 0) g_potrf_nb = nb;

@@ -593,224 +593,219 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// Tile = 128 x 128 of C, computed in TWO passes over K.  The seven digit groups g = s + t need one int32 accumulator each,
+// and 7 x 128 columns do not fit the 512 columns of tensor memory; 7 x 64 would, but a 128 x 64 x 32 MMA is bound by the
+// shared-memory reads of its operands (48 clocks for 32 clocks of math; tools/probes/umma_rate.cu), while 128 x 128 x 32
+// runs at the full rate.  So pass A accumulates groups 0..3 (10 MMAs per K-block, digit slices 0..3 of both operands) and
+// pass B groups 4..6 (18 MMAs, all slices); each pass ends in its own epilogue.  Both passes are bound by L2 -> SM
+// traffic at ~45 B/clk/SM (tools/probes/umma_pipe.cu): 88 KB per K-block and tile.
 struct OgCfg {
-    static constexpr int STAGE_BYTES = OG_S * (OZ_A_BYTES + OZ_B_BYTES);
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (2 * STAGES + 2) * 8 + 16;
+    static constexpr int BN = 128;
+    static constexpr int SLICE = OZ_A_BYTES;                        // 128 rows x 32 B of one digit
+    static constexpr int NS_A = 4, NS_B = OG_S;                     // digit slices a pass needs
+    static constexpr int STAGE_A = 2 * NS_A * SLICE, STAGES_A = 5;  // 32 KB x 5
+    static constexpr int STAGE_B = 2 * NS_B * SLICE, STAGES_B = 3;  // 56 KB x 3
+    static constexpr int RING_BYTES = STAGES_B * STAGE_B;           // 168 KB (>= STAGES_A * STAGE_A)
+    static constexpr int NBAR = 2 * (STAGES_A + STAGES_B) + 3;
+    static constexpr int SMEM_BYTES = RING_BYTES + NBAR * 8 + 16;
 };
+static_assert(OgCfg::STAGES_A * OgCfg::STAGE_A <= OgCfg::RING_BYTES, "pass A ring must fit");
 
-// C[m0 + i][n0 + j] (op)= sa[i] sb[j] sum_g 2^(-12 - 8g) G_g[i][j];  CTA = 128 rows x 64 columns; the B-side operand is
-// the `half`-th 64-row half of 128-row tile n0/128 of Bop.  mode: 0 C -= AB^T, 1 C = AB^T, 2 C = -AB^T.
-// tri_a / tri_b clip the K range per tile exactly like GEMM_A_K_LE_M / GEMM_B_K_GE_N of gemm_f64.cuh.  int32 stays exact
-// for OG_KCHUNK K-blocks; longer products are accumulated chunk by chunk in fp64 through C.
+// int32 stays exact for OG_KCHUNK K-blocks; longer products hand the accumulators over chunk by chunk (fp64 sum in C).
 constexpr int OG_KCHUNK = 512;  // 16 384 samples: 7 * 16384 * 2^14 < 2^31
 
-// Persistent: one CTA per SM walks the tile list (heaviest row tiles first), so tensor memory and the barriers are set
-// up once and the loader runs ahead into the next tile while the epilogue of the current one drains the accumulators.
 // exact int64 -> double for |x| < 2^51 (one integer add, one DADD; I2F.F64 is several times slower)
 __device__ __forceinline__ double og_i2d(long long x) {
     return __longlong_as_double(x + 0x4338000000000000LL) - 0x1.8p52;
 }
 
-struct OgTile {
-    int ptile, ctile, kb_lo, nk;
-};
-// Walks the VALID tiles (lower_only drops 128 x 64 tiles above the block diagonal) in steps of gridDim.x, row tiles in
-// descending order; every role of the CTA runs its own copy and sees the same sequence.
-struct OgWalk {
-    int nx, ny, lower_only, row, off;
-    __device__ __forceinline__ int rowlen(int r) const { return lower_only ? min(nx, 2 * r + 2) : nx; }
-    __device__ __forceinline__ OgWalk(int nx_, int ny_, int lower_) : nx(nx_), ny(ny_), lower_only(lower_) {
-        row = ny - 1;
-        off = (int)blockIdx.x;
-        settle();
-    }
-    __device__ __forceinline__ void settle() {
-        while (row >= 0 && off >= rowlen(row)) off -= rowlen(row--);
-    }
-    __device__ __forceinline__ bool done() const { return row < 0; }
-    __device__ __forceinline__ void next() {
-        off += (int)gridDim.x;
-        settle();
-    }
-    __device__ __forceinline__ OgTile tile(int kblocks, int tri_a, int tri_b) const {
-        OgTile o;
-        o.ptile = row;
-        o.ctile = off;
-        int kb_lo = 0, kb_hi = kblocks;
-        if (tri_a) kb_hi = min(kb_hi, (o.ptile + 1) * (OZ_BM / OZ_KB));              // A(i, k) = 0 for k beyond row tile i
-        if (tri_b) kb_lo = max(kb_lo, ((o.ctile * OZ_BN) / OZ_BM) * (OZ_BM / OZ_KB));  // B(k, j) = 0 for k before column tile j
-        o.kb_lo = kb_lo;
-        o.nk = max(kb_hi - kb_lo, 0);
-        return o;
-    }
-};
-
+// C[128 ptile + i][128 ctile + j] (op)= sa[i] sb[j] sum_g 2^(-12 - 8g) G_g[i][j];  mode: 0 C -= AB^T, 1 C = AB^T,
+// 2 C = -AB^T.  tri_a / tri_b clip the K range per tile exactly like GEMM_A_K_LE_M / GEMM_B_K_GE_N of gemm_f64.cuh.
+// Warps 0-3: epilogue (thread = row), warp 4: loader (bulk copies), warp 5: MMA issue.
 __global__ void __launch_bounds__(OZ_THREADS, 1)
     oz_gemm_nt_kernel(const uint8_t* __restrict__ Aop, const double* __restrict__ sa, const uint8_t* __restrict__ Bop,
                       const double* __restrict__ sb, double* __restrict__ C, int64_t ldc, int kblocks, int lower_only,
-                      int mode, int tri_a, int tri_b, int nx, int ny) {
-    constexpr int S = OG_S;
+                      int mode, int tri_a, int tri_b) {
     using Cfg = OgCfg;
+    constexpr int S = OG_S, SL = Cfg::SLICE, BN = Cfg::BN;
+    const int ctile = blockIdx.x, ptile = blockIdx.y;
+    if (lower_only && ctile > ptile) return;
+    int kb_lo = 0, kb_hi = kblocks;
+    if (tri_a) kb_hi = min(kb_hi, (ptile + 1) * (OZ_BM / OZ_KB));  // A(i, k) = 0 for k beyond row tile i
+    if (tri_b) kb_lo = max(kb_lo, ctile * (BN / OZ_KB));           // B(k, j) = 0 for k before column tile j
+    const int nk = max(kb_hi - kb_lo, 0);
+    const int nchunks = (nk + OG_KCHUNK - 1) / OG_KCHUNK;
     extern __shared__ __align__(1024) uint8_t oz_smem[];
-    uint8_t* stage_base = oz_smem;
-    uint64_t* full = reinterpret_cast<uint64_t*>(oz_smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-    uint64_t* empty = full + Cfg::STAGES;
-    uint64_t* acc_full = empty + Cfg::STAGES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem + Cfg::RING_BYTES);
+    uint64_t* full_a = bars;
+    uint64_t* empty_a = full_a + Cfg::STAGES_A;
+    uint64_t* full_b = empty_a + Cfg::STAGES_A;
+    uint64_t* empty_b = full_b + Cfg::STAGES_B;
+    uint64_t* acc_full = empty_b + Cfg::STAGES_B;
     uint64_t* acc_empty = acc_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
-    __shared__ double col_scale[OZ_BN];
+    uint64_t* ring_free = acc_empty + 1;  // all MMAs of pass A have read their stages: pass B may overwrite the ring
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
+    __shared__ double col_scale[BN];
+    __shared__ double turn[4 * 32 * 17];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (nk == 0) {  // empty K range: the product is zero
+        if (mode != 0 && tid < OZ_BM) {
+            double* crow = C + ((int64_t)ptile * OZ_BM + tid) * ldc + (int64_t)ctile * BN;
+            for (int i = 0; i < BN; ++i) crow[i] = 0.0;
+        }
+        return;
+    }
     if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
     if (tid == 32) {
-        for (int i = 0; i < Cfg::STAGES; ++i) {
-            umma::mbar_init(full + i, 1);
-            umma::mbar_init(empty + i, 1);
-        }
+        for (int i = 0; i < 2 * (Cfg::STAGES_A + Cfg::STAGES_B); ++i) umma::mbar_init(bars + i, 1);
         umma::mbar_init(acc_full, 1);
         umma::mbar_init(acc_empty, 128);
+        umma::mbar_init(ring_free, 1);
         umma::mbar_fence_init();
     }
+    if (tid < BN) col_scale[tid] = sb[(int64_t)ctile * BN + tid];
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     if (warp == 4) {
         if (lane == 0) {
-            uint32_t it = 0;  // stage uses so far, across tiles
-            for (OgWalk w(nx, ny, lower_only); !w.done(); w.next()) {
-                const OgTile o = w.tile(kblocks, tri_a, tri_b);
-                const uint8_t* a_src = Aop + (int64_t)o.ptile * kblocks * (S * OZ_A_BYTES);
-                const uint8_t* b_src =
-                    Bop + (int64_t)(o.ctile >> 1) * kblocks * (S * OZ_A_BYTES) + (o.ctile & 1) * OZ_B_BYTES;
-                for (int i = 0; i < o.nk; ++i, ++it) {
-                    const int kb = o.kb_lo + i;
-                    const uint32_t st = it % Cfg::STAGES, round = it / Cfg::STAGES;
-                    if (round > 0) umma::mbar_wait(empty + st, (round - 1) & 1u);
-                    uint8_t* sA = stage_base + st * Cfg::STAGE_BYTES;
-                    uint8_t* sB = sA + S * OZ_A_BYTES;
-                    umma::mbar_arrive_expect_tx(full + st, Cfg::STAGE_BYTES);
-                    umma::bulk_g2s(sA, a_src + (int64_t)kb * (S * OZ_A_BYTES), S * OZ_A_BYTES, full + st);
-#pragma unroll
-                    for (int d = 0; d < S; ++d)  // the 64-row half of each 128-row digit block
-                        umma::bulk_g2s(sB + d * OZ_B_BYTES, b_src + ((int64_t)kb * S + d) * OZ_A_BYTES, OZ_B_BYTES, full + st);
-                }
+            const uint8_t* a_src = Aop + ((int64_t)ptile * kblocks + kb_lo) * (S * SL);
+            const uint8_t* b_src = Bop + ((int64_t)ctile * kblocks + kb_lo) * (S * SL);
+            for (int i = 0; i < nk; ++i) {  // pass A: slices 0..3
+                const int st = i % Cfg::STAGES_A, round = i / Cfg::STAGES_A;
+                if (round > 0) umma::mbar_wait(empty_a + st, (uint32_t)(round - 1) & 1u);
+                uint8_t* dst = oz_smem + st * Cfg::STAGE_A;
+                umma::mbar_arrive_expect_tx(full_a + st, Cfg::STAGE_A);
+                umma::bulk_g2s(dst, a_src + (int64_t)i * (S * SL), Cfg::NS_A * SL, full_a + st);
+                umma::bulk_g2s(dst + Cfg::NS_A * SL, b_src + (int64_t)i * (S * SL), Cfg::NS_A * SL, full_a + st);
+            }
+            umma::mbar_wait(ring_free, 0);
+            for (int i = 0; i < nk; ++i) {  // pass B: all slices
+                const int st = i % Cfg::STAGES_B, round = i / Cfg::STAGES_B;
+                if (round > 0) umma::mbar_wait(empty_b + st, (uint32_t)(round - 1) & 1u);
+                uint8_t* dst = oz_smem + st * Cfg::STAGE_B;
+                umma::mbar_arrive_expect_tx(full_b + st, Cfg::STAGE_B);
+                umma::bulk_g2s(dst, a_src + (int64_t)i * (S * SL), S * SL, full_b + st);
+                umma::bulk_g2s(dst + S * SL, b_src + (int64_t)i * (S * SL), S * SL, full_b + st);
             }
         }
     } else if (warp == 5) {
         if (lane == 0) {
-            const uint32_t idesc = umma::idesc_i8(OZ_BM, OZ_BN, 1, 1);  // signed digits
-            uint32_t it = 0, cc = 0;                                    // stage uses / accumulator hand-overs so far
-            for (OgWalk w(nx, ny, lower_only); !w.done(); w.next()) {
-                const OgTile o = w.tile(kblocks, tri_a, tri_b);
-                for (int i0 = 0; i0 < o.nk; i0 += OG_KCHUNK, ++cc) {
-                    if (cc > 0) {
-                        umma::mbar_wait(acc_empty, (cc - 1) & 1u);
-                        umma::tc_fence_after();
-                    }
-                    const int i1 = min(o.nk, i0 + OG_KCHUNK);
-                    for (int i = i0; i < i1; ++i, ++it) {
-                        const uint32_t st = it % Cfg::STAGES, round = it / Cfg::STAGES;
-                        umma::mbar_wait(full + st, round & 1u);
-                        umma::tc_fence_after();
-                        const uint32_t sA = umma::smem_u32(stage_base + st * Cfg::STAGE_BYTES), sB = sA + S * OZ_A_BYTES;
-#pragma unroll
-                        for (int a = 0; a < S; ++a) {
-                            const uint64_t da = umma::smem_desc_kmajor_noswizzle(sA + a * OZ_A_BYTES, 128, 256);
-#pragma unroll
-                            for (int b = 0; b + a < S; ++b) {
-                                const uint64_t db = umma::smem_desc_kmajor_noswizzle(sB + b * OZ_B_BYTES, 128, 256);
-                                umma::mma_i8(tmem + (uint32_t)((a + b) * OZ_BN), da, db, idesc, (i > i0 || a > 0) ? 1u : 0u);
-                            }
-                        }
-                        umma::mma_commit(empty + st);
-                    }
-                    umma::mma_commit(acc_full);
+            const uint32_t idesc = umma::idesc_i8(OZ_BM, BN, 1, 1);  // signed digits
+            uint32_t seg = 0;                                        // accumulator hand-overs so far
+            for (int i0 = 0; i0 < nk; i0 += OG_KCHUNK, ++seg) {      // pass A: groups 0..3 -> columns 128 g
+                if (seg > 0) {
+                    umma::mbar_wait(acc_empty, (seg - 1) & 1u);
+                    umma::tc_fence_after();
                 }
+                const int i1 = min(nk, i0 + OG_KCHUNK);
+                for (int i = i0; i < i1; ++i) {
+                    const int st = i % Cfg::STAGES_A, round = i / Cfg::STAGES_A;
+                    umma::mbar_wait(full_a + st, (uint32_t)round & 1u);
+                    umma::tc_fence_after();
+                    const uint32_t sA = umma::smem_u32(oz_smem + st * Cfg::STAGE_A), sB = sA + Cfg::NS_A * SL;
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const uint64_t da = umma::smem_desc_kmajor_noswizzle(sA + a * SL, 128, 256);
+#pragma unroll
+                        for (int b = 0; a + b < 4; ++b)
+                            umma::mma_i8(tmem + (uint32_t)((a + b) * BN), da,
+                                         umma::smem_desc_kmajor_noswizzle(sB + b * SL, 128, 256), idesc,
+                                         (i > i0 || a > 0) ? 1u : 0u);
+                    }
+                    umma::mma_commit(empty_a + st);
+                }
+                if (i1 == nk) umma::mma_commit(ring_free);
+                umma::mma_commit(acc_full);
+            }
+            for (int i0 = 0; i0 < nk; i0 += OG_KCHUNK, ++seg) {  // pass B: groups 4..6 -> columns 128 (g - 4)
+                umma::mbar_wait(acc_empty, (seg - 1) & 1u);
+                umma::tc_fence_after();
+                const int i1 = min(nk, i0 + OG_KCHUNK);
+                for (int i = i0; i < i1; ++i) {
+                    const int st = i % Cfg::STAGES_B, round = i / Cfg::STAGES_B;
+                    umma::mbar_wait(full_b + st, (uint32_t)round & 1u);
+                    umma::tc_fence_after();
+                    const uint32_t sA = umma::smem_u32(oz_smem + st * Cfg::STAGE_B), sB = sA + S * SL;
+#pragma unroll
+                    for (int a = 0; a < S; ++a) {
+                        const uint64_t da = umma::smem_desc_kmajor_noswizzle(sA + a * SL, 128, 256);
+#pragma unroll
+                        for (int b = 0; b < S; ++b)
+                            if (a + b >= 4 && a + b < S)
+                                umma::mma_i8(tmem + (uint32_t)((a + b - 4) * BN), da,
+                                             umma::smem_desc_kmajor_noswizzle(sB + b * SL, 128, 256), idesc,
+                                             (i > i0 || a > 0) ? 1u : 0u);
+                    }
+                    umma::mma_commit(empty_b + st);
+                }
+                umma::mma_commit(acc_full);
             }
         }
     } else {
-        uint32_t cc = 0;
-        const double sgn = (mode == 1) ? 1.0 : -1.0;
-        for (OgWalk w(nx, ny, lower_only); !w.done(); w.next()) {
-            const OgTile o = w.tile(kblocks, tri_a, tri_b);
-            const int64_t row = (int64_t)o.ptile * OZ_BM + tid;
-            double* crow = C + row * ldc + (int64_t)o.ctile * OZ_BN;
-            const double sr = sgn * sa[row];
-            if (o.nk == 0) {  // empty K range: the product is zero
-                if (mode != 0)
-                    for (int i = 0; i < OZ_BN; ++i) crow[i] = 0.0;
-                continue;
-            }
-            if (mode == 0) {  // pull this thread's 512 bytes of C towards the SM while the tensor cores work
+        const int64_t row = (int64_t)ptile * OZ_BM + tid;
+        double* crow = C + row * ldc + (int64_t)ctile * BN;
+        const double sr = ((mode == 1) ? 1.0 : -1.0) * sa[row];
+        if (mode == 0) {  // pull this thread's 1 KB of C towards the SM while the tensor cores work
 #pragma unroll
-                for (int i = 0; i < OZ_BN; i += 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(crow + i));
-            }
-            // column scales of this tile -> shared memory (the previous tile's epilogue has passed its last read)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (tid < OZ_BN) col_scale[tid] = sb[(int64_t)o.ctile * OZ_BN + tid];
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int i0 = 0; i0 < o.nk; i0 += OG_KCHUNK, ++cc) {
-                const bool overwrite = (mode != 0) && i0 == 0;
-                umma::mbar_wait(acc_full, cc & 1u);
-                umma::tc_fence_after();
+            for (int i = 0; i < BN; i += 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(crow + i));
+        }
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        double* tb = turn + warp * (32 * 17);
+        double* cwarp = C + ((int64_t)ptile * OZ_BM + warp * 32) * ldc + (int64_t)ctile * BN;
+        for (uint32_t seg = 0; seg < 2u * (uint32_t)nchunks; ++seg) {
+            const bool pass_b = seg >= (uint32_t)nchunks;
+            const bool overwrite = (mode != 0) && seg == 0;
+            umma::mbar_wait(acc_full, seg & 1u);
+            umma::tc_fence_after();
 #pragma unroll 1
-                for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
-                    double2 cv[8];
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                // sum_g 2^(-12 - 8g) G_g over the pass's groups, merged in exact 64-bit integer arithmetic first
+                // (|G_g| <= (g + 1) K 2^14 and |G_0| <= K 2^12: every partial stays below 2^49) and converted once
+                double v[16];
+                if (!pass_b) {
+                    uint32_t u[4][16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        cv[i] = overwrite ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(crow + c0 + 2 * i);
-                    uint32_t u[S][16];
-#pragma unroll
-                    for (int g = 0; g < S; ++g)
-                        umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * OZ_BN + c0), u[g]);
+                    for (int g = 0; g < 4; ++g) umma::tmem_ld16(trow + (uint32_t)(g * BN + c0), u[g]);
                     umma::tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        // sum_g 2^(-12 - 8g) G_g, the groups merged three at a time in exact 64-bit integer arithmetic
-                        // (|G| < 2^31, so each partial is below 2^48) and converted with the 2^52 trick
-                        const long long hi = ((long long)(int)u[0][i] << 16) + ((long long)(int)u[1][i] << 8) + (int)u[2][i];
-                        const long long mid = ((long long)(int)u[3][i] << 16) + ((long long)(int)u[4][i] << 8) + (int)u[5][i];
-                        const long long lo = (int)u[6][i];
-                        double v = og_i2d(lo) * 0x1p-60;
-                        v = fma(og_i2d(mid), 0x1p-52, v);
-                        v = fma(og_i2d(hi), 0x1p-28, v);
-                        const double add = sr * col_scale[c0 + i] * v;
-                        if (i & 1) cv[i >> 1].y += add;
-                        else cv[i >> 1].x += add;
+                        const long long hi = ((long long)(int)u[0][i] << 8) + (int)u[1][i];
+                        const long long lo = ((long long)(int)u[2][i] << 8) + (int)u[3][i];
+                        v[i] = fma(og_i2d(hi), 0x1p-20, og_i2d(lo) * 0x1p-36);
                     }
+                } else {
+                    uint32_t u[3][16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) *reinterpret_cast<double2*>(crow + c0 + 2 * i) = cv[i];
+                    for (int g = 0; g < 3; ++g) umma::tmem_ld16(trow + (uint32_t)(g * BN + c0), u[g]);
+                    umma::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        v[i] = og_i2d(((long long)(int)u[0][i] << 16) + ((long long)(int)u[1][i] << 8) + (int)u[2][i]) * 0x1p-60;
                 }
-                umma::tc_fence_before();
-                umma::mbar_arrive(acc_empty);
+                // tensor memory hands a thread one ROW; C wants 128 contiguous bytes per row and instruction, so the
+                // 32 x 16 block of the warp is turned through shared memory (two rows of 16 doubles per instruction)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) tb[lane * 17 + i] = sr * col_scale[c0 + i] * v[i];
+                __syncwarp();
+                double* cbase = cwarp + c0 + (lane & 15);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int r = 2 * k + (lane >> 4);
+                    double* cp = cbase + (int64_t)r * ldc;
+                    const double add = tb[r * 17 + (lane & 15)];
+                    *cp = overwrite ? add : (*cp + add);
+                }
+                __syncwarp();
             }
+            umma::tc_fence_before();
+            umma::mbar_arrive(acc_empty);
         }
     }
     umma::tc_fence_before();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, 512);
-}
-
-static int sm_count() {
-    static std::atomic<int> cached[SOCKS_MAX_DEVICES];
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= SOCKS_MAX_DEVICES) return 148;
-    int n = cached[dev].load(std::memory_order_relaxed);
-    if (n == 0) {
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        cached[dev].store(n, std::memory_order_relaxed);
-    }
-    return n;
-}
-
-// Default: one CTA per tile.  Inside socks_potrf_inv the high-priority panel stream needs SMs to free up every few tens of
-// microseconds; a persistent launch holds all of them until the update is over (measured: 100.7 vs 95.8 ms at N = 20k).
-int g_og_persistent = 0;
-static int64_t og_lower_tiles(int nx, int ny) {
-    int64_t t = 0;
-    for (int r = 0; r < ny; ++r) t += std::min(nx, 2 * r + 2);
-    return t;
 }
 
 static int og_configure() {
@@ -865,12 +860,8 @@ int ozaki_gemm_nt_sliced(const uint8_t* abuf, int64_t a_rows_total, int64_t a_ti
     const double* sb = reinterpret_cast<const double*>(bbuf + pad_to(brt * kb * OG_S * OZ_A_BYTES, 1024)) + b_tile0 * OZ_BM;
     const uint8_t* aop = abuf + a_tile0 * (int64_t)kb * OG_S * OZ_A_BYTES;
     const uint8_t* bop = bbuf + b_tile0 * (int64_t)kb * OG_S * OZ_A_BYTES;
-    const int nx = (int)(n / OZ_BN), ny = (int)(m / OZ_BM);
-    // persistent (one CTA per SM walking the tile list) or one CTA per tile (the hardware scheduler balances the load)
-    const int64_t tiles = lower_only ? og_lower_tiles(nx, ny) : (int64_t)nx * ny;
-    const int ctas = (int)(g_og_persistent ? std::min<int64_t>(tiles, sm_count()) : tiles);
-    oz_gemm_nt_kernel<<<ctas, OZ_THREADS, OgCfg::SMEM_BYTES, st>>>(aop, sa, bop, sb, C, ldc, kb, lower_only, mode, tri_a,
-                                                                   tri_b, nx, ny);
+    oz_gemm_nt_kernel<<<dim3((unsigned)(n / OgCfg::BN), (unsigned)(m / OZ_BM)), OZ_THREADS, OgCfg::SMEM_BYTES, st>>>(
+        aop, sa, bop, sb, C, ldc, kb, lower_only, mode, tri_a, tri_b);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("ozaki_gemm_nt: %s", cudaGetErrorString(e));

@@ -23,9 +23,7 @@ if what == "sweep":
     mt.Factorization(dv.to_dev(X[:3000]), (-50.0, 0), 1.0 / 3000)  # warm-up: module load, smem attributes, streams
     out = []
     for nb in [int(a) for a in sys.argv[3].split(",")] if len(sys.argv) > 3 else (0, 512, 1024, 1536, 2048):
-        tail, ozaki, ozmerge, persistent = 1, 1, 1, 0
-        if nb >= 800000:  # e.g. 801024: block 1024, integer GEMM launched persistently instead of one CTA per tile
-            persistent, nb = 1, nb - 800000
+        tail, ozaki, ozmerge = 1, 1, 1
         if nb >= 400000:  # e.g. 401024: block 1024, integer trailing updates but FP64 DMMA merges
             ozmerge, nb = 0, nb - 400000
         if nb >= 200000:  # e.g. 201024: block 1024 with FP64 DMMA trailing updates
@@ -34,7 +32,6 @@ if what == "sweep":
             tail, nb = 0, nb - 100000
         lib.socks_potrf_inv_set_block(-4 if ozaki else -3)
         lib.socks_potrf_inv_set_block(-6 if ozmerge else -5)
-        lib.socks_potrf_inv_set_block(-8 if persistent else -7)
         lib.socks_potrf_inv_set_block(-2 if tail else -1)
         old = lib.socks_potrf_inv_set_block(nb)
         ts = []
@@ -51,11 +48,9 @@ if what == "sweep":
         lib.socks_potrf_inv_set_block(-2)
         lib.socks_potrf_inv_set_block(-4)
         lib.socks_potrf_inv_set_block(-6)
-        lib.socks_potrf_inv_set_block(-7)
         rec = {"N": n, "block": nb, "half_width_tail": bool(tail),
                "trailing_updates": "int8 tensor cores (Ozaki)" if ozaki else "FP64 DMMA",
-               "large_merges": "int8 tensor cores (Ozaki)" if (ozaki and ozmerge) else "FP64 DMMA",
-               "integer_gemm_launch": "persistent" if persistent else "one CTA per tile", "potrf_inv_s": t, "tflops": 2 * npad ** 3 / 3 / t / 1e12, "all_s": ts}
+               "large_merges": "int8 tensor cores (Ozaki)" if (ozaki and ozmerge) else "FP64 DMMA", "potrf_inv_s": t, "tflops": 2 * npad ** 3 / 3 / t / 1e12, "all_s": ts}
         print(json.dumps(rec), flush=True)
         out.append(rec)
     if len(sys.argv) > 4:
