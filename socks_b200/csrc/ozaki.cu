@@ -754,15 +754,35 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
         double* tb = turn + warp * (32 * 17);
         double* cwarp = C + ((int64_t)ptile * OZ_BM + warp * 32) * ldc + (int64_t)ctile * BN;
+        double nxt[16];
+        if (mode == 0) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) nxt[k] = __ldcg(cwarp + (lane & 15) + (int64_t)(2 * k + (lane >> 4)) * ldc);
+        }
         for (uint32_t seg = 0; seg < 2u * (uint32_t)nchunks; ++seg) {
             const bool pass_b = seg >= (uint32_t)nchunks;
             const bool overwrite = (mode != 0) && seg == 0;
+            const bool last_seg = seg + 1 == 2u * (uint32_t)nchunks;
             umma::mbar_wait(acc_full, seg & 1u);
             umma::tc_fence_after();
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 16) {
                 // sum_g 2^(-12 - 8g) G_g over the pass's groups, merged in exact 64-bit integer arithmetic first
                 // (|G_g| <= (g + 1) K 2^14 and |G_0| <= K 2^12: every partial stays below 2^49) and converted once
+                // this chunk's C values were requested one chunk ago (or before the pass); request the next ones now, so
+                // that their latency hides behind the tensor-memory reads and the arithmetic of this chunk.  A lane only
+                // ever reads elements it wrote itself, so a request may run ahead into the next pass.
+                double cur[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) cur[k] = overwrite ? 0.0 : nxt[k];
+                {
+                    const int cn = (c0 + 16) & (BN - 1);
+                    if (c0 + 16 < BN ? !overwrite : !last_seg) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k)
+                            nxt[k] = __ldcg(cwarp + cn + (lane & 15) + (int64_t)(2 * k + (lane >> 4)) * ldc);
+                    }
+                }
                 double v[16];
                 if (!pass_b) {
                     uint32_t u[4][16];
@@ -793,9 +813,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const int r = 2 * k + (lane >> 4);
-                    double* cp = cbase + (int64_t)r * ldc;
-                    const double add = tb[r * 17 + (lane & 15)];
-                    *cp = overwrite ? add : (*cp + add);
+                    cbase[(int64_t)r * ldc] = cur[k] + tb[r * 17 + (lane & 15)];
                 }
                 __syncwarp();
             }
