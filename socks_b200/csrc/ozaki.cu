@@ -106,17 +106,9 @@ extern "C" int socks_dev_i8gemm_check(const void* A, const void* B, void* C, int
 // Points whose normaliser is too small for the fixed-point operand (far from every sample) are listed for the FP64 path.
 namespace socks {
 
-constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KB = 32;
-constexpr int OZ_A_BYTES = OZ_BM * OZ_KB, OZ_B_BYTES = OZ_BN * OZ_KB;
-constexpr int OZ_KCHUNK = 256;  // K-blocks per int32 accumulation chunk
+constexpr int OZ_BM = 128, OZ_KB = 32;
+constexpr int OZ_A_BYTES = OZ_BM * OZ_KB;  // one digit of a 128-row tile, one K-block
 constexpr int OZ_THREADS = 192;
-
-template <int S>
-struct OzCfg {
-    static constexpr int STAGE_BYTES = S * (OZ_A_BYTES + OZ_B_BYTES);
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (2 * STAGES + 2) * 8 + 16;
-};
 
 template <int S>
 __device__ __forceinline__ void oz_digits(double v01, uint32_t (&dig)[S]) {
@@ -127,113 +119,6 @@ __device__ __forceinline__ void oz_digits(double v01, uint32_t (&dig)[S]) {
         const unsigned d = (unsigned)(q >> (7 * (S - 1 - s)));
         dig[s] = (s == 0) ? (d & 0xFFu) : (d & 0x7Fu);
     }
-}
-
-template <int S>
-__global__ void __launch_bounds__(OZ_THREADS, 1)
-    srmax_ozaki_kernel(const uint8_t* __restrict__ Aop, const uint8_t* __restrict__ Bop, double* __restrict__ Cm, int64_t ldc,
-                       int kblocks, const double* __restrict__ colscale) {
-    using Cfg = OzCfg<S>;
-    extern __shared__ __align__(1024) uint8_t oz_smem[];
-    uint8_t* stage_base = oz_smem;
-    uint64_t* full = reinterpret_cast<uint64_t*>(oz_smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-    uint64_t* empty = full + Cfg::STAGES;
-    uint64_t* acc_full = empty + Cfg::STAGES;
-    uint64_t* acc_empty = acc_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ctile = blockIdx.x, ptile = blockIdx.y;
-    if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
-    if (tid == 32) {
-        for (int i = 0; i < Cfg::STAGES; ++i) {
-            umma::mbar_init(full + i, 1);
-            umma::mbar_init(empty + i, 1);
-        }
-        umma::mbar_init(acc_full, 1);
-        umma::mbar_init(acc_empty, 128);
-        umma::mbar_fence_init();
-    }
-    umma::tc_fence_before();
-    __syncthreads();
-    umma::tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    const int nchunks = (kblocks + OZ_KCHUNK - 1) / OZ_KCHUNK;
-
-    if (warp == 4) {
-        if (lane == 0) {  // ---- loader: one stage = S slices of A (128 x 32 B) + S slices of B (64 x 32 B)
-            const uint8_t* a_src = Aop + (int64_t)ptile * kblocks * (S * OZ_A_BYTES);
-            const uint8_t* b_src = Bop + (int64_t)ctile * kblocks * (S * OZ_B_BYTES);
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int st = kb % Cfg::STAGES, round = kb / Cfg::STAGES;
-                if (round > 0) umma::mbar_wait(empty + st, (uint32_t)(round - 1) & 1u);
-                uint8_t* sa = stage_base + st * Cfg::STAGE_BYTES;
-                umma::mbar_arrive_expect_tx(full + st, Cfg::STAGE_BYTES);
-                umma::bulk_g2s(sa, a_src + (int64_t)kb * (S * OZ_A_BYTES), S * OZ_A_BYTES, full + st);
-                umma::bulk_g2s(sa + S * OZ_A_BYTES, b_src + (int64_t)kb * (S * OZ_B_BYTES), S * OZ_B_BYTES, full + st);
-            }
-        }
-    } else if (warp == 5) {
-        if (lane == 0) {  // ---- MMA issuer
-            const uint32_t idesc = umma::idesc_i8(OZ_BM, OZ_BN, 0, 0);  // unsigned digits
-            for (int kc = 0; kc < nchunks; ++kc) {
-                if (kc > 0) {
-                    umma::mbar_wait(acc_empty, (uint32_t)(kc - 1) & 1u);
-                    umma::tc_fence_after();
-                }
-                const int kb0 = kc * OZ_KCHUNK, kb1 = min(kblocks, kb0 + OZ_KCHUNK);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    const int st = kb % Cfg::STAGES, round = kb / Cfg::STAGES;
-                    umma::mbar_wait(full + st, (uint32_t)round & 1u);
-                    umma::tc_fence_after();
-                    const uint32_t sa = umma::smem_u32(stage_base + st * Cfg::STAGE_BYTES), sb = sa + S * OZ_A_BYTES;
-#pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        const uint64_t da = umma::smem_desc_kmajor_noswizzle(sa + s * OZ_A_BYTES, 128, 256);
-#pragma unroll
-                        for (int t = 0; t + s < S; ++t) {
-                            const uint64_t db = umma::smem_desc_kmajor_noswizzle(sb + t * OZ_B_BYTES, 128, 256);
-                            // s = 0 touches every group first: it overwrites at the start of an accumulation chunk
-                            umma::mma_i8(tmem + (uint32_t)((s + t) * OZ_BN), da, db, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
-                        }
-                    }
-                    umma::mma_commit(empty + st);  // the stage is free once these MMAs have read it
-                }
-                umma::mma_commit(acc_full);
-            }
-        }
-    } else {  // ---- epilogue: thread = point row; int32 groups -> fp64, recombine, scale, store / accumulate
-        const int64_t row = (int64_t)ptile * OZ_BM + tid;
-        for (int kc = 0; kc < nchunks; ++kc) {
-            umma::mbar_wait(acc_full, (uint32_t)kc & 1u);
-            umma::tc_fence_after();
-            for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
-                double v[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = 0.0;
-#pragma unroll
-                for (int g = S - 1; g >= 0; --g) {  // smallest weights first
-                    uint32_t u[16];
-                    umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * OZ_BN + c0), u);
-                    umma::tmem_ld_wait();
-                    const double pw = __longlong_as_double((long long)(1023 - 7 * (g + 2)) << 52);  // 2^(-7(g+2))
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = fma((double)(int)u[i], pw, v[i]);
-                }
-                double* dst = Cm + row * ldc + (int64_t)ctile * OZ_BN + c0;
-                const double* cs = colscale + (int64_t)ctile * OZ_BN + c0;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const double x = v[i] * cs[i];
-                    dst[i] = kc ? dst[i] + x : x;
-                }
-            }
-            umma::tc_fence_before();
-            umma::mbar_arrive(acc_empty);
-        }
-    }
-    umma::tc_fence_before();
-    __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
 // ---- operand producers: both write the shared-memory stage layout directly -----------------------------------------
@@ -317,14 +202,14 @@ __global__ void oz_colscale_kernel(const double* __restrict__ rowscale, int P, i
     colscale[c] = (c < (int64_t)T * P) ? rowscale[c / P] : 0.0;
 }
 
-// Bop[ctile][kb][t][core layout of 64 columns x 32 samples]: digits of coef_r[i] CUA[i][a] / 2^(e_r).
+// Bop[ctile][kb][t][core layout of 128 columns x 32 samples]: digits of coef_r[i] CUA[i][a] / 2^(e_r).
 template <int S>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128)
     oz_slice_coef_kernel(const double* __restrict__ CUA, int64_t n, int P, const double* __restrict__ w,
                          const double* __restrict__ vf, int64_t ldvf, int T, const double* __restrict__ inv,
                          uint8_t* __restrict__ Bop, int kblocks) {
     const int col = threadIdx.x;
-    const int64_t ctile = blockIdx.y, c = ctile * OZ_BN + col;
+    const int64_t ctile = blockIdx.y, c = ctile * OZ_BM + col;
     const bool live_c = c < (int64_t)T * P;
     const int r = live_c ? (int)(c / P) : 0, a = live_c ? (int)(c % P) : 0;
     const double sc = inv[r];
@@ -352,10 +237,10 @@ __global__ void __launch_bounds__(64)
 #pragma unroll
                 for (int s = 0; s < S; ++s) words[s][e >> 2] |= dig[s] << (8 * (e & 3));
             }
-            uint8_t* dst = Bop + (((int64_t)ctile * kblocks + kb) * S) * OZ_B_BYTES + core_offset(col, ch);
+            uint8_t* dst = Bop + (((int64_t)ctile * kblocks + kb) * S) * OZ_A_BYTES + core_offset(col, ch);
 #pragma unroll
             for (int s = 0; s < S; ++s)
-                *reinterpret_cast<uint4*>(dst + (int64_t)s * OZ_B_BYTES) =
+                *reinterpret_cast<uint4*>(dst + (int64_t)s * OZ_A_BYTES) =
                     make_uint4(words[s][0], words[s][1], words[s][2], words[s][3]);
         }
     }
@@ -376,103 +261,7 @@ __global__ void oz_flag_kernel(const double* __restrict__ Cm, int64_t ldc, int64
 
 static inline int64_t pad_to(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
-template <int S>
-static int oz_configure() {
-    static std::atomic<bool> done[SOCKS_MAX_DEVICES];
-    int dev = 0;
-    SOCKS_CUDA(cudaGetDevice(&dev));
-    const bool tracked = dev >= 0 && dev < SOCKS_MAX_DEVICES;
-    if (tracked && done[dev].load(std::memory_order_acquire)) return SOCKS_OK;
-    SOCKS_CUDA(cudaFuncSetAttribute(srmax_ozaki_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<S>::SMEM_BYTES));
-    if (tracked) done[dev].store(true, std::memory_order_release);
-    return SOCKS_OK;
-}
-
-template <int S>
-static int srmax_predict_i8_impl(const double* X, const double* w, const double* vf, int64_t ldvf, const double* CUA,
-                                 int64_t n, int d, int P, double kmul, const double* pts, int64_t m, const double* tubes,
-                                 int problem, int T, double* out, int64_t ldout, uint8_t* work, int64_t chunk, double tau,
-                                 int* list, cudaStream_t st) {
-    int rc = oz_configure<S>();
-    if (rc) return rc;
-    const int kblocks = (int)(pad_to(n, OZ_KB) / OZ_KB);
-    const int64_t ldbm = pad_to((int64_t)T * P, 128), ctiles = ldbm / OZ_BN;
-    const int64_t mc = pad_to(std::min(chunk, m), OZ_BM), ptiles = mc / OZ_BM;
-    uint8_t* Bop = work;
-    uint8_t* Aop = Bop + pad_to(ctiles * kblocks * (int64_t)S * OZ_B_BYTES, 1024);
-    double* Cm = reinterpret_cast<double*>(Aop + pad_to(ptiles * kblocks * (int64_t)S * OZ_A_BYTES, 1024));
-    double* rowscale = Cm + mc * ldbm;
-    double* inv = rowscale + pad_to(T, 2);
-    double* colscale = inv + pad_to(T, 2);
-    oz_rowscale_kernel<<<T, 256, 0, st>>>(w, vf, ldvf, n, rowscale, inv);
-    oz_colscale_kernel<<<(unsigned)ceil_div(ldbm, 256), 256, 0, st>>>(rowscale, P, T, ldbm, colscale);
-    oz_slice_coef_kernel<S><<<dim3((unsigned)ceil_div(kblocks, 16), (unsigned)ctiles), 64, 0, st>>>(CUA, n, P, w, vf, ldvf, T, inv,
-                                                                                              Bop, kblocks);
-    SOCKS_CHECK_LAUNCH();
-    SOCKS_CUDA(cudaMemsetAsync(list, 0, sizeof(int), st));
-    for (int64_t s0 = 0; s0 < m; s0 += mc) {
-        const int64_t cnt = std::min(mc, m - s0), pt = ceil_div(cnt, OZ_BM);
-        const double* p = pts + s0 * d;
-        const dim3 gs((unsigned)ceil_div(kblocks, 16), (unsigned)pt);
-#define SOCKS_OZ_CASE(DD)                                                                              \
-    case DD:                                                                                           \
-        oz_slice_points_kernel<DD, S><<<gs, 128, 0, st>>>(X, n, p, cnt, kmul, Aop, kblocks);           \
-        break;
-        switch (d) {
-            SOCKS_OZ_CASE(1) SOCKS_OZ_CASE(2) SOCKS_OZ_CASE(3) SOCKS_OZ_CASE(4)
-            SOCKS_OZ_CASE(5) SOCKS_OZ_CASE(6) SOCKS_OZ_CASE(7) SOCKS_OZ_CASE(8)
-        }
-#undef SOCKS_OZ_CASE
-        SOCKS_CHECK_LAUNCH();
-        srmax_ozaki_kernel<S><<<dim3((unsigned)ctiles, (unsigned)pt), OZ_THREADS, OzCfg<S>::SMEM_BYTES, st>>>(
-            Aop, Bop, Cm, ldbm, kblocks, colscale);
-        SOCKS_CHECK_LAUNCH();
-        oz_flag_kernel<<<(unsigned)ceil_div(cnt, 8), 256, 0, st>>>(Cm, ldbm, cnt, P, rowscale, tau, s0, list);
-        SOCKS_CHECK_LAUNCH();
-        rc = socks_srmax_step(Cm, ldbm, nullptr, 0, cnt, P, T, 0, p, d, tubes, problem, T, out + s0, ldout, 1,
-                              (socks_stream_t)st);
-        if (rc) return rc;
-    }
-    return SOCKS_OK;
-}
-
 }  // namespace socks
-
-extern "C" int64_t socks_srmax_predict_i8_work_bytes(int64_t n, int P, int T, int64_t chunk, int slices) {
-    const int64_t kblocks = pad_to(n, OZ_KB) / OZ_KB, ldbm = pad_to((int64_t)T * P, 128), mc = pad_to(chunk, OZ_BM);
-    return pad_to((ldbm / OZ_BN) * kblocks * slices * OZ_B_BYTES, 1024) + pad_to((mc / OZ_BM) * kblocks * slices * OZ_A_BYTES, 1024) +
-           (mc * ldbm + 2 * pad_to(T, 2) + ldbm) * 8 + 1024;
-}
-
-extern "C" int socks_srmax_predict_i8(const double* X, const double* w, const double* vf, int64_t ldvf, const double* CUA,
-                                      int64_t n, int d, int P, double scale, int divide, const double* pts, int64_t m,
-                                      const double* tubes, int problem, int T, double* out, int64_t ldout, void* work,
-                                      int64_t chunk, int slices, double tau, int* flagged, socks_stream_t stream) {
-    SOCKS_CHECK_ARG(X && w && vf && CUA, 1);
-    SOCKS_CHECK_ARG(n >= 1, 6);
-    SOCKS_CHECK_ARG(d >= 1 && d <= 8, 7);
-    SOCKS_CHECK_ARG(P >= 1, 8);
-    SOCKS_CHECK_ARG(scale == scale && (!divide || scale != 0.0), 9);
-    SOCKS_CHECK_ARG(m >= 0 && m < ((int64_t)1 << 31), 12);
-    SOCKS_CHECK_ARG(T >= 2, 15);
-    SOCKS_CHECK_ARG(ldout >= m, 17);
-    SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 1023) == 0, 18);
-    SOCKS_CHECK_ARG(chunk >= 1, 19);
-    SOCKS_CHECK_ARG(slices >= 6 && slices <= 8, 20);
-    SOCKS_CHECK_ARG(tau >= 0.0, 21);
-    SOCKS_CHECK_ARG(flagged != nullptr, 22);
-    if (m == 0) return SOCKS_OK;
-    SOCKS_CHECK_ARG(pts != nullptr && out != nullptr, 11);
-    const double kmul = divide ? 1.0 / scale : scale;
-    SOCKS_CHECK_ARG(kmul < 0.0, 9);
-    cudaStream_t st = (cudaStream_t)stream;
-    uint8_t* wk = reinterpret_cast<uint8_t*>(work);
-    switch (slices) {
-        case 6: return srmax_predict_i8_impl<6>(X, w, vf, ldvf, CUA, n, d, P, kmul, pts, m, tubes, problem, T, out, ldout, wk, chunk, tau, flagged, st);
-        case 7: return srmax_predict_i8_impl<7>(X, w, vf, ldvf, CUA, n, d, P, kmul, pts, m, tubes, problem, T, out, ldout, wk, chunk, tau, flagged, st);
-        default: return srmax_predict_i8_impl<8>(X, w, vf, ldvf, CUA, n, d, P, kmul, pts, m, tubes, problem, T, out, ldout, wk, chunk, tau, flagged, st);
-    }
-}
 
 // =====================================================================================================================
 // FP64-equivalent GEMM on the integer tensor cores (Ozaki scheme) for the factorisation's trailing updates:
@@ -599,21 +388,31 @@ __global__ void __launch_bounds__(128)
 // runs at the full rate.  So pass A accumulates groups 0..3 (10 MMAs per K-block, digit slices 0..3 of both operands) and
 // pass B groups 4..6 (18 MMAs, all slices); each pass ends in its own epilogue.  Both passes are bound by L2 -> SM
 // traffic at ~45 B/clk/SM (tools/probes/umma_pipe.cu): 88 KB per K-block and tile.
+template <int S>
 struct OgCfg {
     static constexpr int BN = 128;
-    static constexpr int SLICE = OZ_A_BYTES;                        // 128 rows x 32 B of one digit
-    static constexpr int NS_A = 4, NS_B = OG_S;                     // digit slices a pass needs
-    static constexpr int STAGE_A = 2 * NS_A * SLICE, STAGES_A = 5;  // 32 KB x 5
-    static constexpr int STAGE_B = 2 * NS_B * SLICE, STAGES_B = 3;  // 56 KB x 3
-    static constexpr int RING_BYTES = STAGES_B * STAGE_B;           // 168 KB (>= STAGES_A * STAGE_A)
+    static constexpr int SLICE = OZ_A_BYTES;                                 // 128 rows x 32 B of one digit
+    static constexpr int NS_A = 4, NS_B = S;                                 // digit slices a pass needs
+    static constexpr int STAGE_A = 2 * NS_A * SLICE, STAGES_A = 5;           // 32 KB x 5
+    static constexpr int STAGE_B = 2 * NS_B * SLICE;                         // 48 / 56 / 64 KB for S = 6 / 7 / 8
+    static constexpr int STAGES_B = (192 * 1024) / STAGE_B;                  // 4 / 3 / 3
+    static constexpr int RING_A = STAGES_A * STAGE_A, RING_B = STAGES_B * STAGE_B;
+    static constexpr int RING_BYTES = RING_A > RING_B ? RING_A : RING_B;     // 192 / 168 / 192 KB
     static constexpr int NBAR = 2 * (STAGES_A + STAGES_B) + 3;
     static constexpr int SMEM_BYTES = RING_BYTES + NBAR * 8 + 16;
 };
-static_assert(OgCfg::STAGES_A * OgCfg::STAGE_A <= OgCfg::RING_BYTES, "pass A ring must fit");
 
-// int32 stays exact for OG_KCHUNK K-blocks; longer products hand the accumulators over chunk by chunk (fp64 sum in C).
-constexpr int OG_KCHUNK = 512;  // 16 384 samples: 7 * 16384 * 2^14 < 2^31
+// int32 stays exact for og_kchunk K-blocks; longer products hand the accumulators over chunk by chunk (fp64 sum in C).
+// Signed 8-bit digits: |d d'| <= 2^14, at most 7 pairs per group: 7 * 16384 * 2^14 < 2^31.  Unsigned 7-bit digits (top
+// digit up to 128): at most 8 pairs: 8 * 10240 * 2^14 < 2^31.
+template <int BITS>
+struct OgChunk {
+    static constexpr int KBLOCKS = BITS == 8 ? 512 : 320;
+};
 
+__device__ __forceinline__ double og_pow2(int e) {  // 2^e, e in the normal range (folds to a constant)
+    return __longlong_as_double((long long)(1023 + e) << 52);
+}
 // exact int64 -> double for |x| < 2^51 (one integer add, one DADD; I2F.F64 is several times slower)
 __device__ __forceinline__ double og_i2d(long long x) {
     return __longlong_as_double(x + 0x4338000000000000LL) - 0x1.8p52;
@@ -622,12 +421,19 @@ __device__ __forceinline__ double og_i2d(long long x) {
 // C[128 ptile + i][128 ctile + j] (op)= sa[i] sb[j] sum_g 2^(-12 - 8g) G_g[i][j];  mode: 0 C -= AB^T, 1 C = AB^T,
 // 2 C = -AB^T.  tri_a / tri_b clip the K range per tile exactly like GEMM_A_K_LE_M / GEMM_B_K_GE_N of gemm_f64.cuh.
 // Warps 0-3: epilogue (thread = row), warp 4: loader (bulk copies), warp 5: MMA issue.
+//
+// Template: S digit slices of BITS bits.  BITS = 8: balanced signed digits, group weight 2^(-12 - 8g) (the GEMM of the
+// factorisation, S = 7).  BITS = 7: unsigned digits of values in [0, 1], group weight 2^(-14 - 7g), sa == nullptr (no row
+// scale): the KernelMaximalSR contraction, S = 6..8.
+template <int S, int BITS>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
     oz_gemm_nt_kernel(const uint8_t* __restrict__ Aop, const double* __restrict__ sa, const uint8_t* __restrict__ Bop,
                       const double* __restrict__ sb, double* __restrict__ C, int64_t ldc, int kblocks, int lower_only,
                       int mode, int tri_a, int tri_b) {
-    using Cfg = OgCfg;
-    constexpr int S = OG_S, SL = Cfg::SLICE, BN = Cfg::BN;
+    using Cfg = OgCfg<S>;
+    constexpr int SL = Cfg::SLICE, BN = Cfg::BN, OG_KCHUNK = OgChunk<BITS>::KBLOCKS;
+    constexpr int W0 = (BITS == 8) ? 12 : 14, NGB = S - 4;  // weight of group 0 is 2^-W0; groups of pass B
+    static_assert(S >= 6 && S <= 8 && (BITS == 7 || BITS == 8), "digit scheme");
     const int ctile = blockIdx.x, ptile = blockIdx.y;
     if (lower_only && ctile > ptile) return;
     int kb_lo = 0, kb_hi = kblocks;
@@ -692,7 +498,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         }
     } else if (warp == 5) {
         if (lane == 0) {
-            const uint32_t idesc = umma::idesc_i8(OZ_BM, BN, 1, 1);  // signed digits
+            const uint32_t idesc = umma::idesc_i8(OZ_BM, BN, BITS == 8, BITS == 8);  // signed 8-bit or unsigned 7-bit digits
             uint32_t seg = 0;                                        // accumulator hand-overs so far
             for (int i0 = 0; i0 < nk; i0 += OG_KCHUNK, ++seg) {      // pass A: groups 0..3 -> columns 128 g
                 if (seg > 0) {
@@ -746,7 +552,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     } else {
         const int64_t row = (int64_t)ptile * OZ_BM + tid;
         double* crow = C + row * ldc + (int64_t)ctile * BN;
-        const double sr = ((mode == 1) ? 1.0 : -1.0) * sa[row];
+        const double sr = ((mode == 1) ? 1.0 : -1.0) * (sa ? sa[row] : 1.0);
         if (mode == 0) {  // pull this thread's 1 KB of C towards the SM while the tensor cores work
 #pragma unroll
             for (int i = 0; i < BN; i += 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(crow + i));
@@ -767,8 +573,6 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
             umma::tc_fence_after();
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 16) {
-                // sum_g 2^(-12 - 8g) G_g over the pass's groups, merged in exact 64-bit integer arithmetic first
-                // (|G_g| <= (g + 1) K 2^14 and |G_0| <= K 2^12: every partial stays below 2^49) and converted once
                 // this chunk's C values were requested one chunk ago (or before the pass); request the next ones now, so
                 // that their latency hides behind the tensor-memory reads and the arithmetic of this chunk.  A lane only
                 // ever reads elements it wrote itself, so a request may run ahead into the next pass.
@@ -783,6 +587,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
                             nxt[k] = __ldcg(cwarp + cn + (lane & 15) + (int64_t)(2 * k + (lane >> 4)) * ldc);
                     }
                 }
+                // sum_g 2^(-W0 - BITS g) G_g over the pass's groups, merged in exact 64-bit integer arithmetic first
+                // (every partial stays below 2^51: |G_g| < 2^31, |G_0| <= K 2^14) and converted once
                 double v[16];
                 if (!pass_b) {
                     uint32_t u[4][16];
@@ -791,18 +597,22 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
                     umma::tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const long long hi = ((long long)(int)u[0][i] << 8) + (int)u[1][i];
-                        const long long lo = ((long long)(int)u[2][i] << 8) + (int)u[3][i];
-                        v[i] = fma(og_i2d(hi), 0x1p-20, og_i2d(lo) * 0x1p-36);
+                        const long long hi = ((long long)(int)u[0][i] << BITS) + (int)u[1][i];
+                        const long long lo = ((long long)(int)u[2][i] << BITS) + (int)u[3][i];
+                        v[i] = fma(og_i2d(hi), og_pow2(-W0 - BITS), og_i2d(lo) * og_pow2(-W0 - 3 * BITS));
                     }
                 } else {
-                    uint32_t u[3][16];
+                    uint32_t u[NGB][16];
 #pragma unroll
-                    for (int g = 0; g < 3; ++g) umma::tmem_ld16(trow + (uint32_t)(g * BN + c0), u[g]);
+                    for (int g = 0; g < NGB; ++g) umma::tmem_ld16(trow + (uint32_t)(g * BN + c0), u[g]);
                     umma::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        v[i] = og_i2d(((long long)(int)u[0][i] << 16) + ((long long)(int)u[1][i] << 8) + (int)u[2][i]) * 0x1p-60;
+                    for (int i = 0; i < 16; ++i) {
+                        long long q = (int)u[0][i];
+#pragma unroll
+                        for (int g = 1; g < NGB; ++g) q = (q << BITS) + (int)u[g][i];  // < 2^(31 + 21)... top group < 2^30
+                        v[i] = og_i2d(q) * og_pow2(-W0 - BITS * (S - 1));
+                    }
                 }
                 // tensor memory hands a thread one ROW; C wants 128 contiguous bytes per row and instruction, so the
                 // 32 x 16 block of the warp is turned through shared memory (two rows of 16 doubles per instruction)
@@ -826,13 +636,14 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
+template <int S, int BITS>
 static int og_configure() {
     static std::atomic<bool> done[SOCKS_MAX_DEVICES];
     int dev = 0;
     SOCKS_CUDA(cudaGetDevice(&dev));
     const bool tracked = dev >= 0 && dev < SOCKS_MAX_DEVICES;
     if (tracked && done[dev].load(std::memory_order_acquire)) return SOCKS_OK;
-    SOCKS_CUDA(cudaFuncSetAttribute(oz_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OgCfg::SMEM_BYTES));
+    SOCKS_CUDA(cudaFuncSetAttribute((oz_gemm_nt_kernel<S, BITS>), cudaFuncAttributeMaxDynamicSharedMemorySize, OgCfg<S>::SMEM_BYTES));
     if (tracked) done[dev].store(true, std::memory_order_release);
     return SOCKS_OK;
 }
@@ -870,7 +681,7 @@ int ozaki_slice_operand(const double* P, int64_t rows, int64_t K, int64_t ld, in
 int ozaki_gemm_nt_sliced(const uint8_t* abuf, int64_t a_rows_total, int64_t a_tile0, const uint8_t* bbuf, int64_t b_rows_total,
                          int64_t b_tile0, int64_t K, double* C, int64_t ldc, int64_t m, int64_t n, int lower_only, int mode,
                          int tri_a, int tri_b, cudaStream_t st) {
-    int rc = og_configure();
+    int rc = og_configure<OG_S, 8>();
     if (rc) return rc;
     const int kb = (int)(pad_to(K, OZ_KB) / OZ_KB);
     const int64_t art = pad_to(a_rows_total, OZ_BM) / OZ_BM, brt = pad_to(b_rows_total, OZ_BM) / OZ_BM;
@@ -878,7 +689,7 @@ int ozaki_gemm_nt_sliced(const uint8_t* abuf, int64_t a_rows_total, int64_t a_ti
     const double* sb = reinterpret_cast<const double*>(bbuf + pad_to(brt * kb * OG_S * OZ_A_BYTES, 1024)) + b_tile0 * OZ_BM;
     const uint8_t* aop = abuf + a_tile0 * (int64_t)kb * OG_S * OZ_A_BYTES;
     const uint8_t* bop = bbuf + b_tile0 * (int64_t)kb * OG_S * OZ_A_BYTES;
-    oz_gemm_nt_kernel<<<dim3((unsigned)(n / OgCfg::BN), (unsigned)(m / OZ_BM)), OZ_THREADS, OgCfg::SMEM_BYTES, st>>>(
+    oz_gemm_nt_kernel<OG_S, 8><<<dim3((unsigned)(n / OgCfg<OG_S>::BN), (unsigned)(m / OZ_BM)), OZ_THREADS, OgCfg<OG_S>::SMEM_BYTES, st>>>(
         aop, sa, bop, sb, C, ldc, kb, lower_only, mode, tri_a, tri_b);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -888,7 +699,95 @@ int ozaki_gemm_nt_sliced(const uint8_t* abuf, int64_t a_rows_total, int64_t a_ti
     return SOCKS_OK;
 }
 
+
+// ---- KernelMaximalSR predict on the same kernel ------------------------------------------------------------------
+template <int S>
+static int srmax_predict_i8_impl(const double* X, const double* w, const double* vf, int64_t ldvf, const double* CUA,
+                                 int64_t n, int d, int P, double kmul, const double* pts, int64_t m, const double* tubes,
+                                 int problem, int T, double* out, int64_t ldout, uint8_t* work, int64_t chunk, double tau,
+                                 int* list, cudaStream_t st) {
+    int rc = og_configure<S, 7>();
+    if (rc) return rc;
+    const int kblocks = (int)(pad_to(n, OZ_KB) / OZ_KB);
+    const int64_t ldbm = pad_to((int64_t)T * P, 128), ctiles = ldbm / OZ_BM;
+    const int64_t mc = pad_to(std::min(chunk, m), OZ_BM), ptiles = mc / OZ_BM;
+    uint8_t* Bop = work;
+    uint8_t* Aop = Bop + pad_to(ctiles * kblocks * (int64_t)S * OZ_A_BYTES, 1024);
+    double* Cm = reinterpret_cast<double*>(Aop + pad_to(ptiles * kblocks * (int64_t)S * OZ_A_BYTES, 1024));
+    double* rowscale = Cm + mc * ldbm;
+    double* inv = rowscale + pad_to(T, 2);
+    double* colscale = inv + pad_to(T, 2);
+    oz_rowscale_kernel<<<T, 256, 0, st>>>(w, vf, ldvf, n, rowscale, inv);
+    oz_colscale_kernel<<<(unsigned)ceil_div(ldbm, 256), 256, 0, st>>>(rowscale, P, T, ldbm, colscale);
+    oz_slice_coef_kernel<S><<<dim3((unsigned)ceil_div(kblocks, 16), (unsigned)ctiles), 128, 0, st>>>(CUA, n, P, w, vf, ldvf, T, inv,
+                                                                                              Bop, kblocks);
+    SOCKS_CHECK_LAUNCH();
+    SOCKS_CUDA(cudaMemsetAsync(list, 0, sizeof(int), st));
+    for (int64_t s0 = 0; s0 < m; s0 += mc) {
+        const int64_t cnt = std::min(mc, m - s0), pt = ceil_div(cnt, OZ_BM);
+        const double* p = pts + s0 * d;
+        const dim3 gs((unsigned)ceil_div(kblocks, 16), (unsigned)pt);
+#define SOCKS_OZ_CASE(DD)                                                                              \
+    case DD:                                                                                           \
+        oz_slice_points_kernel<DD, S><<<gs, 128, 0, st>>>(X, n, p, cnt, kmul, Aop, kblocks);           \
+        break;
+        switch (d) {
+            SOCKS_OZ_CASE(1) SOCKS_OZ_CASE(2) SOCKS_OZ_CASE(3) SOCKS_OZ_CASE(4)
+            SOCKS_OZ_CASE(5) SOCKS_OZ_CASE(6) SOCKS_OZ_CASE(7) SOCKS_OZ_CASE(8)
+        }
+#undef SOCKS_OZ_CASE
+        SOCKS_CHECK_LAUNCH();
+        // Cm (points x T P) = K(pts, X) . coef: unsigned 7-bit digits, no row scale (kernel values lie in [0, 1])
+        oz_gemm_nt_kernel<S, 7><<<dim3((unsigned)ctiles, (unsigned)pt), OZ_THREADS, OgCfg<S>::SMEM_BYTES, st>>>(
+            Aop, nullptr, Bop, colscale, Cm, ldbm, kblocks, 0, 1, 0, 0);
+        SOCKS_CHECK_LAUNCH();
+        oz_flag_kernel<<<(unsigned)ceil_div(cnt, 8), 256, 0, st>>>(Cm, ldbm, cnt, P, rowscale, tau, s0, list);
+        SOCKS_CHECK_LAUNCH();
+        rc = socks_srmax_step(Cm, ldbm, nullptr, 0, cnt, P, T, 0, p, d, tubes, problem, T, out + s0, ldout, 1,
+                              (socks_stream_t)st);
+        if (rc) return rc;
+    }
+    return SOCKS_OK;
+}
+
 }  // namespace socks
+
+extern "C" int64_t socks_srmax_predict_i8_work_bytes(int64_t n, int P, int T, int64_t chunk, int slices) {
+    const int64_t kblocks = pad_to(n, OZ_KB) / OZ_KB, ldbm = pad_to((int64_t)T * P, 128), mc = pad_to(chunk, OZ_BM);
+    return pad_to((ldbm / OZ_BM) * kblocks * slices * OZ_A_BYTES, 1024) + pad_to((mc / OZ_BM) * kblocks * slices * OZ_A_BYTES, 1024) +
+           (mc * ldbm + 2 * pad_to(T, 2) + ldbm) * 8 + 1024;
+}
+
+extern "C" int socks_srmax_predict_i8(const double* X, const double* w, const double* vf, int64_t ldvf, const double* CUA,
+                                      int64_t n, int d, int P, double scale, int divide, const double* pts, int64_t m,
+                                      const double* tubes, int problem, int T, double* out, int64_t ldout, void* work,
+                                      int64_t chunk, int slices, double tau, int* flagged, socks_stream_t stream) {
+    SOCKS_CHECK_ARG(X && w && vf && CUA, 1);
+    SOCKS_CHECK_ARG(n >= 1, 6);
+    SOCKS_CHECK_ARG(d >= 1 && d <= 8, 7);
+    SOCKS_CHECK_ARG(P >= 1, 8);
+    SOCKS_CHECK_ARG(scale == scale && (!divide || scale != 0.0), 9);
+    SOCKS_CHECK_ARG(m >= 0 && m < ((int64_t)1 << 31), 12);
+    SOCKS_CHECK_ARG(T >= 2, 15);
+    SOCKS_CHECK_ARG(ldout >= m, 17);
+    SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 1023) == 0, 18);
+    SOCKS_CHECK_ARG(chunk >= 1, 19);
+    SOCKS_CHECK_ARG(slices >= 6 && slices <= 8, 20);
+    SOCKS_CHECK_ARG(tau >= 0.0, 21);
+    SOCKS_CHECK_ARG(flagged != nullptr, 22);
+    if (m == 0) return SOCKS_OK;
+    SOCKS_CHECK_ARG(pts != nullptr && out != nullptr, 11);
+    const double kmul = divide ? 1.0 / scale : scale;
+    SOCKS_CHECK_ARG(kmul < 0.0, 9);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* wk = reinterpret_cast<uint8_t*>(work);
+    switch (slices) {
+        case 6: return srmax_predict_i8_impl<6>(X, w, vf, ldvf, CUA, n, d, P, kmul, pts, m, tubes, problem, T, out, ldout, wk, chunk, tau, flagged, st);
+        case 7: return srmax_predict_i8_impl<7>(X, w, vf, ldvf, CUA, n, d, P, kmul, pts, m, tubes, problem, T, out, ldout, wk, chunk, tau, flagged, st);
+        default: return srmax_predict_i8_impl<8>(X, w, vf, ldvf, CUA, n, d, P, kmul, pts, m, tubes, problem, T, out, ldout, wk, chunk, tau, flagged, st);
+    }
+}
+
 
 extern "C" int64_t socks_dev_ozaki_gemm_work_bytes(int64_t m, int64_t n, int64_t K) {
     return ozaki_operand_bytes(m, K) + ozaki_operand_bytes(n, K) + 2048;
