@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128)
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int m0 = blockIdx.y * I8_BM, n0 = blockIdx.x * I8_BN;
-    if (warp == 0) umma::tmem_alloc(&tmem_base, 64);
+    if (warp == 0) umma::tmem_alloc(&tmem_base, 128);
     if (tid == 0) {
         umma::mbar_init(&bar, 1);
         umma::mbar_fence_init();
@@ -34,13 +34,23 @@ __global__ void __launch_bounds__(128)
     umma::tc_fence_after();
     const uint32_t tmem = tmem_base;
     const uint32_t idesc = umma::idesc_i8(I8_BM, I8_BN, 1, 1);
-    const uint32_t lbo = variant ? 256 : 128, sbo = variant ? 128 : 256;
+    const uint32_t lbo = variant == 1 ? 256 : 128, sbo = variant == 1 ? 128 : 256;
     uint32_t phase = 0;
     for (int k0 = 0; k0 < K; k0 += I8_KB) {
-        for (int ch = tid; ch < I8_BM * 2; ch += 128) {
-            const int r = ch >> 1, c = ch & 1;
-            *reinterpret_cast<int4*>(sA + core_offset(r, c)) =
-                *reinterpret_cast<const int4*>(A + (int64_t)(m0 + r) * K + k0 + c * 16);
+        if (variant == 2) {  // A operand through tensor memory: thread = row, its 32 K-bytes -> 8 columns at column 64
+            const int4* src = reinterpret_cast<const int4*>(A + (int64_t)(m0 + tid) * K + k0);
+            const int4 lo = src[0], hi = src[1];
+            const uint32_t w[8] = {(uint32_t)lo.x, (uint32_t)lo.y, (uint32_t)lo.z, (uint32_t)lo.w,
+                                   (uint32_t)hi.x, (uint32_t)hi.y, (uint32_t)hi.z, (uint32_t)hi.w};
+            umma::tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + 64, w);
+            umma::tmem_st_wait();
+            umma::tc_fence_before();
+        } else {
+            for (int ch = tid; ch < I8_BM * 2; ch += 128) {
+                const int r = ch >> 1, c = ch & 1;
+                *reinterpret_cast<int4*>(sA + core_offset(r, c)) =
+                    *reinterpret_cast<const int4*>(A + (int64_t)(m0 + r) * K + k0 + c * 16);
+            }
         }
         for (int ch = tid; ch < I8_BN * 2; ch += 128) {
             const int r = ch >> 1, c = ch & 1;
@@ -53,7 +63,8 @@ __global__ void __launch_bounds__(128)
             umma::tc_fence_after();
             const uint64_t da = umma::smem_desc_kmajor_noswizzle(umma::smem_u32(sA), lbo, sbo);
             const uint64_t db = umma::smem_desc_kmajor_noswizzle(umma::smem_u32(sB), lbo, sbo);
-            umma::mma_i8(tmem, da, db, idesc, k0 > 0 ? 1u : 0u);
+            if (variant == 2) umma::mma_i8_ts(tmem, tmem + 64, db, idesc, k0 > 0 ? 1u : 0u);
+            else umma::mma_i8(tmem, da, db, idesc, k0 > 0 ? 1u : 0u);
             umma::mma_commit(&bar);
         }
         umma::mbar_wait(&bar, phase);  // the MMA has consumed this K-block: shared memory may be overwritten
@@ -69,7 +80,7 @@ __global__ void __launch_bounds__(128)
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 64);
+    if (warp == 0) umma::tmem_dealloc(tmem, 128);
 }
 
 }  // namespace socks

@@ -28,9 +28,11 @@
 //
 // Work per pair: N*M*(3d+2+E+2T) algorithmic flops; 8*M*(d+T) bytes of I/O.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 
 #include "exp_f64.cuh"
+#include "umma.cuh"
 
 namespace socks {
 
@@ -39,6 +41,16 @@ constexpr int SP_TS = 64;        // samples per shared-memory stage
 constexpr int SP_SPLIT = 2048;   // samples per CTA (blockIdx.y): FIXED, so the summation order does not depend on M
 constexpr int SP_HDR = 16;       // header doubles of the packed state: [0] factored-ok, [1] R_x^2, [2..10) centre
 constexpr double SP_RANGE = 600.0;
+
+// Integer tensor-core engine (sr_predict_i8_kernel below)
+constexpr int PI_KB = 32;            // samples per K-block (one tcgen05.mma kind::i8 K step)
+constexpr int PI_SPLIT = 4096;       // samples per CTA = one exact int32 accumulation: 8 pairs * 255^2 * 4096 < 2^31
+constexpr int PI_STAGES = 4;         // K-blocks in flight (tensor-memory stages of the kernel-value digits)
+constexpr int PI_TBL = 256;          // table of 2^(j/256) ...
+constexpr int PI_REP = 16;           // ... replicated 16x: lane l reads copy l % 16, so a lookup never bank-conflicts
+constexpr int PI_TW = 128;           // points per CTA = tensor-memory lanes
+constexpr int PI_GROUPS = 10;        // digit groups kept (weight of group g: 2^(-13 - 8 g)); the rest is < 2^-90 of the scale
+constexpr double PI_TAU = 6.103515625e-05;  // 2^-14: columns with a smaller normaliser (relative) take the direct form
 
 
 __host__ __device__ inline int64_t sp_npad(int64_t n) { return (n + SP_TS - 1) / SP_TS * SP_TS; }
@@ -118,6 +130,59 @@ __global__ void sr_pack_kernel(const double* __restrict__ X, const double* __res
             if (live && r < R) c = (r == 0) ? wi : vf[(int64_t)(t0 + r) * ldvf + i] * wi;
             ce[r] = c;
             cf[r] = c * e;
+        }
+    }
+}
+
+// ---- operands of the integer tensor-core engine (once per fit) -----------------------------------------------
+// cscale[b][r] = 2^e > max_i coefE[b][i][r] (1 for an all-zero row)
+__global__ void __launch_bounds__(256) pi_rowscale_kernel(const double* __restrict__ coefE, int64_t n_pad,
+                                                          double* __restrict__ cscale) {
+    __shared__ double sm[256];
+    const int b = blockIdx.x / 16, r = blockIdx.x % 16;
+    const double* c = coefE + (int64_t)b * n_pad * SR_CP + r;
+    double mx = 0.0;
+    for (int64_t i = threadIdx.x; i < n_pad; i += 256) mx = fmax(mx, c[i * SR_CP]);
+    sm[threadIdx.x] = mx;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + off]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) cscale[blockIdx.x] = (sm[0] > 0.0 && sm[0] < INFINITY) ? ldexp(1.0, ilogb(sm[0]) + 1) : 1.0;
+}
+
+// Core-matrix layout of an (R rows x 32 bytes) K-major operand tile (see umma.cuh): [r / 8][16-byte chunk c][r % 8][16 B].
+__device__ __forceinline__ int pi_core_offset(int r, int c) { return (r >> 3) * 256 + c * 128 + (r & 7) * 16; }
+
+// coefD[b][kb]: the B operand of one K-block, 128 rows x 32 bytes: row 16 t + r = digit t (byte 7 - t, unsigned) of
+// rint(coefE[b][i][r] / cscale[b][r] * 2^63), column = sample i % 32.
+// xsD[kb][i % 32] = (x'_i[0..d), cx_i) with cx_i = kmul |x'_i|^2 * 256/ln2: the sample's share of the exponent.
+// tbl[j][rep] = 2^(j/256).
+__global__ void pi_pack_kernel(const double* __restrict__ Xc, const double* __restrict__ coefE,
+                               const double* __restrict__ cscale, int64_t n_pad, int d, int nblk, double kmul,
+                               uint8_t* __restrict__ coefD, double* __restrict__ xsD, double* __restrict__ tbl) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < PI_TBL * PI_REP) tbl[i] = exp2((double)(i / PI_REP) / PI_TBL);
+    if (i >= n_pad) return;
+    const int64_t kb = i / PI_KB;
+    const int e = (int)(i % PI_KB);
+    double q2 = 0.0;
+    double* xs = xsD + i * (d + 1);
+    for (int k = 0; k < d; ++k) {
+        const double t = Xc[i * d + k];
+        xs[k] = t;
+        q2 = fma(t, t, q2);
+    }
+    xs[d] = kmul * q2 * (PI_TBL / 0.693147180559945309417232121458176568);
+    for (int b = 0; b < nblk; ++b) {
+        uint8_t* tile = coefD + ((int64_t)b * (n_pad / PI_KB) + kb) * 4096;
+        for (int r = 0; r < 16; ++r) {
+            const double c = coefE[((int64_t)b * n_pad + i) * SR_CP + r] / cscale[b * 16 + r];  // in [0, 1)
+            const unsigned long long q = __double2ull_rn(c * 0x1p63);
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                tile[pi_core_offset(16 * t + r, e >> 4) + (e & 15)] = (uint8_t)(q >> (8 * (7 - t)));
         }
     }
 }
@@ -344,6 +409,269 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     }
 }
 
+// ---- integer tensor-core engine ----------------------------------------------------------------------------------
+// Same contraction acc[r][j] = sum_i coef[i][r] k(x_i, p_j), but off the FP64 pipe: the kernel value k in (0, 1] is turned
+// into a 62-bit fixed-point integer whose BYTES are unsigned 8-bit digits, the coefficients (>= 0, row-scaled) likewise
+// (once per fit), and every digit product is an exact int8 x int8 -> int32 MMA (tcgen05.mma kind::i8, accumulators in
+// tensor memory).  The FP64 pipe is left with the exponent and the exponential alone (10 instructions per pair), the 32
+// DMMA cycles per 32 pairs of the fp64 kernel are gone.
+//   * CTA = 128 points (thread = point = TMEM lane) x one fixed 4096-sample split; warps 0-3 produce, lane 0 of warp 4
+//     loads (bulk copies), lane 0 of warp 5 issues the MMAs.
+//   * Per K-block (32 samples) a producer thread evaluates its point against the 32 samples,
+//         a = ps . x' + cx_i + cp   (exponent in units of ln2/256, expanded form of -g |x - p|^2),
+//         2^(a/256) = 2^(k >> 8) * tbl[k & 255] * (1 + f (d1 + f (d2 + f d3))),   k = rint(a), f = a - k,
+//     converts to q = rint(k 2^62) (F2I.S64), transposes the bytes of 4 q's at a time (PRMT) and writes the 8 digit rows of
+//     its lane straight into tensor memory (tcgen05.st): the A operand never touches shared memory.
+//   * The B operand of the K-block stacks the 8 coefficient digits of the 16 rows: 128 "columns" n = 16 t + r.  The MMA of
+//     kernel digit s targets D columns 16 s .. 16 s + 127, so the product (s, t) lands in group g = s + t at columns
+//     16 g + r: 8 MMAs (128 x 128 x 32) per K-block accumulate all 64 digit pairs into 15 groups of 16 columns.
+//   * Epilogue: groups 0..9 -> exact 64-bit integer merge -> fp64 -> x cscale[r] -> partial sums of this split; the last
+//     CTA of the tile sums the splits in index order and finishes the column exactly like the fp64 kernel.  Integer sums
+//     are exact, the split boundaries are fixed: every column is bit-identical however the points are chunked or sharded.
+// A column stands only if the expanded exponent is accurate for it (same range test as the factored fp64 form), the
+// point is finite and its normaliser is >= 2^-14 of the scale (then the fixed-point error is < 1e-10 relative); every other
+// column is queued for the direct form, which reproduces numpy's underflow / 0/0 behaviour.
+template <int D>
+struct PiCfg {
+    static constexpr int XS_BYTES = PI_KB * (D + 1) * 8;
+    static constexpr int STAGE_BYTES = 4096 + XS_BYTES;  // coefficient digits + samples of one K-block
+    static constexpr int TBL_BYTES = PI_TBL * PI_REP * 8;
+    static constexpr int NBAR = 3 * PI_STAGES + 2;
+    static constexpr int SMEM_BYTES = TBL_BYTES + PI_STAGES * STAGE_BYTES + NBAR * 8 + 16;
+};
+
+template <int D>
+__global__ void __launch_bounds__(192, 1)
+    sr_predict_i8_kernel(const uint8_t* __restrict__ coefD, const double* __restrict__ xsD, const double* __restrict__ tblG,
+                         const double* __restrict__ cscale, int nkb_total, const double* __restrict__ pts, int64_t m,
+                         const double* __restrict__ hdr, double* __restrict__ part, FinishArgs fa) {
+    if (hdr[0] == 0.0) return;  // launch-uniform: the direct kernels handle this launch
+    using Cfg = PiCfg<D>;
+    extern __shared__ __align__(1024) uint8_t pi_smem[];
+    const double* tbl = reinterpret_cast<const double*>(pi_smem);
+    uint8_t* stages = pi_smem + Cfg::TBL_BYTES;
+    uint64_t* ld_full = reinterpret_cast<uint64_t*>(stages + PI_STAGES * Cfg::STAGE_BYTES);
+    uint64_t* a_full = ld_full + PI_STAGES;
+    uint64_t* empty = a_full + PI_STAGES;
+    uint64_t* acc_full = empty + PI_STAGES;
+    uint64_t* tbl_full = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tbl_full + 1);
+    __shared__ int s_last;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int split = blockIdx.x, nsplit = gridDim.x;
+    const int64_t tile = blockIdx.y;
+    const int kb0 = split * (PI_SPLIT / PI_KB);
+    const int nk = min(nkb_total - kb0, PI_SPLIT / PI_KB);
+    if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
+    if (tid == 32) {
+        for (int i = 0; i < PI_STAGES; ++i) {
+            umma::mbar_init(ld_full + i, 1);
+            umma::mbar_init(a_full + i, 128);
+            umma::mbar_init(empty + i, 1);
+        }
+        umma::mbar_init(acc_full, 1);
+        umma::mbar_init(tbl_full, 1);
+        umma::mbar_fence_init();
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    constexpr uint32_t A_COL = 256;  // kernel-value digits: stage st at columns 256 + 64 st, digit s at + 8 s
+
+    if (warp == 4) {
+        if (lane == 0) {
+            umma::mbar_arrive_expect_tx(tbl_full, Cfg::TBL_BYTES);
+            umma::bulk_g2s(pi_smem, tblG, Cfg::TBL_BYTES, tbl_full);
+            for (int i = 0; i < nk; ++i) {
+                const int st = i % PI_STAGES, round = i / PI_STAGES;
+                if (round > 0) umma::mbar_wait(empty + st, (uint32_t)(round - 1) & 1u);
+                uint8_t* dst = stages + st * Cfg::STAGE_BYTES;
+                umma::mbar_arrive_expect_tx(ld_full + st, Cfg::STAGE_BYTES);
+                umma::bulk_g2s(dst, coefD + (int64_t)(kb0 + i) * 4096, 4096, ld_full + st);
+                umma::bulk_g2s(dst + 4096, xsD + (int64_t)(kb0 + i) * (PI_KB * (D + 1)), Cfg::XS_BYTES, ld_full + st);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc = umma::idesc_i8(128, 128, 0, 0);  // unsigned digits
+            for (int i = 0; i < nk; ++i) {
+                const int st = i % PI_STAGES, round = i / PI_STAGES;
+                umma::mbar_wait(ld_full + st, (uint32_t)round & 1u);
+                umma::mbar_wait(a_full + st, (uint32_t)round & 1u);
+                umma::tc_fence_after();
+                const uint64_t db = umma::smem_desc_kmajor_noswizzle(umma::smem_u32(stages + st * Cfg::STAGE_BYTES), 128, 256);
+#pragma unroll
+                for (int sd = 0; sd < 8; ++sd)
+                    umma::mma_i8_ts(tmem + (uint32_t)(16 * sd), tmem + A_COL + (uint32_t)(64 * st + 8 * sd), db, idesc, 1u);
+                umma::mma_commit(empty + st);
+            }
+            umma::mma_commit(acc_full);
+        }
+    } else {
+        // ---- producers: thread = point
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        {   // zero the 15 accumulator groups of this lane (every MMA accumulates)
+            const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < 240; c += 8) umma::tmem_st8(trow + (uint32_t)c, z);
+        }
+        const int64_t j = min(tile * PI_TW + tid, m - 1);
+        const double L = -fa.kmul * (PI_TBL / 0.693147180559945309417232121458176568);  // g * 256/ln2
+        double ps[D], cp = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const double t = __ldg(pts + j * D + k) - hdr[2 + k];
+            ps[k] = 2.0 * L * t;
+            cp = fma(-L * t, t, cp);
+        }
+        const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+        const double d1 = 2.70760617406228636e-03;  // ln2 / 256
+        const double d2 = 3.66556559691664515e-06;  // d1^2 / 2
+        const double d3 = 3.30823122780754510e-09;  // d1^3 / 6
+        const char* tb_lane = reinterpret_cast<const char*>(tbl) + ((lane & 15) << 3);
+        umma::mbar_wait(tbl_full, 0);
+        for (int i = 0; i < nk; ++i) {
+            const int st = i % PI_STAGES, round = i / PI_STAGES;
+            umma::mbar_wait(ld_full + st, (uint32_t)round & 1u);
+            if (round > 0) {
+                umma::mbar_wait(empty + st, (uint32_t)(round - 1) & 1u);  // the MMAs that read this TMEM stage are done
+                umma::tc_fence_after();
+            }
+            const double* xs = reinterpret_cast<const double*>(stages + st * Cfg::STAGE_BYTES + 4096);
+            uint32_t dig[8][8];  // [digit][word = 4 samples]
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t qh[16], ql[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const double* x = xs + (c * 16 + e) * (D + 1);
+                    double a = x[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) a = fma(ps[k], x[k], a);
+                    a += cp;
+                    const double t = a + kMagic;
+                    const int ki = __double2loint(t);
+                    const double f = a - __int2double_rn(ki);
+                    const double tb = *reinterpret_cast<const double*>(tb_lane + ((ki & (PI_TBL - 1)) << 7));
+                    double pl = fma(f, d3, d2);
+                    pl = fma(f, pl, d1);
+                    pl = pl * f;
+                    const double res = fma(tb, pl, tb);
+                    const int e2 = max(ki >> 8, -1000) + 62;  // k 2^62; values below 2^-62 round to 0
+                    const long long q = __double2ll_rn(__hiloint2double(__double2hiint(res) + (e2 << 20), __double2loint(res)));
+                    qh[e] = (uint32_t)((unsigned long long)q >> 32);
+                    ql[e] = (uint32_t)q;
+                }
+                // bytes of 4 q's -> one word per digit (4 x 4 byte transposes)
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    const int w = c * 4 + g4;
+                    {
+                        const uint32_t a01 = __byte_perm(qh[4 * g4], qh[4 * g4 + 1], 0x5140), b01 = __byte_perm(qh[4 * g4], qh[4 * g4 + 1], 0x7362);
+                        const uint32_t a23 = __byte_perm(qh[4 * g4 + 2], qh[4 * g4 + 3], 0x5140), b23 = __byte_perm(qh[4 * g4 + 2], qh[4 * g4 + 3], 0x7362);
+                        dig[3][w] = __byte_perm(a01, a23, 0x5410);  // byte 4 of q
+                        dig[2][w] = __byte_perm(a01, a23, 0x7632);  // byte 5
+                        dig[1][w] = __byte_perm(b01, b23, 0x5410);  // byte 6
+                        dig[0][w] = __byte_perm(b01, b23, 0x7632);  // byte 7 (top digit)
+                    }
+                    {
+                        const uint32_t a01 = __byte_perm(ql[4 * g4], ql[4 * g4 + 1], 0x5140), b01 = __byte_perm(ql[4 * g4], ql[4 * g4 + 1], 0x7362);
+                        const uint32_t a23 = __byte_perm(ql[4 * g4 + 2], ql[4 * g4 + 3], 0x5140), b23 = __byte_perm(ql[4 * g4 + 2], ql[4 * g4 + 3], 0x7362);
+                        dig[7][w] = __byte_perm(a01, a23, 0x5410);  // byte 0
+                        dig[6][w] = __byte_perm(a01, a23, 0x7632);
+                        dig[5][w] = __byte_perm(b01, b23, 0x5410);
+                        dig[4][w] = __byte_perm(b01, b23, 0x7632);  // byte 3
+                    }
+                }
+            }
+#pragma unroll
+            for (int sd = 0; sd < 8; ++sd) umma::tmem_st8(trow + A_COL + (uint32_t)(64 * st + 8 * sd), dig[sd]);
+            umma::tmem_st_wait();
+            umma::tc_fence_before();
+            umma::mbar_arrive(a_full + st);
+        }
+        // ---- epilogue of the split: groups -> fp64 partial sums
+        umma::mbar_wait(acc_full, 0);
+        umma::tc_fence_after();
+        double val[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) val[r] = 0.0;
+#pragma unroll
+        for (int g = PI_GROUPS - 2; g >= 0; g -= 2) {  // pairs (g, g + 1), smallest weights first
+            uint32_t u0[16], u1[16];
+            umma::tmem_ld16(trow + (uint32_t)(16 * g), u0);
+            umma::tmem_ld16(trow + (uint32_t)(16 * (g + 1)), u1);
+            umma::tmem_ld_wait();
+            const double wgt = __longlong_as_double((long long)(1023 - 13 - 8 * (g + 1)) << 52);  // 2^(-13 - 8 (g + 1))
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const long long pr = ((long long)(int)u0[r] << 8) + (long long)(int)u1[r];  // < 2^40, exact
+                val[r] = fma(__longlong_as_double(pr + 0x4338000000000000LL) - 0x1.8p52, wgt, val[r]);
+            }
+        }
+        double* tpart = part + (tile * nsplit + split) * (int64_t)(16 * PI_TW);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) tpart[r * PI_TW + tid] = val[r] * cscale[r];
+    }
+    umma::tc_fence_before();
+    __threadfence();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
+    if (tid == 0) s_last = (atomicAdd(fa.counters + tile, 1) == nsplit - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const double* tbase = part + tile * nsplit * (int64_t)(16 * PI_TW);
+    if (tid < PI_TW) {
+        const int64_t j = tile * PI_TW + tid;
+        if (j < m) {
+            double sum[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) sum[r] = 0.0;
+            for (int sp = 0; sp < nsplit; ++sp) {
+                const double* src = tbase + (int64_t)sp * (16 * PI_TW) + tid;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) sum[r] += __ldcg(src + r * PI_TW);
+            }
+            const double* p = pts + j * D;
+            if (fa.write_last)
+                fa.out[(int64_t)(fa.T - 1) * fa.ldout + j] = in_box(p, fa.tubes + (int64_t)(fa.T - 1) * 4 * D, 1, D) ? 1.0 : 0.0;
+            if (fa.R > 1) {
+                double q2 = 0.0;
+                bool finite = true;
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    const double t = p[k] - hdr[2 + k];
+                    q2 = fma(t, t, q2);
+                    finite = finite && (fabs(p[k]) < INFINITY);
+                }
+                const double g = -fa.kmul;
+                bool ok = finite && (g * q2 < SP_RANGE) && (2.0 * g * sqrt(q2 * hdr[1]) < SP_RANGE);
+                ok = ok && (sum[0] >= PI_TAU * cscale[0]);
+                if (!ok) {
+                    if (fa.build_list) fa.list[1 + atomicAdd(fa.list, 1)] = (int)j;
+                } else {
+#pragma unroll
+                    for (int r = 1; r < 16; ++r)
+                        if (r < fa.R) {
+                            const int t = fa.t0 + r - 1;
+                            fa.out[(int64_t)t * fa.ldout + j] =
+                                sr_step(p, fa.tubes + (int64_t)t * 4 * D, D, fa.problem, sum[r] / sum[0]);
+                        }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const char* base = reinterpret_cast<const char*>(tbase);
+        const int lines = nsplit * 16 * PI_TW * 8 / 128;
+        for (int l = tid; l < lines; l += 192)
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + (int64_t)l * 128) : "memory");
+    }
+}
+
 // ---- direct form (whole launch): distance by differences + table exp with IEEE range handling ---------------
 template <int D, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
@@ -550,13 +878,18 @@ __global__ void sr_last_row_kernel(const double* __restrict__ pts, int64_t m, in
 
 struct PackView {
     const double *hdr, *Xc, *coefE, *coefF;
+    // integer tensor-core engine: table, row scales, samples per K-block, coefficient digits per block and K-block
+    const double *tbl, *cscale, *xsD;
+    const uint8_t* coefD;
     int64_t n_pad;
     int nblk;
 };
 
 static inline int64_t pack_doubles(int64_t n, int d, int T) {
-    const int64_t n_pad = sp_npad(n);
-    return SP_HDR + n_pad * d + 2 * (int64_t)sp_blocks(T) * n_pad * SR_CP + 64;
+    const int64_t n_pad = sp_npad(n), nblk = sp_blocks(T);
+    const int64_t fp64_part = SP_HDR + n_pad * d + 2 * nblk * n_pad * SR_CP;
+    const int64_t i8_part = PI_TBL * PI_REP + nblk * 16 + n_pad * (d + 1) + nblk * (n_pad / PI_KB) * (4096 / 8);
+    return fp64_part + i8_part + 64;
 }
 static inline PackView pack_view(const double* pack, int64_t n, int d, int T) {
     PackView v;
@@ -566,6 +899,10 @@ static inline PackView pack_view(const double* pack, int64_t n, int d, int T) {
     v.Xc = pack + SP_HDR;
     v.coefE = v.Xc + v.n_pad * d;
     v.coefF = v.coefE + (int64_t)v.nblk * v.n_pad * SR_CP;
+    v.tbl = v.coefF + (int64_t)v.nblk * v.n_pad * SR_CP;  // every offset is a multiple of 2 doubles: 16-byte aligned
+    v.cscale = v.tbl + PI_TBL * PI_REP;
+    v.xsD = v.cscale + (int64_t)v.nblk * 16;
+    v.coefD = reinterpret_cast<const uint8_t*>(v.xsD + v.n_pad * (d + 1));
     return v;
 }
 static inline int predict_splits(int64_t n) { return (int)ceil_div(sp_npad(n), SP_SPLIT); }
@@ -582,6 +919,26 @@ static inline bool small_tiles(int64_t m, int splits, int pts_per_cta) {
 }
 
 template <int D>
+static int launch_i8(const PackView& v, const double* pts, int64_t m, int b, double* part, const FinishArgs& fa,
+                     cudaStream_t st) {
+    static std::atomic<bool> done[SOCKS_MAX_DEVICES];  // dynamic-smem opt-in is per device
+    constexpr int smem = 120 * 1024;                    // > half an SM: one CTA per SM (each allocates all of tensor memory)
+    static_assert(PiCfg<D>::SMEM_BYTES <= smem, "stage ring");
+    int dev = 0;
+    SOCKS_CUDA(cudaGetDevice(&dev));
+    const bool tracked = dev >= 0 && dev < SOCKS_MAX_DEVICES;
+    if (!tracked || !done[dev].load(std::memory_order_acquire)) {
+        SOCKS_CUDA(cudaFuncSetAttribute(sr_predict_i8_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (tracked) done[dev].store(true, std::memory_order_release);
+    }
+    const int nkb = (int)(v.n_pad / PI_KB);
+    const int splits = (int)ceil_div(v.n_pad, PI_SPLIT);
+    sr_predict_i8_kernel<D><<<dim3((unsigned)splits, (unsigned)ceil_div(m, PI_TW)), 192, smem, st>>>(
+        v.coefD + (int64_t)b * nkb * 4096, v.xsD, v.tbl, v.cscale + b * 16, nkb, pts, m, v.hdr, part, fa);
+    return SOCKS_OK;
+}
+
+template <int D>
 static void launch_tensor(const PackView& v, const double* X, int64_t n, const double* pts, int64_t m, double kmul,
                           int b, int R, int force_direct, int shape, double* part, int64_t ldp, int splits,
                           const FinishArgs& fa, cudaStream_t st) {
@@ -595,7 +952,9 @@ static void launch_tensor(const PackView& v, const double* X, int64_t n, const d
         v.Xc, cf, v.n_pad, pts, m, v.hdr, pscale, force_direct, part, fa)
     // 8 warps x 2 CTAs/SM (unroll 2) and 4 warps x 4 CTAs/SM (unroll 4): best of the shape sweep in
     // profiles/r2_predict_shape_sweep.json (all shapes within 4 %)
-    if (small) {
+    if (shape == 3) {  // integer tensor-core engine
+        if (!force_direct) launch_i8<D>(v, pts, m, b, part, fa, st);
+    } else if (small) {
         if (R > 8) SOCKS_FAST_LAUNCH(4, 4, true, 4); else SOCKS_FAST_LAUNCH(4, 4, false, 4);
     } else {
         if (R > 8) SOCKS_FAST_LAUNCH(8, 2, true, 2); else SOCKS_FAST_LAUNCH(8, 2, false, 2);
@@ -632,6 +991,13 @@ extern "C" int socks_sr_pack(const double* X, const double* w, const double* vf,
                                                                      const_cast<double*>(v.coefE),
                                                                      const_cast<double*>(v.coefF));
     SOCKS_CHECK_LAUNCH();
+    if (d <= 8) {  // operands of the integer tensor-core engine
+        pi_rowscale_kernel<<<(unsigned)(v.nblk * 16), 256, 0, st>>>(v.coefE, v.n_pad, const_cast<double*>(v.cscale));
+        pi_pack_kernel<<<(unsigned)ceil_div(std::max<int64_t>(v.n_pad, PI_TBL * PI_REP), 128), 128, 0, st>>>(
+            v.Xc, v.coefE, v.cscale, v.n_pad, d, v.nblk, kmul, const_cast<uint8_t*>(v.coefD), const_cast<double*>(v.xsD),
+            const_cast<double*>(v.tbl));
+        SOCKS_CHECK_LAUNCH();
+    }
     return SOCKS_OK;
 }
 
@@ -654,9 +1020,9 @@ extern "C" int socks_sr_predict_packed(const double* pack, const double* X, int6
     SOCKS_CHECK_ARG(T >= 1, 11);
     SOCKS_CHECK_ARG(ldout >= m, 13);
     SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 15) == 0, 14);
-    // variant: 0 auto | 1 FMA-pipe kernel | 2 direct form on the tensor cores | 3 / 4: auto with the CTA shape forced
-    // to 8 / 4 warps (measurement only)
-    SOCKS_CHECK_ARG(variant >= 0 && variant <= 4, 15);
+    // variant: 0 auto (integer tensor-core engine) | 1 FMA-pipe kernel | 2 direct form on the fp64 tensor cores |
+    // 3 / 4: factored fp64 kernel with the CTA shape forced to 8 / 4 warps | 5: factored fp64 kernel, shape by size
+    SOCKS_CHECK_ARG(variant >= 0 && variant <= 5, 15);
     if (m == 0) return SOCKS_OK;
     SOCKS_CHECK_ARG(pts != nullptr && out != nullptr, 7);
     const double kmul = divide ? 1.0 / scale : scale;
@@ -683,7 +1049,7 @@ extern "C" int socks_sr_predict_packed(const double* pack, const double* X, int6
     const int64_t ldp = round_up(m, 2);
     const int splits = predict_splits(n);
     const int force_direct = (variant == 2);
-    const int shape = variant == 3 ? 1 : (variant == 4 ? 2 : 0);
+    const int shape = variant == 3 ? 1 : (variant == 4 ? 2 : (variant == 5 ? 0 : 3));
     SOCKS_CHECK_ARG(ceil_div(m, 64) <= 65535, 8);  // point tiles ride on gridDim.y
     for (int b = 0; b < v.nblk; ++b) {
         const int t0 = b * (SOCKS_SR_ROWS - 1);
@@ -754,7 +1120,7 @@ extern "C" int socks_sr_predict(const double* X, const double* w, const double* 
     SOCKS_CHECK_ARG(T >= 1 && T <= 256, 13);
     SOCKS_CHECK_ARG(ldout >= m, 15);
     SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 15) == 0, 16);
-    SOCKS_CHECK_ARG(variant >= 0 && variant <= 4, 17);
+    SOCKS_CHECK_ARG(variant >= 0 && variant <= 5, 17);
     if (m == 0) return SOCKS_OK;
     SOCKS_CHECK_ARG(pts != nullptr && out != nullptr, 9);
     int rc = socks_sr_pack(X, w, vf, ldvf, n, d, scale, divide, T, work, stream);

@@ -12,7 +12,7 @@ for (M, N, K) in ((128, 64, 32), (128, 64, 128), (256, 128, 512), (1024, 512, 40
     A = torch.randint(-128, 128, (M, K), dtype=torch.int8, device="cuda")
     B = torch.randint(-128, 128, (N, K), dtype=torch.int8, device="cuda")
     want = (A.double() @ B.double().T).to(torch.int32)
-    for variant in (0, 1):
+    for variant in (0, 1, 2):  # 2: A operand written to tensor memory by tcgen05.st (TS form)
         C = torch.full((M, N), -7, dtype=torch.int32, device="cuda")
         _lib.call("socks_dev_i8gemm_check", A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, variant, dv.stream())
         torch.cuda.synchronize()

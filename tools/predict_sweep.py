@@ -11,7 +11,7 @@ import torch
 from socks_b200 import _device as dv, synthetic as syn
 from socks_b200.algorithms.reach.kernel_sr import KernelSR
 
-NAMES = {0: "auto (factored, shape by M)", 1: "FMA pipe + CUDA exp", 2: "direct form on DMMA (r1 kernel)",
+NAMES = {0: "auto: integer tensor-core engine (tcgen05 kind::i8)", 5: "factored fp64 form on DMMA, shape by M", 1: "FMA pipe + CUDA exp", 2: "direct form on DMMA (r1 kernel)",
          3: "factored, 8-warp CTAs x3, unroll 2", 4: "factored, 4-warp CTAs x5, unroll 2",
          10: "factored, 8 warps x3, unroll 4", 11: "factored, 8 warps x2, unroll 2", 12: "factored, 8 warps x2, unroll 4",
          13: "attribution (vs 11): +4 integer instr per value", 14: "attribution (vs 11): +1 FP64 add per value",
