@@ -167,8 +167,10 @@ int socks_sr_recursion(const double* B, int64_t n, int64_t m, int64_t ldb, const
  * call (pack at the head of `work`).
  * variant: 0 = automatic (factored exponent on the tensor cores, direct form for the columns / launches where a
  * factor could over- or underflow), 1 = FMA-pipe contraction with CUDA's exp, 2 = direct form on the tensor cores,
- * 3 / 4 = automatic with the CTA shape forced to 8 / 4 warps (measurement).  The sample axis is cut into fixed
- * 2048-sample splits summed in order, and the form chosen for a column depends only on that column and the fitted
+ * 3 / 4 = automatic with the CTA shape forced to 8 / 4 warps (measurement), 6 = the same contraction on the integer
+ * tensor cores (tcgen05.mma kind::i8 over fixed-point digits of the kernel values; agrees with 0 to ~3e-14, slower; kept
+ * as an independent cross-check).  The sample axis is cut into fixed
+ * 2048-sample splits (4096 for variant 6) summed in order, and the form chosen for a column depends only on that column and the fitted
  * state, so each output column is bit-identical however the test points are chunked or sharded. */
 int64_t socks_sr_pack_bytes(int64_t n, int d, int T);
 int socks_sr_pack(const double* X, const double* w, const double* vf, int64_t ldvf, int64_t n, int d, double scale,

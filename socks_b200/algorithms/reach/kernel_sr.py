@@ -36,8 +36,9 @@ class KernelSR:
     attributes `X`, `W`, `value_functions`.  `batch_size` is accepted for API parity and does not change
     results (test points are independent columns; the fused predict kernel streams them anyway)."""
 
-    # 0: automatic = integer tensor-core engine (tcgen05.mma kind::i8), 1: FMA-pipe contraction, 2: direct form on the fp64
-    # tensor cores, 5: factored form on the fp64 tensor cores (round-2 kernel; 3 / 4 force its CTA shape) -- csrc/sr_predict.cu
+    # 0: automatic (factored form on the fp64 tensor cores), 1: FMA-pipe contraction, 2: direct form on the fp64 tensor
+    # cores, 3 / 4: forced CTA shapes, 6: integer tensor-core engine (tcgen05.mma kind::i8; slower, kept as a cross-check)
+    # -- csrc/sr_predict.cu
     predict_variant = 0
 
     def __init__(self, time_horizon=None, constraint_tube=None, target_tube=None, problem="THT", kernel_fn=None,

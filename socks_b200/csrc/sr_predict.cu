@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 
 #include "exp_f64.cuh"
 #include "umma.cuh"
@@ -45,7 +46,8 @@ constexpr double SP_RANGE = 600.0;
 // Integer tensor-core engine (sr_predict_i8_kernel below)
 constexpr int PI_KB = 32;            // samples per K-block (one tcgen05.mma kind::i8 K step)
 constexpr int PI_SPLIT = 4096;       // samples per CTA = one exact int32 accumulation: 8 pairs * 255^2 * 4096 < 2^31
-constexpr int PI_STAGES = 4;         // K-blocks in flight (tensor-memory stages of the kernel-value digits)
+constexpr int PI_STAGES = 4;         // K-blocks in flight in tensor memory (stages of the kernel-value digits)
+constexpr int PI_LSTAGES = 16;       // K-blocks in flight in shared memory (coefficient digits + samples): hides the L2 latency
 constexpr int PI_TBL = 256;          // table of 2^(j/256) ...
 constexpr int PI_REP = 16;           // ... replicated 16x: lane l reads copy l % 16, so a lookup never bank-conflicts
 constexpr int PI_TW = 128;           // points per CTA = tensor-memory lanes
@@ -158,12 +160,12 @@ __device__ __forceinline__ int pi_core_offset(int r, int c) { return (r >> 3) * 
 // coefD[b][kb]: the B operand of one K-block, 128 rows x 32 bytes: row 16 t + r = digit t (byte 7 - t, unsigned) of
 // rint(coefE[b][i][r] / cscale[b][r] * 2^63), column = sample i % 32.
 // xsD[kb][i % 32] = (x'_i[0..d), cx_i) with cx_i = kmul |x'_i|^2 * 256/ln2: the sample's share of the exponent.
-// tbl[j][rep] = 2^(j/256).
+// tbl[j][rep] = 2^50 2^(j/256).
 __global__ void pi_pack_kernel(const double* __restrict__ Xc, const double* __restrict__ coefE,
                                const double* __restrict__ cscale, int64_t n_pad, int d, int nblk, double kmul,
                                uint8_t* __restrict__ coefD, double* __restrict__ xsD, double* __restrict__ tbl) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < PI_TBL * PI_REP) tbl[i] = exp2((double)(i / PI_REP) / PI_TBL);
+    if (i < PI_TBL * PI_REP) tbl[i] = exp2((double)(i / PI_REP) / PI_TBL) * 0x1p50;  // pre-scaled: see the producers
     if (i >= n_pad) return;
     const int64_t kb = i / PI_KB;
     const int e = (int)(i % PI_KB);
@@ -415,19 +417,26 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 // (once per fit), and every digit product is an exact int8 x int8 -> int32 MMA (tcgen05.mma kind::i8, accumulators in
 // tensor memory).  The FP64 pipe is left with the exponent and the exponential alone (10 instructions per pair), the 32
 // DMMA cycles per 32 pairs of the fp64 kernel are gone.
-//   * CTA = 128 points (thread = point = TMEM lane) x one fixed 4096-sample split; warps 0-3 produce, lane 0 of warp 4
-//     loads (bulk copies), lane 0 of warp 5 issues the MMAs.
+//   * CTA = 128 points (TMEM lane = point) x one fixed 4096-sample split; 4 PW producer warps (warp w serves the points
+//     of lane quarter w % 4 and the samples of slice w / 4 of every K-block: PW warps per scheduler hide the latencies of
+//     the dependent FP64 chain), then one loader lane (bulk copies) and one MMA-issuing lane.
 //   * Per K-block (32 samples) a producer thread evaluates its point against the 32 samples,
 //         a = ps . x' + cx_i + cp   (exponent in units of ln2/256, expanded form of -g |x - p|^2),
 //         2^(a/256) = 2^(k >> 8) * tbl[k & 255] * (1 + f (d1 + f (d2 + f d3))),   k = rint(a), f = a - k,
-//     converts to q = rint(k 2^62) (F2I.S64), transposes the bytes of 4 q's at a time (PRMT) and writes the 8 digit rows of
-//     its lane straight into tensor memory (tcgen05.st): the A operand never touches shared memory.
+//     takes the 62-bit fixed-point q = k(x, p) 2^62 out of the mantissa bits by shifts (no F2I/I2F: 64-bit conversions run
+//     at one lane per clock and scheduler), transposes the bytes of 4 q's at a time (PRMT) and writes the 8 digit rows
+//     of its lane straight into tensor memory (tcgen05.st): the A operand never touches shared memory.
 //   * The B operand of the K-block stacks the 8 coefficient digits of the 16 rows: 128 "columns" n = 16 t + r.  The MMA of
 //     kernel digit s targets D columns 16 s .. 16 s + 127, so the product (s, t) lands in group g = s + t at columns
 //     16 g + r: 8 MMAs (128 x 128 x 32) per K-block accumulate all 64 digit pairs into 15 groups of 16 columns.
 //   * Epilogue: groups 0..9 -> exact 64-bit integer merge -> fp64 -> x cscale[r] -> partial sums of this split; the last
 //     CTA of the tile sums the splits in index order and finishes the column exactly like the fp64 kernel.  Integer sums
 //     are exact, the split boundaries are fixed: every column is bit-identical however the points are chunked or sharded.
+// MEASURED (configs[1], 250 000 points): 9.5 ms against 8.0 ms for the fp64 kernel above, so this engine is NOT the default
+// (variant 6).  The contraction is indeed gone from the FP64 pipe (tensor pipe 23 % busy, FP64 29 %), but every
+// instruction that goes to a 16-lane pipe (FP64, ALU, IMAD) holds the scheduler's dispatch port for two cycles, and the
+// digit extraction + byte transposes + exponential are ~35 such instructions per pair-warp = 70 cycles against the 60
+// of the fp64 kernel (ncu: alu 45 % + fp64 29 % + lsu 15 % + fma 8 % + adu 6 % = 103 % of the issue bandwidth).
 // A column stands only if the expanded exponent is accurate for it (same range test as the factored fp64 form), the
 // point is finite and its normaliser is >= 2^-14 of the scale (then the fixed-point error is < 1e-10 relative); every other
 // column is queued for the direct form, which reproduces numpy's underflow / 0/0 behaviour.
@@ -436,12 +445,12 @@ struct PiCfg {
     static constexpr int XS_BYTES = PI_KB * (D + 1) * 8;
     static constexpr int STAGE_BYTES = 4096 + XS_BYTES;  // coefficient digits + samples of one K-block
     static constexpr int TBL_BYTES = PI_TBL * PI_REP * 8;
-    static constexpr int NBAR = 3 * PI_STAGES + 2;
-    static constexpr int SMEM_BYTES = TBL_BYTES + PI_STAGES * STAGE_BYTES + NBAR * 8 + 16;
+    static constexpr int NBAR = 2 * PI_LSTAGES + 2 * PI_STAGES + 2;
+    static constexpr int SMEM_BYTES = TBL_BYTES + PI_LSTAGES * STAGE_BYTES + NBAR * 8 + 16;
 };
 
-template <int D>
-__global__ void __launch_bounds__(192, 1)
+template <int D, int PW>  // PW producer warps per 32 points: each evaluates 32 / PW samples of a K-block
+__global__ void __launch_bounds__(128 * PW + 64, 1)
     sr_predict_i8_kernel(const uint8_t* __restrict__ coefD, const double* __restrict__ xsD, const double* __restrict__ tblG,
                          const double* __restrict__ cscale, int nkb_total, const double* __restrict__ pts, int64_t m,
                          const double* __restrict__ hdr, double* __restrict__ part, FinishArgs fa) {
@@ -450,8 +459,9 @@ __global__ void __launch_bounds__(192, 1)
     extern __shared__ __align__(1024) uint8_t pi_smem[];
     const double* tbl = reinterpret_cast<const double*>(pi_smem);
     uint8_t* stages = pi_smem + Cfg::TBL_BYTES;
-    uint64_t* ld_full = reinterpret_cast<uint64_t*>(stages + PI_STAGES * Cfg::STAGE_BYTES);
-    uint64_t* a_full = ld_full + PI_STAGES;
+    uint64_t* ld_full = reinterpret_cast<uint64_t*>(stages + PI_LSTAGES * Cfg::STAGE_BYTES);
+    uint64_t* ld_empty = ld_full + PI_LSTAGES;
+    uint64_t* a_full = ld_empty + PI_LSTAGES;
     uint64_t* empty = a_full + PI_STAGES;
     uint64_t* acc_full = empty + PI_STAGES;
     uint64_t* tbl_full = acc_full + 1;
@@ -464,9 +474,12 @@ __global__ void __launch_bounds__(192, 1)
     const int nk = min(nkb_total - kb0, PI_SPLIT / PI_KB);
     if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
     if (tid == 32) {
-        for (int i = 0; i < PI_STAGES; ++i) {
+        for (int i = 0; i < PI_LSTAGES; ++i) {
             umma::mbar_init(ld_full + i, 1);
-            umma::mbar_init(a_full + i, 128);
+            umma::mbar_init(ld_empty + i, 1);
+        }
+        for (int i = 0; i < PI_STAGES; ++i) {
+            umma::mbar_init(a_full + i, 128 * PW);
             umma::mbar_init(empty + i, 1);
         }
         umma::mbar_init(acc_full, 1);
@@ -479,44 +492,49 @@ __global__ void __launch_bounds__(192, 1)
     const uint32_t tmem = *tmem_slot;
     constexpr uint32_t A_COL = 256;  // kernel-value digits: stage st at columns 256 + 64 st, digit s at + 8 s
 
-    if (warp == 4) {
+    if (warp == 4 * PW) {
         if (lane == 0) {
             umma::mbar_arrive_expect_tx(tbl_full, Cfg::TBL_BYTES);
             umma::bulk_g2s(pi_smem, tblG, Cfg::TBL_BYTES, tbl_full);
             for (int i = 0; i < nk; ++i) {
-                const int st = i % PI_STAGES, round = i / PI_STAGES;
-                if (round > 0) umma::mbar_wait(empty + st, (uint32_t)(round - 1) & 1u);
+                const int st = i % PI_LSTAGES, round = i / PI_LSTAGES;
+                if (round > 0) umma::mbar_wait(ld_empty + st, (uint32_t)(round - 1) & 1u);
                 uint8_t* dst = stages + st * Cfg::STAGE_BYTES;
                 umma::mbar_arrive_expect_tx(ld_full + st, Cfg::STAGE_BYTES);
                 umma::bulk_g2s(dst, coefD + (int64_t)(kb0 + i) * 4096, 4096, ld_full + st);
                 umma::bulk_g2s(dst + 4096, xsD + (int64_t)(kb0 + i) * (PI_KB * (D + 1)), Cfg::XS_BYTES, ld_full + st);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 4 * PW + 1) {
         if (lane == 0) {
             const uint32_t idesc = umma::idesc_i8(128, 128, 0, 0);  // unsigned digits
             for (int i = 0; i < nk; ++i) {
                 const int st = i % PI_STAGES, round = i / PI_STAGES;
-                umma::mbar_wait(ld_full + st, (uint32_t)round & 1u);
+                const int ls = i % PI_LSTAGES, lround = i / PI_LSTAGES;
+                umma::mbar_wait(ld_full + ls, (uint32_t)lround & 1u);
                 umma::mbar_wait(a_full + st, (uint32_t)round & 1u);
                 umma::tc_fence_after();
-                const uint64_t db = umma::smem_desc_kmajor_noswizzle(umma::smem_u32(stages + st * Cfg::STAGE_BYTES), 128, 256);
+                const uint64_t db = umma::smem_desc_kmajor_noswizzle(umma::smem_u32(stages + ls * Cfg::STAGE_BYTES), 128, 256);
 #pragma unroll
                 for (int sd = 0; sd < 8; ++sd)
                     umma::mma_i8_ts(tmem + (uint32_t)(16 * sd), tmem + A_COL + (uint32_t)(64 * st + 8 * sd), db, idesc, 1u);
                 umma::mma_commit(empty + st);
+                umma::mma_commit(ld_empty + ls);  // (the producers read the samples of this stage before they arrived)
             }
             umma::mma_commit(acc_full);
         }
     } else {
-        // ---- producers: thread = point
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-        {   // zero the 15 accumulator groups of this lane (every MMA accumulates)
+        // ---- producers: thread = (point, sample slice)
+        constexpr int NS = PI_KB / PW, NW = NS / 4;  // samples / digit words of this warp per K-block
+        const int quarter = warp & 3, sub = warp >> 2;
+        const int col = quarter * 32 + lane;          // point of the tile = TMEM lane
+        const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+        if (sub == 0) {  // zero the 15 accumulator groups of this lane (every MMA accumulates)
             const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int c = 0; c < 240; c += 8) umma::tmem_st8(trow + (uint32_t)c, z);
         }
-        const int64_t j = min(tile * PI_TW + tid, m - 1);
+        const int64_t j = min(tile * PI_TW + col, m - 1);
         const double L = -fa.kmul * (PI_TBL / 0.693147180559945309417232121458176568);  // g * 256/ln2
         double ps[D], cp = 0.0;
 #pragma unroll
@@ -533,65 +551,71 @@ __global__ void __launch_bounds__(192, 1)
         umma::mbar_wait(tbl_full, 0);
         for (int i = 0; i < nk; ++i) {
             const int st = i % PI_STAGES, round = i / PI_STAGES;
-            umma::mbar_wait(ld_full + st, (uint32_t)round & 1u);
-            if (round > 0) {
-                umma::mbar_wait(empty + st, (uint32_t)(round - 1) & 1u);  // the MMAs that read this TMEM stage are done
-                umma::tc_fence_after();
-            }
-            const double* xs = reinterpret_cast<const double*>(stages + st * Cfg::STAGE_BYTES + 4096);
-            uint32_t dig[8][8];  // [digit][word = 4 samples]
+            const int ls = i % PI_LSTAGES, lround = i / PI_LSTAGES;
+            umma::mbar_wait(ld_full + ls, (uint32_t)lround & 1u);
+            const double* xs = reinterpret_cast<const double*>(stages + ls * Cfg::STAGE_BYTES + 4096) + sub * NS * (D + 1);
+            uint32_t dig[8][NW];  // [digit][word = 4 samples]
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t qh[16], ql[16];
+            for (int w = 0; w < NW; ++w) {
+                uint32_t qh[4], ql[4];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const double* x = xs + (c * 16 + e) * (D + 1);
+                for (int e = 0; e < 4; ++e) {
+                    const double* x = xs + (w * 4 + e) * (D + 1);
                     double a = x[D];
 #pragma unroll
                     for (int k = 0; k < D; ++k) a = fma(ps[k], x[k], a);
                     a += cp;
                     const double t = a + kMagic;
                     const int ki = __double2loint(t);
-                    const double f = a - __int2double_rn(ki);
-                    const double tb = *reinterpret_cast<const double*>(tb_lane + ((ki & (PI_TBL - 1)) << 7));
+                    const double f = a - (t - kMagic);  // no I2F / F2I below: 64-bit conversions run at 1 lane/clk/SMSP
+                    const double tb = *reinterpret_cast<const double*>(tb_lane + ((ki & (PI_TBL - 1)) << 7));  // 2^50 2^(j/256)
                     double pl = fma(f, d3, d2);
                     pl = fma(f, pl, d1);
-                    pl = pl * f;
-                    const double res = fma(tb, pl, tb);
-                    const int e2 = max(ki >> 8, -1000) + 62;  // k 2^62; values below 2^-62 round to 0
-                    const long long q = __double2ll_rn(__hiloint2double(__double2hiint(res) + (e2 << 20), __double2loint(res)));
-                    qh[e] = (uint32_t)((unsigned long long)q >> 32);
-                    ql[e] = (uint32_t)q;
+                    pl = fma(f, pl, 1.0);
+                    // Y = 2^52 + rint(2^50 tbl (1 + p)): the mantissa field IS the 51-bit integer M; k 2^62 = (M << 12) >> r
+                    const double y = fma(tb, pl, 4503599627370496.0);
+                    const uint32_t hi12 = __funnelshift_l((uint32_t)__double2loint(y), (uint32_t)__double2hiint(y), 12);
+                    const uint32_t lo12 = (uint32_t)__double2loint(y) << 12;
+                    const int r = min(-(ki >> 8), 63);  // values below 2^-63 shift out to 0; ki <= 0 up to rounding noise
+                    const uint32_t fa_ = __funnelshift_r(lo12, hi12, r), fb_ = __funnelshift_r(hi12, 0u, r);  // shift mod 32
+                    qh[e] = (r >= 32) ? 0u : fb_;
+                    ql[e] = (r >= 32) ? fb_ : fa_;
                 }
                 // bytes of 4 q's -> one word per digit (4 x 4 byte transposes)
-#pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) {
-                    const int w = c * 4 + g4;
-                    {
-                        const uint32_t a01 = __byte_perm(qh[4 * g4], qh[4 * g4 + 1], 0x5140), b01 = __byte_perm(qh[4 * g4], qh[4 * g4 + 1], 0x7362);
-                        const uint32_t a23 = __byte_perm(qh[4 * g4 + 2], qh[4 * g4 + 3], 0x5140), b23 = __byte_perm(qh[4 * g4 + 2], qh[4 * g4 + 3], 0x7362);
-                        dig[3][w] = __byte_perm(a01, a23, 0x5410);  // byte 4 of q
-                        dig[2][w] = __byte_perm(a01, a23, 0x7632);  // byte 5
-                        dig[1][w] = __byte_perm(b01, b23, 0x5410);  // byte 6
-                        dig[0][w] = __byte_perm(b01, b23, 0x7632);  // byte 7 (top digit)
-                    }
-                    {
-                        const uint32_t a01 = __byte_perm(ql[4 * g4], ql[4 * g4 + 1], 0x5140), b01 = __byte_perm(ql[4 * g4], ql[4 * g4 + 1], 0x7362);
-                        const uint32_t a23 = __byte_perm(ql[4 * g4 + 2], ql[4 * g4 + 3], 0x5140), b23 = __byte_perm(ql[4 * g4 + 2], ql[4 * g4 + 3], 0x7362);
-                        dig[7][w] = __byte_perm(a01, a23, 0x5410);  // byte 0
-                        dig[6][w] = __byte_perm(a01, a23, 0x7632);
-                        dig[5][w] = __byte_perm(b01, b23, 0x5410);
-                        dig[4][w] = __byte_perm(b01, b23, 0x7632);  // byte 3
-                    }
+                {
+                    const uint32_t a01 = __byte_perm(qh[0], qh[1], 0x5140), b01 = __byte_perm(qh[0], qh[1], 0x7362);
+                    const uint32_t a23 = __byte_perm(qh[2], qh[3], 0x5140), b23 = __byte_perm(qh[2], qh[3], 0x7362);
+                    dig[3][w] = __byte_perm(a01, a23, 0x5410);  // byte 4 of q
+                    dig[2][w] = __byte_perm(a01, a23, 0x7632);  // byte 5
+                    dig[1][w] = __byte_perm(b01, b23, 0x5410);  // byte 6
+                    dig[0][w] = __byte_perm(b01, b23, 0x7632);  // byte 7 (top digit)
+                }
+                {
+                    const uint32_t a01 = __byte_perm(ql[0], ql[1], 0x5140), b01 = __byte_perm(ql[0], ql[1], 0x7362);
+                    const uint32_t a23 = __byte_perm(ql[2], ql[3], 0x5140), b23 = __byte_perm(ql[2], ql[3], 0x7362);
+                    dig[7][w] = __byte_perm(a01, a23, 0x5410);  // byte 0
+                    dig[6][w] = __byte_perm(a01, a23, 0x7632);
+                    dig[5][w] = __byte_perm(b01, b23, 0x5410);
+                    dig[4][w] = __byte_perm(b01, b23, 0x7632);  // byte 3
                 }
             }
+            if (round > 0) {
+                umma::mbar_wait(empty + st, (uint32_t)(round - 1) & 1u);  // the MMAs that read this TMEM stage are done
+                umma::tc_fence_after();
+            }
 #pragma unroll
-            for (int sd = 0; sd < 8; ++sd) umma::tmem_st8(trow + A_COL + (uint32_t)(64 * st + 8 * sd), dig[sd]);
+            for (int sd = 0; sd < 8; ++sd) {
+                const uint32_t ta = trow + A_COL + (uint32_t)(64 * st + 8 * sd + sub * NW);
+                if constexpr (NW == 8) umma::tmem_st8(ta, dig[sd]);
+                else if constexpr (NW == 4) umma::tmem_st4(ta, dig[sd]);
+                else umma::tmem_st2(ta, dig[sd]);
+            }
             umma::tmem_st_wait();
             umma::tc_fence_before();
             umma::mbar_arrive(a_full + st);
         }
         // ---- epilogue of the split: groups -> fp64 partial sums
+        if (sub == 0) {
         umma::mbar_wait(acc_full, 0);
         umma::tc_fence_after();
         double val[16];
@@ -612,7 +636,8 @@ __global__ void __launch_bounds__(192, 1)
         }
         double* tpart = part + (tile * nsplit + split) * (int64_t)(16 * PI_TW);
 #pragma unroll
-        for (int r = 0; r < 16; ++r) tpart[r * PI_TW + tid] = val[r] * cscale[r];
+        for (int r = 0; r < 16; ++r) tpart[r * PI_TW + col] = val[r] * cscale[r];
+        }
     }
     umma::tc_fence_before();
     __threadfence();
@@ -667,7 +692,7 @@ __global__ void __launch_bounds__(192, 1)
     {
         const char* base = reinterpret_cast<const char*>(tbase);
         const int lines = nsplit * 16 * PI_TW * 8 / 128;
-        for (int l = tid; l < lines; l += 192)
+        for (int l = tid; l < lines; l += 128 * PW + 64)
             asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + (int64_t)l * 128) : "memory");
     }
 }
@@ -918,23 +943,35 @@ static inline bool small_tiles(int64_t m, int splits, int pts_per_cta) {
     return ceil_div(m, pts_per_cta) * splits < 148 * 24;
 }
 
+static int g_pi_pw = 4;  // producer warps per lane quarter (2 or 4); SOCKS_PREDICT_I8_PW overrides (measurement)
+
 template <int D>
 static int launch_i8(const PackView& v, const double* pts, int64_t m, int b, double* part, const FinishArgs& fa,
                      cudaStream_t st) {
     static std::atomic<bool> done[SOCKS_MAX_DEVICES];  // dynamic-smem opt-in is per device
-    constexpr int smem = 120 * 1024;                    // > half an SM: one CTA per SM (each allocates all of tensor memory)
+    constexpr int smem = 160 * 1024;                    // > half an SM: one CTA per SM (each allocates all of tensor memory)
     static_assert(PiCfg<D>::SMEM_BYTES <= smem, "stage ring");
     int dev = 0;
     SOCKS_CUDA(cudaGetDevice(&dev));
     const bool tracked = dev >= 0 && dev < SOCKS_MAX_DEVICES;
     if (!tracked || !done[dev].load(std::memory_order_acquire)) {
-        SOCKS_CUDA(cudaFuncSetAttribute(sr_predict_i8_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SOCKS_CUDA(cudaFuncSetAttribute((sr_predict_i8_kernel<D, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SOCKS_CUDA(cudaFuncSetAttribute((sr_predict_i8_kernel<D, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         if (tracked) done[dev].store(true, std::memory_order_release);
     }
+    static const int pw_env = [] {
+        const char* e = getenv("SOCKS_PREDICT_I8_PW");
+        return e ? atoi(e) : 0;
+    }();
+    if (pw_env == 2 || pw_env == 4) g_pi_pw = pw_env;
     const int nkb = (int)(v.n_pad / PI_KB);
     const int splits = (int)ceil_div(v.n_pad, PI_SPLIT);
-    sr_predict_i8_kernel<D><<<dim3((unsigned)splits, (unsigned)ceil_div(m, PI_TW)), 192, smem, st>>>(
-        v.coefD + (int64_t)b * nkb * 4096, v.xsD, v.tbl, v.cscale + b * 16, nkb, pts, m, v.hdr, part, fa);
+    if (g_pi_pw == 2)
+        sr_predict_i8_kernel<D, 2><<<dim3((unsigned)splits, (unsigned)ceil_div(m, PI_TW)), 128 * 2 + 64, smem, st>>>(
+            v.coefD + (int64_t)b * nkb * 4096, v.xsD, v.tbl, v.cscale + b * 16, nkb, pts, m, v.hdr, part, fa);
+    else
+        sr_predict_i8_kernel<D, 4><<<dim3((unsigned)splits, (unsigned)ceil_div(m, PI_TW)), 128 * 4 + 64, smem, st>>>(
+            v.coefD + (int64_t)b * nkb * 4096, v.xsD, v.tbl, v.cscale + b * 16, nkb, pts, m, v.hdr, part, fa);
     return SOCKS_OK;
 }
 
@@ -1020,9 +1057,10 @@ extern "C" int socks_sr_predict_packed(const double* pack, const double* X, int6
     SOCKS_CHECK_ARG(T >= 1, 11);
     SOCKS_CHECK_ARG(ldout >= m, 13);
     SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 15) == 0, 14);
-    // variant: 0 auto (integer tensor-core engine) | 1 FMA-pipe kernel | 2 direct form on the fp64 tensor cores |
-    // 3 / 4: factored fp64 kernel with the CTA shape forced to 8 / 4 warps | 5: factored fp64 kernel, shape by size
-    SOCKS_CHECK_ARG(variant >= 0 && variant <= 5, 15);
+    // variant: 0 auto (factored form on the fp64 tensor cores, CTA shape by size) | 1 FMA-pipe kernel | 2 direct form on
+    // the fp64 tensor cores | 3 / 4: auto with the CTA shape forced to 8 / 4 warps (measurement only) | 5: same as 0 |
+    // 6: integer tensor-core engine (tcgen05.mma kind::i8; correct to 3e-14 of variant 0 but 20 % slower: see DESIGN 4.5)
+    SOCKS_CHECK_ARG(variant >= 0 && variant <= 6, 15);
     if (m == 0) return SOCKS_OK;
     SOCKS_CHECK_ARG(pts != nullptr && out != nullptr, 7);
     const double kmul = divide ? 1.0 / scale : scale;
@@ -1049,7 +1087,7 @@ extern "C" int socks_sr_predict_packed(const double* pack, const double* X, int6
     const int64_t ldp = round_up(m, 2);
     const int splits = predict_splits(n);
     const int force_direct = (variant == 2);
-    const int shape = variant == 3 ? 1 : (variant == 4 ? 2 : (variant == 5 ? 0 : 3));
+    const int shape = variant == 3 ? 1 : (variant == 4 ? 2 : (variant == 6 ? 3 : 0));
     SOCKS_CHECK_ARG(ceil_div(m, 64) <= 65535, 8);  // point tiles ride on gridDim.y
     for (int b = 0; b < v.nblk; ++b) {
         const int t0 = b * (SOCKS_SR_ROWS - 1);
@@ -1120,7 +1158,7 @@ extern "C" int socks_sr_predict(const double* X, const double* w, const double* 
     SOCKS_CHECK_ARG(T >= 1 && T <= 256, 13);
     SOCKS_CHECK_ARG(ldout >= m, 15);
     SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 15) == 0, 16);
-    SOCKS_CHECK_ARG(variant >= 0 && variant <= 5, 17);
+    SOCKS_CHECK_ARG(variant >= 0 && variant <= 6, 17);
     if (m == 0) return SOCKS_OK;
     SOCKS_CHECK_ARG(pts != nullptr && out != nullptr, 9);
     int rc = socks_sr_pack(X, w, vf, ldvf, n, d, scale, divide, T, work, stream);

@@ -18,6 +18,8 @@ __device__ __forceinline__ void mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint
 }
 
 // mode 0: SS; mode 1: TS (A in TMEM columns 448..); mode 2: SS but all MMAs share ONE A tile address (tests operand caching)
+// mode 3: TS with the D window SHIFTED by 16 columns from one MMA to the next (overlapping accumulator windows, 8 per K-block)
+// mode 4: TS, 8 MMAs per K-block all on the SAME D window (reference for mode 3)
 template <int N, int MODE>
 __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -46,7 +48,9 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, long long* out)
                 const uint64_t da = umma::smem_desc_kmajor_noswizzle(sA + (MODE == 2 ? 0 : s) * 4096, 128, 256);
                 const uint64_t db = umma::smem_desc_kmajor_noswizzle(sB + t * (N * 32), 128, 256);
                 const uint32_t d = tmem + (uint32_t)((j % NACC) * N);
-                if (MODE == 1) mma_i8_ts(d, tmem + 448 + s * 8, db, idesc, (it | j) ? 1u : 0u);
+                if (MODE == 3) mma_i8_ts(tmem + 16 * (j % 8), tmem + 448 + (j % 8) * 8, db, idesc, 1u);
+                else if (MODE == 4) mma_i8_ts(tmem, tmem + 448 + (j % 8) * 8, db, idesc, 1u);
+                else if (MODE == 1) mma_i8_ts(d, tmem + 448 + s * 8, db, idesc, (it | j) ? 1u : 0u);
                 else umma::mma_i8(d, da, db, idesc, (it | j) ? 1u : 0u);
             }
         }
@@ -90,5 +94,7 @@ int main() {
     run<64, 2>("SS, one A tile for every MMA", dout);
     run<64, 1>("TS (A from tensor memory)", dout);
     run<128, 1>("TS (A from tensor memory)", dout);
+    run<128, 3>("TS, D window shifted by 16 columns per MMA (overlapping windows)", dout);
+    run<128, 4>("TS, same D window for every MMA", dout);
     return 0;
 }
