@@ -22,12 +22,16 @@ int socks_dev_potf2_phases(double* A, int64_t lda, double* dinv, int* info_dev, 
 int socks_dev_i8gemm_check(const void* A, const void* B, void* C, int M, int N, int K, int variant,
                            socks_stream_t stream);
 /* FP64-equivalent C (m x n) -= A (m x K) B (n x K)^T on the integer tensor cores (Ozaki scheme: 7 balanced base-256
- * digits per operand, 28 exact int8 GEMMs on tcgen05.mma kind::i8, fp64 recombination); m, n % 128 == 0, K % 32 == 0,
- * K <= 16384; syrk != 0: B = A.  The factorisation's trailing updates run through the same kernels. */
+ * digits per operand, 28 exact int8 GEMMs on tcgen05.mma kind::i8, fp64 recombination); m, n % 128 == 0, K % 32 == 0
+ * (longer K than one int32 accumulation chunk is handed over chunk by chunk); syrk bit 0: B = A, bit 1: 8 digits
+ * (36 GEMMs, 256x smaller truncation error).  The factorisation's trailing updates (7 digits) and the merges of
+ * inv(L) (8 digits) run through the same kernels. */
 int64_t socks_dev_ozaki_gemm_work_bytes(int64_t m, int64_t n, int64_t K);
 int socks_dev_ozaki_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t m,
                             int64_t n, int64_t K, int syrk, int lower_only, void* work, socks_stream_t stream);
-/* Block-column width of socks_potrf_inv's look-ahead factorisation (see socks_b200.h); returns the previous value. */
+/* Block-column width of socks_potrf_inv's look-ahead factorisation (multiple of 128, 0 = pure recursion); returns the
+ * previous value.  Negative codes switch measurement variants: -1/-2 half-width tail off/on, -3/-4 trailing updates on
+ * FP64 DMMA / integer tensor cores, -5/-6 large merges likewise, -7/-8 seven / eight digits in the merges. */
 int socks_potrf_inv_set_block(int nb);
 
 #ifdef __cplusplus

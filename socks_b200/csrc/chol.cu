@@ -509,6 +509,10 @@ static Lookahead* lookahead_for_device(int* rc_out) {
 }
 
 static int g_potrf_ozaki = 1;  // 1: trailing updates on the integer tensor cores (csrc/ozaki.cu), 0: FP64 DMMA GEMM
+// Digits of the merges: the entries of inv(L) span many orders of magnitude WITHIN a row, and the digit scheme truncates
+// relative to the row maximum; with 7 digits the residual |W G - I| rose from 3e-9 (DMMA) to 4e-7 at N = 20k, with 8 it is
+// back at the DMMA level (tools/inverse_residual.py).  The trailing updates (rows of L21: narrow range) keep 7.
+static int g_potrf_merge_digits = 8;
 static int g_potrf_ozaki_merge = 1;  // 1: the large merges of inv(L) on the integer tensor cores as well
 static int g_potrf_tail = 1;   // 1: half-width block columns over the last 4 NB columns
 static int g_potrf_nb = 1024;  // block-column width of the look-ahead factorisation (multiple of 128; 0 = pure recursion)
@@ -535,19 +539,20 @@ static void run_merge(CholCtx& cx, double* M, int64_t ldm, const int64_t* bnd, c
     double* M21 = M + o2 * ldm + o1;  // holds L21
     double* M22 = M + o2 * ldm + o2;
     const int64_t kmax = std::max(n1, n2);
-    if (digits && ozaki_operand_bytes(n2, kmax) + ozaki_operand_bytes(n1, kmax) <= digit_bytes) {
+    const int S = g_potrf_merge_digits;
+    if (digits && ozaki_operand_bytes(n2, kmax, S) + ozaki_operand_bytes(n1, kmax, S) <= digit_bytes) {
         int rc = SOCKS_OK;
         // T = M22 L21: A = rows of M22 (lower triangular), B = columns of L21, K = n2
         uint8_t* da = digits;
-        uint8_t* db = digits + ozaki_operand_bytes(n2, n2);
-        if (!rc) rc = ozaki_slice_operand(M22, n2, n2, ldm, 0, 1, da, cx.st);
-        if (!rc) rc = ozaki_slice_operand(M21, n1, n2, ldm, 1, 0, db, cx.st);
-        if (!rc) rc = ozaki_gemm_nt_sliced(da, n2, 0, db, n1, 0, n2, work, n1, n2, n1, 0, 1, 1, 0, cx.st);
+        uint8_t* db = digits + ozaki_operand_bytes(n2, n2, S);
+        if (!rc) rc = ozaki_slice_operand(M22, n2, n2, ldm, 0, 1, da, S, cx.st);
+        if (!rc) rc = ozaki_slice_operand(M21, n1, n2, ldm, 1, 0, db, S, cx.st);
+        if (!rc) rc = ozaki_gemm_nt_sliced(da, n2, 0, db, n1, 0, n2, work, n1, n2, n1, 0, 1, 1, 0, S, cx.st);
         // M21 = -T M11: A = rows of T, B = columns of M11 (zero above the diagonal: k >= j), K = n1
-        db = digits + ozaki_operand_bytes(n2, n1);
-        if (!rc) rc = ozaki_slice_operand(work, n2, n1, n1, 0, 0, da, cx.st);
-        if (!rc) rc = ozaki_slice_operand(M11, n1, n1, ldm, 1, 2, db, cx.st);
-        if (!rc) rc = ozaki_gemm_nt_sliced(da, n2, 0, db, n1, 0, n1, M21, ldm, n2, n1, 0, 2, 0, 1, cx.st);
+        db = digits + ozaki_operand_bytes(n2, n1, S);
+        if (!rc) rc = ozaki_slice_operand(work, n2, n1, n1, 0, 0, da, S, cx.st);
+        if (!rc) rc = ozaki_slice_operand(M11, n1, n1, ldm, 1, 2, db, S, cx.st);
+        if (!rc) rc = ozaki_gemm_nt_sliced(da, n2, 0, db, n1, 0, n1, M21, ldm, n2, n1, 0, 2, 0, 1, S, cx.st);
         if (rc) cx.note(cudaErrorUnknown);
         return;
     }
@@ -564,7 +569,7 @@ static inline int64_t trtri_scratch_doubles(int64_t np) {
 // ... and the two digit operands of the largest merge (rows n1 + n2 <= np, K <= max(n1, n2) <= np/2 + 2 block columns)
 static inline int64_t potrf_digit_bytes(int64_t np) {
     const int64_t kmax = std::min<int64_t>(np, np / 2 + 2048);
-    return std::max(ozaki_operand_bytes(np, 2048), 2 * ozaki_operand_bytes((np + 1) / 2 + 2048, kmax)) + 2048;
+    return std::max(ozaki_operand_bytes(np, 2048, 7), 2 * ozaki_operand_bytes((np + 1) / 2 + 2048, kmax, 8)) + 2048;
 }
 
 static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, int64_t np, double* work, int* info,
@@ -619,11 +624,11 @@ static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, i
         // next block column first (rows rem x cols b1), then the rest of the trailing lower triangle
         if (use_ozaki) {
             // A22 -= L21 L21^T on the integer tensor cores: the panel is split into digits once, both updates read them
-            if ((rc = ozaki_slice_operand(L21, rem, bk, ldm, 0, 0, digits, s1))) return rc;
-            if ((rc = ozaki_gemm_nt_sliced(digits, rem, 0, digits, rem, 0, bk, A22, lda, rem, b1, 1, 0, 0, 0, s1))) return rc;
+            if ((rc = ozaki_slice_operand(L21, rem, bk, ldm, 0, 0, digits, 7, s1))) return rc;
+            if ((rc = ozaki_gemm_nt_sliced(digits, rem, 0, digits, rem, 0, bk, A22, lda, rem, b1, 1, 0, 0, 0, 7, s1))) return rc;
             c1.note(cudaEventRecord(la->ev_col, s1));
             if (rem > b1 && (rc = ozaki_gemm_nt_sliced(digits, rem, b1 / LF, digits, rem, b1 / LF, bk, A22 + b1 * lda + b1,
-                                                       lda, rem - b1, rem - b1, 1, 0, 0, 0, s1)))
+                                                       lda, rem - b1, rem - b1, 1, 0, 0, 0, 7, s1)))
                 return rc;
         } else {
             c1.note(gemm_f64<false, true>(L21, ldm, L21, ldm, A22, lda, rem, b1, bk, -1.0, 1.0, 0, 1, s1));
@@ -768,7 +773,8 @@ extern "C" int socks_potrf_inv_set_block(int nb) {
                    // -5 / -6: large merges of the inverse on FP64 DMMA / on the integer tensor cores
         if (nb >= -2) g_potrf_tail = (nb == -2);
         else if (nb >= -4) g_potrf_ozaki = (nb == -4);
-        else g_potrf_ozaki_merge = (nb == -6);
+        else if (nb >= -6) g_potrf_ozaki_merge = (nb == -6);
+        else g_potrf_merge_digits = (nb == -7) ? 7 : 8;  // -7 / -8: 7 / 8 digits in the merges
         return old;
     }
     if (nb % LF == 0) g_potrf_nb = nb;

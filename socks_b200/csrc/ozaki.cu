@@ -286,7 +286,12 @@ static inline int64_t pad_to(int64_t v, int64_t a) { return (v + a - 1) / a * a;
 // layout: Dop[tile][kb][s][128 rows x 32 B core-matrix layout].
 namespace socks {
 
-constexpr int OG_S = 7;
+constexpr int OG_S = 7;  // digits of the trailing updates; the merges of inv(L) take 8 (see chol.cu)
+
+__device__ __forceinline__ double og_pow2(int e) {  // 2^e, e in the normal range (folds to a constant)
+    return __longlong_as_double((long long)(1023 + e) << 52);
+}
+
 
 // Structure masks (128-tile granularity, as everywhere in chol.cu: tiles beyond the block diagonal hold garbage):
 //   OZ_TRI_K_LE_ROW  operand row r only has entries for k <  128 (floor(r/128) + 1)   (lower-triangular A: k <= row)
@@ -339,10 +344,11 @@ __device__ __forceinline__ bool oz_kb_live(int tri, int64_t rtile, int kb) {
     return true;
 }
 
-// Balanced base-256 digits of q (|q| < 2^54): q = sum_s d_s 256^(6-s), d_s in [-128, 127] (d_0 in [-64, 64]).
-__device__ __forceinline__ void oz_signed_digits(long long q, uint32_t (&dig)[OG_S]) {
+// Balanced base-256 digits of q (|q| < 2^(8S-2)): q = sum_s d_s 256^(S-1-s), d_s in [-128, 127] (d_0 in [-64, 64]).
+template <int S>
+__device__ __forceinline__ void oz_signed_digits(long long q, uint32_t (&dig)[S]) {
 #pragma unroll
-    for (int s = OG_S - 1; s > 0; --s) {
+    for (int s = S - 1; s > 0; --s) {
         const int d = (int)(signed char)(q & 0xFF);
         dig[s] = (uint32_t)(d & 0xFF);
         q = (q - d) >> 8;  // exact: q - d is a multiple of 256
@@ -353,14 +359,14 @@ __device__ __forceinline__ void oz_signed_digits(long long q, uint32_t (&dig)[OG
 // Dop[rtile][kb][s][core layout]: digits of op(row, k) / scale[row]; thread = operand row of the tile, OZ_SLICE_KB
 // K-blocks per CTA (few, so that a 1024-wide panel still fills the machine).
 constexpr int OZ_SLICE_KB = 2;
-template <bool TRANS>
+template <bool TRANS, int S>
 __global__ void __launch_bounds__(128)
     oz_slice_rows_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t ld, int tri,
                          const double* __restrict__ scale, uint8_t* __restrict__ Dop, int kblocks) {
     const int r = threadIdx.x;
     const int64_t rtile = blockIdx.y, row = rtile * OZ_BM + r;
     const bool live = row < rows;
-    const double inv = live ? (0x1p54 / scale[row]) : 0.0;  // exact power of two; |q| < 2^54 keeps the top digit in [-64, 64]
+    const double inv = live ? (og_pow2(8 * S - 2) / scale[row]) : 0.0;  // exact power of two; |q| < 2^(8S-2): top digit in [-64, 64]
     const int kb0 = blockIdx.x * OZ_SLICE_KB;
 #pragma unroll 1
     for (int kbl = 0; kbl < OZ_SLICE_KB; ++kbl) {
@@ -369,9 +375,9 @@ __global__ void __launch_bounds__(128)
         if (!oz_kb_live(tri, rtile, kb)) continue;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            uint32_t words[OG_S][4];
+            uint32_t words[S][4];
 #pragma unroll
-            for (int s = 0; s < OG_S; ++s)
+            for (int s = 0; s < S; ++s)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) words[s][q] = 0;
 #pragma unroll
@@ -379,14 +385,14 @@ __global__ void __launch_bounds__(128)
                 const int64_t k = (int64_t)kb * 32 + c * 16 + e;
                 double v = 0.0;
                 if (live && k < K && oz_in_range(tri, row, k)) v = TRANS ? P[k * ld + row] : P[row * ld + k];
-                uint32_t d[OG_S];
-                oz_signed_digits(__double2ll_rn(v * inv), d);
+                uint32_t d[S];
+                oz_signed_digits<S>(__double2ll_rn(v * inv), d);
 #pragma unroll
-                for (int s = 0; s < OG_S; ++s) words[s][e >> 2] |= d[s] << (8 * (e & 3));
+                for (int s = 0; s < S; ++s) words[s][e >> 2] |= d[s] << (8 * (e & 3));
             }
-            uint8_t* dst = Dop + (((int64_t)rtile * kblocks + kb) * OG_S) * OZ_A_BYTES + core_offset(r, c);
+            uint8_t* dst = Dop + (((int64_t)rtile * kblocks + kb) * S) * OZ_A_BYTES + core_offset(r, c);
 #pragma unroll
-            for (int s = 0; s < OG_S; ++s)
+            for (int s = 0; s < S; ++s)
                 *reinterpret_cast<uint4*>(dst + (int64_t)s * OZ_A_BYTES) =
                     make_uint4(words[s][0], words[s][1], words[s][2], words[s][3]);
         }
@@ -416,14 +422,11 @@ struct OgCfg {
 // int32 stays exact for og_kchunk K-blocks; longer products hand the accumulators over chunk by chunk (fp64 sum in C).
 // Signed 8-bit digits: |d d'| <= 2^14, at most 7 pairs per group: 7 * 16384 * 2^14 < 2^31.  Unsigned 7-bit digits (top
 // digit up to 128): at most 8 pairs: 8 * 10240 * 2^14 < 2^31.
-template <int BITS>
-struct OgChunk {
-    static constexpr int KBLOCKS = BITS == 8 ? 512 : 320;
+template <int BITS, int S>
+struct OgChunk {  // 8 signed digits: the last group has 8 pairs, 8 * 2^14 * 16384 would reach 2^31 exactly
+    static constexpr int KBLOCKS = BITS == 8 ? (S == 8 ? 448 : 512) : 320;
 };
 
-__device__ __forceinline__ double og_pow2(int e) {  // 2^e, e in the normal range (folds to a constant)
-    return __longlong_as_double((long long)(1023 + e) << 52);
-}
 // exact int64 -> double for |x| < 2^51 (one integer add, one DADD; I2F.F64 is several times slower)
 __device__ __forceinline__ double og_i2d(long long x) {
     return __longlong_as_double(x + 0x4338000000000000LL) - 0x1.8p52;
@@ -442,7 +445,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
                       const double* __restrict__ sb, double* __restrict__ C, int64_t ldc, int kblocks, int lower_only,
                       int mode, int tri_a, int tri_b) {
     using Cfg = OgCfg<S>;
-    constexpr int SL = Cfg::SLICE, BN = Cfg::BN, OG_KCHUNK = OgChunk<BITS>::KBLOCKS;
+    constexpr int SL = Cfg::SLICE, BN = Cfg::BN, OG_KCHUNK = OgChunk<BITS, S>::KBLOCKS;
     constexpr int W0 = (BITS == 8) ? 12 : 14, NGB = S - 4;  // weight of group 0 is 2^-W0; groups of pass B
     static_assert(S >= 6 && S <= 8 && (BITS == 7 || BITS == 8), "digit scheme");
     const int ctile = blockIdx.x, ptile = blockIdx.y;
@@ -619,10 +622,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
                     umma::tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        long long q = (int)u[0][i];
+                        if constexpr (NGB == 4) {  // two halves: one merged integer could pass 2^51
+                            const long long hi = ((long long)(int)u[0][i] << BITS) + (int)u[1][i];
+                            const long long lo = ((long long)(int)u[2][i] << BITS) + (int)u[3][i];
+                            v[i] = fma(og_i2d(hi), og_pow2(-W0 - 5 * BITS), og_i2d(lo) * og_pow2(-W0 - 7 * BITS));
+                        } else {
+                            long long q = (int)u[0][i];
 #pragma unroll
-                        for (int g = 1; g < NGB; ++g) q = (q << BITS) + (int)u[g][i];  // < 2^(31 + 21)... top group < 2^30
-                        v[i] = og_i2d(q) * og_pow2(-W0 - BITS * (S - 1));
+                            for (int g = 1; g < NGB; ++g) q = (q << BITS) + (int)u[g][i];
+                            v[i] = og_i2d(q) * og_pow2(-W0 - BITS * (S - 1));
+                        }
                     }
                 }
                 // tensor memory hands a thread one ROW; C wants 128 contiguous bytes per row and instruction, so the
@@ -660,26 +669,28 @@ static int og_configure() {
 }
 
 // Digits + row scales of a (rows x K) fp64 operand; rows are padded to whole 128-row tiles with zeros.
-int64_t ozaki_operand_bytes(int64_t rows, int64_t K) {
+int64_t ozaki_operand_bytes(int64_t rows, int64_t K, int S) {
     const int64_t rt = pad_to(rows, OZ_BM) / OZ_BM, kb = pad_to(K, OZ_KB) / OZ_KB;
-    return pad_to(rt * kb * OG_S * OZ_A_BYTES, 1024) + pad_to(rt * OZ_BM * 8, 1024);
+    return pad_to(rt * kb * S * OZ_A_BYTES, 1024) + pad_to(rt * OZ_BM * 8, 1024);
 }
 // trans == 0: operand(r, k) = P[r][k];  trans != 0: operand(r, k) = P[k][r].  tri: OzTri mask of the operand.
-int ozaki_slice_operand(const double* P, int64_t rows, int64_t K, int64_t ld, int trans, int tri, uint8_t* buf,
+int ozaki_slice_operand(const double* P, int64_t rows, int64_t K, int64_t ld, int trans, int tri, uint8_t* buf, int S,
                         cudaStream_t st) {
     const int64_t rt = pad_to(rows, OZ_BM) / OZ_BM;
     const int kb = (int)(pad_to(K, OZ_KB) / OZ_KB);
-    double* scale = reinterpret_cast<double*>(buf + pad_to(rt * kb * OG_S * OZ_A_BYTES, 1024));
+    double* scale = reinterpret_cast<double*>(buf + pad_to(rt * kb * S * OZ_A_BYTES, 1024));
     const dim3 gs((unsigned)ceil_div(kb, OZ_SLICE_KB), (unsigned)rt);
     if (trans) {
         cudaMemsetAsync(scale, 0, (size_t)rt * OZ_BM * 8, st);
         oz_colmax_kernel<<<dim3((unsigned)ceil_div(rows, 128), (unsigned)ceil_div(K, 256)), 128, 0, st>>>(
             P, rows, K, ld, tri, reinterpret_cast<unsigned long long*>(scale));
         oz_scale_from_max_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, st>>>(scale, rows);
-        oz_slice_rows_kernel<true><<<gs, 128, 0, st>>>(P, rows, K, ld, tri, scale, buf, kb);
+        if (S == 8) oz_slice_rows_kernel<true, 8><<<gs, 128, 0, st>>>(P, rows, K, ld, tri, scale, buf, kb);
+        else oz_slice_rows_kernel<true, 7><<<gs, 128, 0, st>>>(P, rows, K, ld, tri, scale, buf, kb);
     } else {
         oz_rowscale_rows_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(P, rows, K, ld, tri, scale);
-        oz_slice_rows_kernel<false><<<gs, 128, 0, st>>>(P, rows, K, ld, tri, scale, buf, kb);
+        if (S == 8) oz_slice_rows_kernel<false, 8><<<gs, 128, 0, st>>>(P, rows, K, ld, tri, scale, buf, kb);
+        else oz_slice_rows_kernel<false, 7><<<gs, 128, 0, st>>>(P, rows, K, ld, tri, scale, buf, kb);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -691,17 +702,22 @@ int ozaki_slice_operand(const double* P, int64_t rows, int64_t K, int64_t ld, in
 // C (m x n) (op)= A B^T from sliced operands (tile offsets in units of 128 operand rows); mode 0: -=, 1: =, 2: = -.
 int ozaki_gemm_nt_sliced(const uint8_t* abuf, int64_t a_rows_total, int64_t a_tile0, const uint8_t* bbuf, int64_t b_rows_total,
                          int64_t b_tile0, int64_t K, double* C, int64_t ldc, int64_t m, int64_t n, int lower_only, int mode,
-                         int tri_a, int tri_b, cudaStream_t st) {
-    int rc = og_configure<OG_S, 8>();
+                         int tri_a, int tri_b, int S, cudaStream_t st) {
+    int rc = (S == 8) ? og_configure<8, 8>() : og_configure<7, 8>();
     if (rc) return rc;
     const int kb = (int)(pad_to(K, OZ_KB) / OZ_KB);
     const int64_t art = pad_to(a_rows_total, OZ_BM) / OZ_BM, brt = pad_to(b_rows_total, OZ_BM) / OZ_BM;
-    const double* sa = reinterpret_cast<const double*>(abuf + pad_to(art * kb * OG_S * OZ_A_BYTES, 1024)) + a_tile0 * OZ_BM;
-    const double* sb = reinterpret_cast<const double*>(bbuf + pad_to(brt * kb * OG_S * OZ_A_BYTES, 1024)) + b_tile0 * OZ_BM;
-    const uint8_t* aop = abuf + a_tile0 * (int64_t)kb * OG_S * OZ_A_BYTES;
-    const uint8_t* bop = bbuf + b_tile0 * (int64_t)kb * OG_S * OZ_A_BYTES;
-    oz_gemm_nt_kernel<OG_S, 8><<<dim3((unsigned)(n / OgCfg<OG_S>::BN), (unsigned)(m / OZ_BM)), OZ_THREADS, OgCfg<OG_S>::SMEM_BYTES, st>>>(
-        aop, sa, bop, sb, C, ldc, kb, lower_only, mode, tri_a, tri_b);
+    const double* sa = reinterpret_cast<const double*>(abuf + pad_to(art * kb * S * OZ_A_BYTES, 1024)) + a_tile0 * OZ_BM;
+    const double* sb = reinterpret_cast<const double*>(bbuf + pad_to(brt * kb * S * OZ_A_BYTES, 1024)) + b_tile0 * OZ_BM;
+    const uint8_t* aop = abuf + a_tile0 * (int64_t)kb * S * OZ_A_BYTES;
+    const uint8_t* bop = bbuf + b_tile0 * (int64_t)kb * S * OZ_A_BYTES;
+    const dim3 grid((unsigned)(n / 128), (unsigned)(m / OZ_BM));
+    if (S == 8)
+        oz_gemm_nt_kernel<8, 8><<<grid, OZ_THREADS, OgCfg<8>::SMEM_BYTES, st>>>(aop, sa, bop, sb, C, ldc, kb, lower_only, mode,
+                                                                                tri_a, tri_b);
+    else
+        oz_gemm_nt_kernel<7, 8><<<grid, OZ_THREADS, OgCfg<7>::SMEM_BYTES, st>>>(aop, sa, bop, sb, C, ldc, kb, lower_only, mode,
+                                                                                tri_a, tri_b);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("ozaki_gemm_nt: %s", cudaGetErrorString(e));
@@ -801,7 +817,7 @@ extern "C" int socks_srmax_predict_i8(const double* X, const double* w, const do
 
 
 extern "C" int64_t socks_dev_ozaki_gemm_work_bytes(int64_t m, int64_t n, int64_t K) {
-    return ozaki_operand_bytes(m, K) + ozaki_operand_bytes(n, K) + 2048;
+    return ozaki_operand_bytes(m, K, 8) + ozaki_operand_bytes(n, K, 8) + 2048;
 }
 
 // C (m x n, ldc) -= A (m x K, lda) B (n x K, ldb)^T through the integer tensor cores; m, n multiples of 128, K of 32,
@@ -818,9 +834,11 @@ extern "C" int socks_dev_ozaki_gemm_nt(const double* A, int64_t lda, const doubl
     SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 1023) == 0, 12);
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* abuf = reinterpret_cast<uint8_t*>(work);
-    uint8_t* bbuf = syrk ? abuf : abuf + ozaki_operand_bytes(m, K);
-    int rc = ozaki_slice_operand(A, m, K, lda, 0, 0, abuf, st);
+    const int S = (syrk & 2) ? 8 : 7;  // bit 1 of `syrk`: 8 digits
+    syrk &= 1;
+    uint8_t* bbuf = syrk ? abuf : abuf + ozaki_operand_bytes(m, K, S);
+    int rc = ozaki_slice_operand(A, m, K, lda, 0, 0, abuf, S, st);
     if (rc) return rc;
-    if (!syrk && (rc = ozaki_slice_operand(B, n, K, ldb, 0, 0, bbuf, st))) return rc;
-    return ozaki_gemm_nt_sliced(abuf, m, 0, bbuf, syrk ? m : n, 0, K, C, ldc, m, n, lower_only, 0, 0, 0, st);
+    if (!syrk && (rc = ozaki_slice_operand(B, n, K, ldb, 0, 0, bbuf, S, st))) return rc;
+    return ozaki_gemm_nt_sliced(abuf, m, 0, bbuf, syrk ? m : n, 0, K, C, ldc, m, n, lower_only, 0, 0, 0, S, st);
 }

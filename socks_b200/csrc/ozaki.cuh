@@ -5,16 +5,17 @@
 namespace socks {
 
 // bytes of the sliced form (digits + row scales) of a (rows x K) fp64 operand
-int64_t ozaki_operand_bytes(int64_t rows, int64_t K);
-// operand(r, k) = P[r][k] (trans == 0) or P[k][r] (trans != 0) -> buf (1024-byte aligned): 7 balanced base-256 digits per
+int64_t ozaki_operand_bytes(int64_t rows, int64_t K, int S);
+// S = 7 or 8 digits per entry (one more digit = 256x smaller truncation error, 36 instead of 28 MMAs per K-block).
+// operand(r, k) = P[r][k] (trans == 0) or P[k][r] (trans != 0) -> buf (1024-byte aligned): S balanced base-256 digits per
 // entry + per-row power-of-two scales.  tri: 0 none, 1 operand(r, k) = 0 for k >= 128 (floor(r/128) + 1), 2 operand(r, k) = 0
 // for k < 128 floor(r/128) (those regions of P are never read: they hold garbage in the factorisation's buffers).
-int ozaki_slice_operand(const double* P, int64_t rows, int64_t K, int64_t ld, int trans, int tri, uint8_t* buf,
+int ozaki_slice_operand(const double* P, int64_t rows, int64_t K, int64_t ld, int trans, int tri, uint8_t* buf, int S,
                         cudaStream_t st);
 // C (m x n, ldc) (op)= A B^T with A = operand rows [128 a_tile0, ..) of abuf, B likewise (m % 128 == 0, n % 128 == 0);
 // mode 0: C -= AB^T, 1: C = AB^T, 2: C = -AB^T; tri_a / tri_b clip each tile's K range (A lower / B "k >= n").
 int ozaki_gemm_nt_sliced(const uint8_t* abuf, int64_t a_rows_total, int64_t a_tile0, const uint8_t* bbuf, int64_t b_rows_total,
                          int64_t b_tile0, int64_t K, double* C, int64_t ldc, int64_t m, int64_t n, int lower_only, int mode,
-                         int tri_a, int tri_b, cudaStream_t st);
+                         int tri_a, int tri_b, int S, cudaStream_t st);
 
 }  // namespace socks
