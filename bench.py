@@ -270,6 +270,9 @@ def run_ours(args):
             "gram_solve_s": st["gram_sym"] + st["potrf_inv"] + st["diag_inv"],
             "gram_solve_tflops": (2 * npad ** 3 / 3) / (st["gram_sym"] + st["potrf_inv"] + st["diag_inv"]) / 1e12,
             "potrf_inv_s": st["potrf_inv"], "potrf_inv_tflops": (2 * npad ** 3 / 3) / st["potrf_inv"] / 1e12,
+            "potrf_inv_engine": "look-ahead Cholesky + inverse; large GEMMs as fp64-accurate digit GEMMs on tcgen05.mma "
+                                "kind::i8 (7 digits in the trailing updates, 8 in the merges), so *_tflops are "
+                                "fp64-EQUIVALENT rates (fp64 DMMA peak: roofline.peak)",
             "gram_sym_s": st["gram_sym"], "gram_cross_s": st["gram_cross"],
             "fit_recursion_s": st["fit_recursion"],
             # HBM-bound stage: (T-1) GEMV passes over the resident N x N beta, bytes = (T-1) * 8 * N^2 (the
