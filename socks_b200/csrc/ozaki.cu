@@ -1,7 +1,9 @@
 // Integer tensor-core (tcgen05.mma kind::i8, TMEM accumulators) building blocks.
 // Phase-1 check kernel: C (M x N, int32) = A (M x K, int8, K contiguous) * B (N x K, int8, K contiguous)^T, one CTA per
 // 128 x 64 tile, one MMA (K = 32) per staged K-block.  Validates the descriptor / layout conventions of umma.cuh against
-// an exact integer reference (tools/i8gemm_check.py) before anything is built on them.
+// an exact integer reference (tools/i8gemm_check.py) before anything is built on them: variant 0 = the convention used
+// everywhere (LBO 128, SBO 256), 1 = the swapped one (negative control: every entry wrong), 2 = A operand written to
+// tensor memory by tcgen05.st and read by the TS form of the MMA (what sr_predict_i8_kernel does).
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -108,12 +110,9 @@ extern "C" int socks_dev_i8gemm_check(const void* A, const void* B, void* C, int
 //     K_ij = sum_s a_s 2^(-7(s+1)),   Bm_ic / 2^(e_r) = sum_t b_t 2^(-7(t+1))      (e_r: exponent of max_i coef_r[i]),
 // and every digit product A_s^T B_t is an EXACT int8 x int8 -> int32 GEMM on tcgen05.mma kind::i8.  Products with
 // s + t = g share one TMEM accumulator; groups g >= S are dropped (below 2^(-7(S+2)) K 127^2 of the scale); the
-// epilogue converts the S accumulators to fp64 and recombines sum_g 2^(-7(g+2)) G_g * 2^(e_r).  CTA tile 128 points x 64
-// columns, S accumulators of 64 TMEM columns (S = 8: all 512), K-block = 32 samples = one MMA per digit pair;
-// int32 is exact for 8192 samples (9 * 8192 * 128 * 127 < 2^31), so the epilogue runs once per 256 K-blocks.
-// Warp roles: warps 0-3 epilogue (TMEM lane = point row), warp 4 = one thread issuing two bulk async copies per stage
-// (the producers write both operands in the exact shared-memory stage layout, so a stage is two contiguous blocks),
-// warp 5 = one thread issuing S(S+1)/2 MMAs per stage; full/empty mbarriers per stage, acc_full/acc_empty per chunk.
+// epilogue merges the group sums in exact 64-bit integer arithmetic, converts once and applies 2^(e_r).  The contraction
+// runs on the two-pass 128 x 128 kernel of the next section (oz_gemm_nt_kernel<S, 7>; this section holds the operand
+// producers, which write both operands directly in the shared-memory stage layout, and the host side).
 // Points whose normaliser is too small for the fixed-point operand (far from every sample) are listed for the FP64 path.
 namespace socks {
 
