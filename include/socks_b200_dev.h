@@ -33,6 +33,11 @@ int socks_dev_ozaki_gemm_nt(const double* A, int64_t lda, const double* B, int64
  * previous value.  Negative codes switch measurement variants: -1/-2 half-width tail off/on, -3/-4 trailing updates on
  * FP64 DMMA / integer tensor cores, -5/-6 large merges likewise, -7/-8 seven / eight digits in the merges. */
 int socks_potrf_inv_set_block(int nb);
+/* Timeline of one socks_potrf_inv call (CUDA events on both streams): call with NULL pointers to arm it for the next
+ * factorisation; afterwards it returns the number of events and fills code = 1000 * kind + step (kinds: 0 start, 1 diagonal
+ * block done, 2 panel done, 3 small merges done [panel stream]; 4 column update done, 5 rest update done, 6 join, 7 large
+ * merge done [caller's stream]) and the time in ms since the start. */
+int socks_dev_potrf_trace(int* codes, double* ms, int cap);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,7 @@ SIGNATURES = {
     "socks_pad_spd": (_I, [_P, _L, _L, _D, _P, _L, _P]),
     "socks_potrf_inv": (_I, [_P, _L, _L, _P, _L, _P, _P, _I, _P]),
     "socks_potrf_inv_set_block": (_I, [_I]),
+    "socks_dev_potrf_trace": (_I, [_P, _P, _I]),
     "socks_trtri": (_I, [_P, _L, _L, _P, _P, _L, _P, _P]),
     "socks_diag_inv": (_I, [_P, _L, _L, _P, _P, _P]),
     "socks_potrs": (_I, [_P, _L, _L, _P, _L, _L, _P, _P]),

@@ -475,8 +475,11 @@ static void potrf_inv_rec(CholCtx& cx, double* A, int64_t lda, double* M, int64_
 // (M21 = -(M22 L21) M11, large GEMMs only).  Same arithmetic per block as the pure recursion, different association
 // across blocks, i.e. results differ at the rounding level (~cond * eps; tests compare both).
 struct Lookahead {
-    cudaStream_t s2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_panel = nullptr, ev_col = nullptr;
+    // panel stream (greatest priority), update stream (middle), merge stream (least): the block scheduler serves pending
+    // CTAs in that order, so the merges of inv(L) only fill what the factorisation leaves idle
+    cudaStream_t s2 = nullptr, su = nullptr, s3 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_panel = nullptr, ev_col = nullptr, ev_su = nullptr, ev_s3 = nullptr;
+    std::vector<cudaEvent_t> ev_step;  // panel stream after step k (block, panel, small merges)
     bool ready = false;
 };
 
@@ -495,6 +498,10 @@ static Lookahead* lookahead_for_device(int* rc_out) {
         int lo = 0, hi = 0;
         cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = greatest priority (numerically lowest)
         if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&l.s2, cudaStreamNonBlocking, hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&l.su, cudaStreamNonBlocking, (lo + hi) / 2);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&l.s3, cudaStreamNonBlocking, lo);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l.ev_su, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l.ev_s3, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l.ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l.ev_panel, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l.ev_col, cudaEventDisableTiming);
@@ -507,6 +514,23 @@ static Lookahead* lookahead_for_device(int* rc_out) {
     }
     return &l;
 }
+
+// ---- optional timeline of one socks_potrf_inv call (tools/potrf_trace.py): timed events on both streams ----------------
+struct PotrfTrace {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> code;  // 1000 * kind + step; kinds: 0 start, 1 block done (s2), 2 panel done (s2), 3 small merges done (s2),
+                            // 4 column update done (s1), 5 rest update done (s1), 6 join, 7 large merge done (s1)
+    void mark(int kind, int step, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+        code.push_back(1000 * kind + step);
+    }
+};
+static PotrfTrace g_trace;
 
 static int g_potrf_ozaki = 1;  // 1: trailing updates on the integer tensor cores (csrc/ozaki.cu), 0: FP64 DMMA GEMM
 // Digits of the merges: the entries of inv(L) span many orders of magnitude WITHIN a row, and the digit scheme truncates
@@ -530,34 +554,39 @@ static void plan_merges(int lo, int hi, std::vector<Merge>& out) {
     plan_merges(mid, hi, out);
     out.push_back(Merge{lo, mid, hi});
 }
-// digits == nullptr: FP64 DMMA GEMMs.  Otherwise both products run on the integer tensor cores (csrc/ozaki.cu) when
-// their digit operands fit in `digit_bytes`; the triangular structure is clipped exactly as the DMMA GEMM clips it.
-static void run_merge(CholCtx& cx, double* M, int64_t ldm, const int64_t* bnd, const Merge& g, double* work,
-                      uint8_t* digits = nullptr, int64_t digit_bytes = 0) {
+// One merge M21 = -M22 L21 M11 as two products, associated so that the first needs nothing from the right half:
+//   product 1:  T (n2 x n1, ld n1) = L21 M11    -- ready once blocks [lo, mid) are factored and M11 is complete
+//   product 2:  M21 = -M22 T                    -- ready once M22 is complete as well; overwrites L21
+// digits == nullptr: FP64 DMMA GEMMs.  Otherwise the product runs on the integer tensor cores (csrc/ozaki.cu) when its
+// digit operands fit in `digit_bytes`; the triangular structure is clipped exactly as the DMMA GEMM clips it.
+static void merge_product(CholCtx& cx, int which, double* M, int64_t ldm, const int64_t* bnd, const Merge& g, double* T,
+                          uint8_t* digits, int64_t digit_bytes) {
     const int64_t o1 = bnd[g.lo], o2 = bnd[g.mid], n1 = bnd[g.mid] - bnd[g.lo], n2 = bnd[g.hi] - bnd[g.mid];
     double* M11 = M + o1 * ldm + o1;
-    double* M21 = M + o2 * ldm + o1;  // holds L21
+    double* M21 = M + o2 * ldm + o1;  // holds L21 until product 2
     double* M22 = M + o2 * ldm + o2;
-    const int64_t kmax = std::max(n1, n2);
     const int S = g_potrf_merge_digits;
-    if (digits && ozaki_operand_bytes(n2, kmax, S) + ozaki_operand_bytes(n1, kmax, S) <= digit_bytes) {
+    const int64_t K = (which == 1) ? n1 : n2;
+    if (digits && ozaki_operand_bytes(n2, K, S) + ozaki_operand_bytes(n1, K, S) <= digit_bytes) {
         int rc = SOCKS_OK;
-        // T = M22 L21: A = rows of M22 (lower triangular), B = columns of L21, K = n2
         uint8_t* da = digits;
-        uint8_t* db = digits + ozaki_operand_bytes(n2, n2, S);
-        if (!rc) rc = ozaki_slice_operand(M22, n2, n2, ldm, 0, 1, da, S, cx.st);
-        if (!rc) rc = ozaki_slice_operand(M21, n1, n2, ldm, 1, 0, db, S, cx.st);
-        if (!rc) rc = ozaki_gemm_nt_sliced(da, n2, 0, db, n1, 0, n2, work, n1, n2, n1, 0, 1, 1, 0, S, cx.st);
-        // M21 = -T M11: A = rows of T, B = columns of M11 (zero above the diagonal: k >= j), K = n1
-        db = digits + ozaki_operand_bytes(n2, n1, S);
-        if (!rc) rc = ozaki_slice_operand(work, n2, n1, n1, 0, 0, da, S, cx.st);
-        if (!rc) rc = ozaki_slice_operand(M11, n1, n1, ldm, 1, 2, db, S, cx.st);
-        if (!rc) rc = ozaki_gemm_nt_sliced(da, n2, 0, db, n1, 0, n1, M21, ldm, n2, n1, 0, 2, 0, 1, S, cx.st);
+        uint8_t* db = digits + ozaki_operand_bytes(n2, K, S);
+        if (which == 1) {  // A = rows of L21, B = columns of M11 (zero above the diagonal: k >= j), K = n1
+            if (!rc) rc = ozaki_slice_operand(M21, n2, n1, ldm, 0, 0, da, S, cx.st);
+            if (!rc) rc = ozaki_slice_operand(M11, n1, n1, ldm, 1, 2, db, S, cx.st);
+            if (!rc) rc = ozaki_gemm_nt_sliced(da, n2, 0, db, n1, 0, n1, T, n1, n2, n1, 0, 1, 0, 1, S, cx.st);
+        } else {  // A = rows of M22 (lower triangular: k <= i), B = columns of T, K = n2
+            if (!rc) rc = ozaki_slice_operand(M22, n2, n2, ldm, 0, 1, da, S, cx.st);
+            if (!rc) rc = ozaki_slice_operand(T, n1, n2, n1, 1, 0, db, S, cx.st);
+            if (!rc) rc = ozaki_gemm_nt_sliced(da, n2, 0, db, n1, 0, n2, M21, ldm, n2, n1, 0, 2, 1, 0, S, cx.st);
+        }
         if (rc) cx.note(cudaErrorUnknown);
         return;
     }
-    cx.note(gemm_f64<false, false>(M22, ldm, M21, ldm, work, n1, n2, n1, n2, 1.0, 0.0, GEMM_A_K_LE_M, 0, cx.st));
-    cx.note(gemm_f64<false, false>(work, n1, M11, ldm, M21, ldm, n2, n1, n1, -1.0, 0.0, GEMM_B_K_GE_N, 0, cx.st));
+    if (which == 1)
+        cx.note(gemm_f64<false, false>(M21, ldm, M11, ldm, T, n1, n2, n1, n1, 1.0, 0.0, GEMM_B_K_GE_N, 0, cx.st));
+    else
+        cx.note(gemm_f64<false, false>(M22, ldm, T, n1, M21, ldm, n2, n1, n2, -1.0, 0.0, GEMM_A_K_LE_M, 0, cx.st));
 }
 
 static inline int64_t trtri_scratch_doubles(int64_t np) {
@@ -566,10 +595,19 @@ static inline int64_t trtri_scratch_doubles(int64_t np) {
     return n1 * (np - n1);
 }
 // digits of one block-column panel (np x NB) for the integer tensor-core trailing updates, after the merge scratch
-// ... and the two digit operands of the largest merge (rows n1 + n2 <= np, K <= max(n1, n2) <= np/2 + 2 block columns)
-static inline int64_t potrf_digit_bytes(int64_t np) {
+// Workspace of the look-ahead factorisation, in this order:
+//   [scratch of the diagonal-block recursion and of the small merges | one T per large merge | panel digits | merge digits]
+// T arena: every pair of distinct block columns meets in exactly one merge, so sum n1 n2 < np^2 / 2.
+constexpr int64_t kRecScratchDoubles = (int64_t)4096 * 4096;  // merges spanning <= 4 block columns of <= 2048
+static inline int64_t potrf_arena_doubles(int64_t np) { return np * np / 2; }
+static inline int64_t potrf_panel_digit_bytes(int64_t np) { return ozaki_operand_bytes(np, 2048, 7) + 1024; }
+// the two digit operands of the largest product (rows n1 + n2 <= np, K <= max(n1, n2) <= np/2 + 2 block columns)
+static inline int64_t potrf_merge_digit_bytes(int64_t np) {
     const int64_t kmax = std::min<int64_t>(np, np / 2 + 2048);
-    return std::max(ozaki_operand_bytes(np, 2048, 7), 2 * ozaki_operand_bytes((np + 1) / 2 + 2048, kmax, 8)) + 2048;
+    return 2 * ozaki_operand_bytes((np + 1) / 2 + 2048, kmax, 8) + 1024;
+}
+static inline int64_t potrf_lookahead_bytes(int64_t np) {
+    return (kRecScratchDoubles + potrf_arena_doubles(np)) * 8 + potrf_panel_digit_bytes(np) + potrf_merge_digit_bytes(np) + 2048;
 }
 
 static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, int64_t np, double* work, int* info,
@@ -577,10 +615,15 @@ static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, i
     int rc;
     Lookahead* la = lookahead_for_device(&rc);
     if (!la) return rc;
+    // workspace (socks_trtri_work_bytes): recursion scratch | T arena | panel digits | merge digits
+    double* arena = work + kRecScratchDoubles;
     uint8_t* digits = reinterpret_cast<uint8_t*>(
-        (reinterpret_cast<uintptr_t>(work + trtri_scratch_doubles(np)) + 1023) & ~(uintptr_t)1023);
+        (reinterpret_cast<uintptr_t>(arena + potrf_arena_doubles(np)) + 1023) & ~(uintptr_t)1023);
+    uint8_t* mdigits = digits + ((potrf_panel_digit_bytes(np) + 1023) & ~(int64_t)1023);
+    const int64_t mdigit_bytes = potrf_merge_digit_bytes(np) - 1024;
     const bool use_ozaki = g_potrf_ozaki && NB <= 2048;
-    CholCtx c1{s1}, c2{la->s2};
+    cudaStream_t su = la->su, s3 = la->s3;
+    CholCtx c1{su}, c2{la->s2}, c3{s3};
     // block-column boundaries: NB wide, but half as wide over the last 4 NB columns -- there the trailing update is
     // shorter than the critical path of a block (leaves + small GEMMs), so shorter blocks shorten what is exposed
     std::vector<int64_t> bnd;
@@ -594,14 +637,38 @@ static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, i
     std::vector<Merge> merges;
     plan_merges(0, nb, merges);
     constexpr int kSmallMerge = 4;  // merges spanning <= 4 block columns ride on the panel stream
-    c1.note(cudaEventRecord(la->ev_fork, s1));  // everything already enqueued on s1 (the Gram build) precedes s2's work
+    // one T per large merge
+    std::vector<int64_t> t_off(merges.size(), -1);
+    int64_t used = 0;
+    for (size_t i = 0; i < merges.size(); ++i) {
+        const Merge& g = merges[i];
+        if (g.hi - g.lo <= kSmallMerge) continue;
+        t_off[i] = used;
+        used += (bnd[g.mid] - bnd[g.lo]) * (bnd[g.hi] - bnd[g.mid]);
+    }
+    if (used > potrf_arena_doubles(np)) {
+        set_error("socks_potrf_inv: merge arena too small (%lld > %lld doubles)", (long long)used,
+                  (long long)potrf_arena_doubles(np));
+        return SOCKS_EINVAL(6);
+    }
+    while ((int)la->ev_step.size() < nb) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return SOCKS_ECUDA;
+        la->ev_step.push_back(e);
+    }
+    // fork: everything already enqueued on the caller's stream (the Gram build) precedes the work of all three streams
+    g_trace.mark(0, 0, s1);
+    c1.note(cudaEventRecord(la->ev_fork, s1));
+    c1.note(cudaStreamWaitEvent(su, la->ev_fork, 0));
     c2.note(cudaStreamWaitEvent(la->s2, la->ev_fork, 0));
+    c3.note(cudaStreamWaitEvent(s3, la->ev_fork, 0));
     for (int k = 0; k < nb; ++k) {
         const int64_t k0 = bnd[k], bk = bnd[k + 1] - k0, rem = np - k0 - bk;
         double* Akk = A + k0 * lda + k0;
         double* Mkk = M + k0 * ldm + k0;
         if (k > 0) c2.note(cudaStreamWaitEvent(la->s2, la->ev_col, 0));
         potrf_inv_rec(c2, Akk, lda, Mkk, ldm, bk, work, info, k0, keep_l);
+        g_trace.mark(1, k, la->s2);
         if (rem > 0) {  // panel: L21 = A21 * inv(L_kk)^T, stored in M's (2,1) block until the inverse overwrites it
             double* A21 = A + (k0 + bk) * lda + k0;
             double* L21 = M + (k0 + bk) * ldm + k0;
@@ -612,11 +679,33 @@ static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, i
                 c2.note(cudaGetLastError());
             }
         }
+        g_trace.mark(2, k, la->s2);
         c2.note(cudaEventRecord(la->ev_panel, la->s2));
-        c1.note(cudaStreamWaitEvent(s1, la->ev_panel, 0));
-        // small merges of the inverse that end at this block: on the panel stream, in the shadow of s1's column update
+        c1.note(cudaStreamWaitEvent(su, la->ev_panel, 0));
+        // small merges of the inverse that end at this block: on the panel stream, in the shadow of the column update
         for (const Merge& g : merges)
-            if (g.hi == k + 1 && g.hi - g.lo <= kSmallMerge) run_merge(c2, M, ldm, bnd.data(), g, work);
+            if (g.hi == k + 1 && g.hi - g.lo <= kSmallMerge) {
+                merge_product(c2, 1, M, ldm, bnd.data(), g, work, nullptr, 0);
+                merge_product(c2, 2, M, ldm, bnd.data(), g, work, nullptr, 0);
+            }
+        g_trace.mark(3, k, la->s2);
+        // large merges: whatever became ready with this step goes to the merge stream (children before parents: post-order)
+        c2.note(cudaEventRecord(la->ev_step[k], la->s2));
+        bool waited = false;
+        for (size_t i = 0; i < merges.size(); ++i) {
+            const Merge& g = merges[i];
+            if (t_off[i] < 0) continue;
+            for (int which = 1; which <= 2; ++which) {
+                if ((which == 1 ? g.mid : g.hi) != k + 1) continue;
+                if (!waited) {
+                    c3.note(cudaStreamWaitEvent(s3, la->ev_step[k], 0));
+                    waited = true;
+                }
+                merge_product(c3, which, M, ldm, bnd.data(), g, arena + t_off[i],
+                              (use_ozaki && g_potrf_ozaki_merge) ? mdigits : nullptr, mdigit_bytes);
+                g_trace.mark(7, 100 * which + (g.hi - g.lo), s3);
+            }
+        }
         if (rem == 0) break;
         const int64_t b1 = bnd[k + 2] - bnd[k + 1];
         const double* L21 = M + (k0 + bk) * ldm + k0;
@@ -624,28 +713,32 @@ static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, i
         // next block column first (rows rem x cols b1), then the rest of the trailing lower triangle
         if (use_ozaki) {
             // A22 -= L21 L21^T on the integer tensor cores: the panel is split into digits once, both updates read them
-            if ((rc = ozaki_slice_operand(L21, rem, bk, ldm, 0, 0, digits, 7, s1))) return rc;
-            if ((rc = ozaki_gemm_nt_sliced(digits, rem, 0, digits, rem, 0, bk, A22, lda, rem, b1, 1, 0, 0, 0, 7, s1))) return rc;
-            c1.note(cudaEventRecord(la->ev_col, s1));
+            if ((rc = ozaki_slice_operand(L21, rem, bk, ldm, 0, 0, digits, 7, su))) return rc;
+            if ((rc = ozaki_gemm_nt_sliced(digits, rem, 0, digits, rem, 0, bk, A22, lda, rem, b1, 1, 0, 0, 0, 7, su))) return rc;
+            g_trace.mark(4, k, su);
+            c1.note(cudaEventRecord(la->ev_col, su));
             if (rem > b1 && (rc = ozaki_gemm_nt_sliced(digits, rem, b1 / LF, digits, rem, b1 / LF, bk, A22 + b1 * lda + b1,
-                                                       lda, rem - b1, rem - b1, 1, 0, 0, 0, 7, s1)))
+                                                       lda, rem - b1, rem - b1, 1, 0, 0, 0, 7, su)))
                 return rc;
+            g_trace.mark(5, k, su);
         } else {
-            c1.note(gemm_f64<false, true>(L21, ldm, L21, ldm, A22, lda, rem, b1, bk, -1.0, 1.0, 0, 1, s1));
-            c1.note(cudaEventRecord(la->ev_col, s1));
+            c1.note(gemm_f64<false, true>(L21, ldm, L21, ldm, A22, lda, rem, b1, bk, -1.0, 1.0, 0, 1, su));
+            c1.note(cudaEventRecord(la->ev_col, su));
             if (rem > b1)
                 c1.note(gemm_f64<false, true>(L21 + b1 * ldm, ldm, L21 + b1 * ldm, ldm, A22 + b1 * lda + b1, lda, rem - b1,
-                                              rem - b1, bk, -1.0, 1.0, 0, 1, s1));
+                                              rem - b1, bk, -1.0, 1.0, 0, 1, su));
         }
     }
-    // join, then the large merges (most of the inverse's flops: machine-filling GEMMs) in post-order on the caller's stream
+    // join all three streams back into the caller's
     c2.note(cudaEventRecord(la->ev_panel, la->s2));
-    c1.note(cudaStreamWaitEvent(s1, la->ev_panel, 0));
-    for (const Merge& g : merges)
-        if (g.hi - g.lo > kSmallMerge)
-            run_merge(c1, M, ldm, bnd.data(), g, work, (use_ozaki && g_potrf_ozaki_merge) ? digits : nullptr,
-                      potrf_digit_bytes(np) - 1024);
-    const cudaError_t err = (c1.err != cudaSuccess) ? c1.err : c2.err;
+    c1.note(cudaEventRecord(la->ev_su, su));
+    c3.note(cudaEventRecord(la->ev_s3, s3));
+    cudaError_t je = cudaStreamWaitEvent(s1, la->ev_panel, 0);
+    if (je == cudaSuccess) je = cudaStreamWaitEvent(s1, la->ev_su, 0);
+    if (je == cudaSuccess) je = cudaStreamWaitEvent(s1, la->ev_s3, 0);
+    g_trace.mark(6, 0, s1);
+    cudaError_t err = (c1.err != cudaSuccess) ? c1.err : ((c2.err != cudaSuccess) ? c2.err : c3.err);
+    if (err == cudaSuccess) err = je;
     if (err != cudaSuccess) {
         set_error("socks_potrf_inv: CUDA call failed: %s", cudaGetErrorString(err));
         return SOCKS_ECUDA;
@@ -675,8 +768,11 @@ extern "C" int64_t socks_potrf_work_bytes(int64_t n) { return socks_padded_dim(n
 extern "C" int64_t socks_trtri_work_bytes(int64_t n) {
     const int64_t np = socks_padded_dim(n);
     if (np <= LF) return 16;
-    // merge scratch T (n2 x n1) + the digit form of one block-column panel (socks_potrf_inv's integer tensor-core updates)
-    return trtri_scratch_doubles(np) * 8 + potrf_digit_bytes(np);
+    // pure recursion: the merge scratch T (n2 x n1).  Look-ahead factorisation (more than 2 block columns, the same
+    // test as in socks_potrf_inv): recursion scratch, one T per large merge and the digit operands of the integer GEMMs.
+    const bool lookahead = g_potrf_nb > 0 && np > 2 * g_potrf_nb;
+    return lookahead ? std::max<int64_t>(trtri_scratch_doubles(np) * 8, potrf_lookahead_bytes(np))
+                     : trtri_scratch_doubles(np) * 8;
 }
 
 extern "C" int64_t socks_reduce_work_bytes(int64_t cols) { return 2 * CR_MAX_SPLITS * colreduce_ldpart(cols) * 8; }
@@ -777,8 +873,31 @@ extern "C" int socks_potrf_inv_set_block(int nb) {
         else g_potrf_merge_digits = (nb == -7) ? 7 : 8;  // -7 / -8: 7 / 8 digits in the merges
         return old;
     }
-    if (nb % LF == 0) g_potrf_nb = nb;
+    if (nb % LF == 0 && nb <= 2048) g_potrf_nb = nb;  // the recursion scratch is sized for block columns of <= 2048
     return old;
+}
+
+// Timeline of the NEXT socks_potrf_inv call: socks_dev_potrf_trace(nullptr, nullptr, 0) arms it; after the call (and a
+// stream synchronise) socks_dev_potrf_trace(codes, ms, cap) returns the number of events and fills code = 1000 kind +
+// step (kinds in PotrfTrace) and the time in ms since the start event.
+extern "C" int socks_dev_potrf_trace(int* codes, double* ms, int cap) {
+    if (!codes || !ms) {
+        for (cudaEvent_t e : g_trace.ev) cudaEventDestroy(e);
+        g_trace.ev.clear();
+        g_trace.code.clear();
+        g_trace.on = true;
+        return 0;
+    }
+    g_trace.on = false;
+    const int n = std::min<int>(cap, (int)g_trace.ev.size());
+    for (int i = 0; i < n; ++i) {
+        float t = 0.f;
+        cudaEventSynchronize(g_trace.ev[i]);
+        cudaEventElapsedTime(&t, g_trace.ev[0], g_trace.ev[i]);
+        codes[i] = g_trace.code[i];
+        ms[i] = t;
+    }
+    return n;
 }
 
 extern "C" int socks_diag_inv(const double* M, int64_t n, int64_t ldm, double* w, double* work,
