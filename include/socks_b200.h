@@ -100,7 +100,8 @@ int socks_gram_sym_family(int kind, const double* X, int64_t n, int dx, const do
 /* ---- Regularised solve: gym_socks/kernel/metrics.py:278-280 (inv(K + lambda N I)) ------ */
 
 int64_t socks_potrf_work_bytes(int64_t n);   /* dinv: np * 128 doubles                       */
-int64_t socks_trtri_work_bytes(int64_t n);   /* scratch for the recursive triangular inverse */
+int64_t socks_trtri_work_bytes(int64_t n);   /* scratch of socks_trtri / socks_potrf_inv (for n > 2048: recursion scratch,
+                                                 one T per large merge < np^2/2 doubles, digit operands: 4.4 GB at n = 20 000) */
 int64_t socks_reduce_work_bytes(int64_t cols); /* partial sums for column reductions         */
 
 /* In-place lower Cholesky G = L L^T of the padded matrix (blocked, recursive, DMMA trailing
@@ -124,9 +125,12 @@ int socks_pad_spd(const double* Gin, int64_t n, int64_t ldin, double diag_add, d
  * blocks (L21 = A21 inv(L11)^T), so there are no leaf TRSM kernels.  work: socks_trtri_work_bytes(n). */
 int socks_potrf_inv(double* G, int64_t n, int64_t ldg, double* M, int64_t ldm, double* work, int* info_dev,
                     int keep_l, socks_stream_t stream);
-/* socks_potrf_inv factors right-looking over 1024-wide block columns with a look-ahead of one: the next diagonal block
- * and panel run on an internal high-priority stream while the trailing update proceeds; the library owns that stream
- * and joins it back into `stream` before returning. */
+/* socks_potrf_inv factors right-looking over 1024-wide block columns with a look-ahead of one on three internal
+ * streams that the library owns, forks from `stream` and joins back into it before returning: the next diagonal block
+ * and panel (greatest priority), the trailing updates (middle), and the merges of inv(L) (least priority; each merge
+ * M21 = -M22 (L21 M11) is two products that start as soon as their inputs exist, so they fill what the factorisation
+ * leaves idle).  The large GEMMs -- trailing updates and merges -- run as fp64-accurate digit GEMMs on the integer
+ * tensor cores (tcgen05.mma kind::i8; 7 digits in the updates, 8 in the merges). */
 
 /* w[i] = sum_k M[k][i]^2 = diag(inv(G))[i]  (the only part of W the SR algorithms use:
  * np.einsum("ii,ij->ij", W, CXY), kernel_sr.py:45).  work: socks_reduce_work_bytes(np). */
