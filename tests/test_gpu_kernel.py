@@ -146,6 +146,32 @@ def test_factorization_pieces(n, d, sigma, lam, with_u, two_pass):
         assert np.array_equal(Wp[n:, n:], np.eye(npad - n)) and not Wp[n:, :n].any() and not Wp[:n, n:].any()
 
 
+def test_factorization_engine_switch():
+    """metrics.set_factorization_engine: the FP64 DMMA engine and the integer tensor-core engine give the same inverse."""
+    torch, dv, _lib, mt = _mods()
+    rng = np.random.default_rng(11)
+    n = 3000
+    X = rng.uniform(-1.1, 1.1, (n, 2))
+    res = {}
+    try:
+        for engine in ("fp64", "int8"):
+            mt.set_factorization_engine(engine)
+            fac = mt.factorize(X, None, mt.RBFSpec(sigma=0.2), 1e-4)
+            fac.check()
+            res[engine] = (fac.diag().cpu().numpy(), fac.full()[:n, :n].cpu().numpy())
+    finally:
+        mt.set_factorization_engine("int8")
+    with pytest.raises(ValueError):
+        mt.set_factorization_engine("fp32")
+    G = orc.rbf_kernel(X, X, 0.2)
+    G[np.diag_indices(n)] += 1e-4 * n
+    cond = np.linalg.cond(G)
+    assert np.max(np.abs(res["int8"][0] - res["fp64"][0]) / res["fp64"][0]) <= 100 * cond * 2.0 ** -53
+    for engine in ("fp64", "int8"):
+        R = res[engine][1] @ G - np.eye(n)
+        assert np.abs(R).max() <= 100 * cond * 2.0 ** -53
+
+
 @pytest.mark.parametrize("n,nb,keep_l", [(3300, 1024, True), (2900, 512, False), (1400, 256, True), (2100, 1024, False)])
 def test_potrf_inv_lookahead_matches_recursion_and_numpy(n, nb, keep_l):
     """socks_potrf_inv's look-ahead factorisation (second stream, block columns of `nb`, ragged last block) against the
