@@ -377,8 +377,12 @@ __global__ void pad_spd_kernel(const double* __restrict__ Gin, int64_t n, int64_
 struct CholCtx {
     cudaStream_t st;
     cudaError_t err = cudaSuccess;
+    int rc = SOCKS_OK;  // first failing status of a library call made on this stream (its message is already set)
     void note(cudaError_t e) {
         if (err == cudaSuccess && e != cudaSuccess) err = e;
+    }
+    void note_rc(int r) {
+        if (rc == SOCKS_OK && r != SOCKS_OK) rc = r;
     }
 };
 
@@ -580,7 +584,7 @@ static void merge_product(CholCtx& cx, int which, double* M, int64_t ldm, const 
             if (!rc) rc = ozaki_slice_operand(T, n1, n2, n1, 1, 0, db, S, cx.st);
             if (!rc) rc = ozaki_gemm_nt_sliced(da, n2, 0, db, n1, 0, n2, M21, ldm, n2, n1, 0, 2, 1, 0, S, cx.st);
         }
-        if (rc) cx.note(cudaErrorUnknown);
+        cx.note_rc(rc);
         return;
     }
     if (which == 1)
@@ -737,6 +741,7 @@ static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, i
     if (je == cudaSuccess) je = cudaStreamWaitEvent(s1, la->ev_su, 0);
     if (je == cudaSuccess) je = cudaStreamWaitEvent(s1, la->ev_s3, 0);
     g_trace.mark(6, 0, s1);
+    if (c2.rc || c3.rc) return c2.rc ? c2.rc : c3.rc;  // an integer-GEMM call failed: its message stands
     cudaError_t err = (c1.err != cudaSuccess) ? c1.err : ((c2.err != cudaSuccess) ? c2.err : c3.err);
     if (err == cudaSuccess) err = je;
     if (err != cudaSuccess) {
