@@ -275,6 +275,14 @@ int64_t socks_srmax_fit_work_bytes(int64_t n, int P);
 int socks_srmax_fit(const double* X, const double* Y, const double* U, const double* A, const double* w, int64_t n,
                     int d, int du, int P, double scale, int divide, const double* tubes, int problem, int T,
                     double* CUA, double* vf, int64_t ldvf, double* work, socks_stream_t stream);
+/* The same fit with the backward recursion's contractions on the integer tensor cores (csrc/ozaki.cu: kernel values and
+ * coefficients as `slices` unsigned 7-bit digits, exact int8 MMAs).  *flagged (device int) receives the number of
+ * samples whose normaliser is below `tau` of the scale, i.e. outside the fixed-point range: if it is not 0 the caller
+ * must redo the fit with socks_srmax_fit.  work: 1024-byte aligned, socks_srmax_fit_i8_work_bytes. */
+int64_t socks_srmax_fit_i8_work_bytes(int64_t n, int P, int slices);
+int socks_srmax_fit_i8(const double* X, const double* Y, const double* U, const double* A, const double* w, int64_t n, int d,
+                       int du, int P, double scale, int divide, const double* tubes, int problem, int T, double* CUA,
+                       double* vf, int64_t ldvf, void* work, int slices, double tau, int* flagged, socks_stream_t stream);
 
 /* KernelMaximalSR.predict (kernel_sr_max.py:368-384): out (T x m); test points are processed `chunk` at a time (one
  * Gram tile + one DMMA GEMM for all T rows + fused divide/max/step per chunk). */

@@ -65,6 +65,8 @@ SIGNATURES = {
     "socks_sr_fit": (_I, [_P, _P, _P, _L, _I, _D, _I, _P, _I, _I, _P, _L, _P, _P, _P]),
     "socks_srmax_fit_work_bytes": (_L, [_L, _I]),
     "socks_srmax_fit": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _D, _I, _P, _I, _I, _P, _P, _L, _P, _P]),
+    "socks_srmax_fit_i8_work_bytes": (_L, [_L, _I, _I]),
+    "socks_srmax_fit_i8": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _D, _I, _P, _I, _I, _P, _P, _L, _P, _I, _D, _P, _P]),
     "socks_srmax_predict_work_bytes": (_L, [_L, _I, _I, _L]),
     "socks_srmax_predict": (_I, [_P, _P, _P, _L, _P, _L, _I, _I, _D, _I, _P, _L, _P, _I, _I, _P, _L, _P, _L, _P]),
     "socks_srmax_predict_i8_work_bytes": (_L, [_L, _I, _I, _L, _I]),

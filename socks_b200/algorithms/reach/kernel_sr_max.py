@@ -84,6 +84,11 @@ class KernelMaximalSR:
         self._tubes = pack_tubes(self.constraint_tube, self.target_tube, T, d)
         return self.state_tensors()
 
+    @staticmethod
+    def _kmul_negative(kparams):
+        scale, divide = kparams
+        return (1.0 / scale if divide else scale) < 0.0
+
     def fit(self, S, A):
         self._validate_params(S, A)
         self._validate_data(S)
@@ -117,6 +122,23 @@ class KernelMaximalSR:
             # one enqueue (csrc/compose.cu: socks_srmax_fit): CUA, K(X,Y), normaliser GEMM, T-1 x (pack, GEMM, max/step)
             logger.debug("Computing covariance matrices and value functions.")
             CUA = dv.empty(n, P)
+            if self.predict_engine == "i8" and d <= 8 and self._kmul_negative(kp_xy):
+                # the backward recursion on the integer tensor cores; samples outside the fixed-point range (counted
+                # on the device) send the whole fit to the FP64 engine below
+                import torch
+
+                wk = dv.work(lib.socks_srmax_fit_i8_work_bytes(n, P, int(self.predict_slices)) + 1024)
+                base = (wk.data_ptr() + 1023) // 1024 * 1024
+                flagged = torch.zeros(1, dtype=torch.int32, device=Xd.device)
+                _lib.call("socks_srmax_fit_i8", dv.ptr(Xd), dv.ptr(Yd), dv.ptr(Ud), dv.ptr(Ad), dv.ptr(w), n, d, Ud.shape[1],
+                          P, float(kp_xy[0]), int(kp_xy[1]), dv.ptr(self._tubes), prob, T, dv.ptr(CUA), dv.ptr(vf), n, base,
+                          int(self.predict_slices), float(self.predict_tau), dv.ptr(flagged), st)
+                self.last_fit_flagged = int(flagged.item())
+                if self.last_fit_flagged == 0:
+                    self._CUA = CUA
+                    self._vf = vf[:T]
+                    self._vf_host = None
+                    return self
             wk = dv.work(lib.socks_srmax_fit_work_bytes(n, P))
             _lib.call("socks_srmax_fit", dv.ptr(Xd), dv.ptr(Yd), dv.ptr(Ud), dv.ptr(Ad), dv.ptr(w), n, d, Ud.shape[1], P,
                       float(kp_xy[0]), int(kp_xy[1]), dv.ptr(self._tubes), prob, T, dv.ptr(CUA), dv.ptr(vf), n,

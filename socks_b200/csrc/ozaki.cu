@@ -778,6 +778,105 @@ static int srmax_predict_i8_impl(const double* X, const double* w, const double*
 
 }  // namespace socks
 
+// ---- KernelMaximalSR fit on the same engine (kernel_sr_max.py:323-366) -----------------------------------------------
+// The backward recursion is the predict contraction with the NEXT STATES Y as the points, one time step at a time
+// (vf[t] needs vf[t+1]): the digits of K(x_i, y_j) are produced once, each step slices the two coefficient rows
+// {w, vf[t+1] w} x CUA (2 P columns), runs the integer GEMM and applies the max / step.  The normaliser is the same at
+// every step, so the points whose normaliser is too small for the fixed-point range are counted once: if any, the caller
+// redoes the fit with the FP64 engine (socks_srmax_fit).
+namespace socks {
+
+template <int S>
+static int srmax_fit_i8_impl(const double* X, const double* Y, const double* CUA, const double* w, int64_t n, int d, int P,
+                             double kmul, const double* tubes, int problem, int T, double* vf, int64_t ldvf, uint8_t* work,
+                             double tau, int* flagged, cudaStream_t st) {
+    int rc = og_configure<S, 7>();
+    if (rc) return rc;
+    const int kblocks = (int)(pad_to(n, OZ_KB) / OZ_KB);
+    const int64_t ldbm = pad_to(2 * (int64_t)P, 128), ctiles = ldbm / OZ_BM;
+    const int64_t mc = pad_to(n, OZ_BM), ptiles = mc / OZ_BM;
+    uint8_t* Bop = work;
+    uint8_t* Aop = Bop + pad_to(ctiles * kblocks * (int64_t)S * OZ_A_BYTES, 1024);
+    double* Cm = reinterpret_cast<double*>(Aop + pad_to(ptiles * kblocks * (int64_t)S * OZ_A_BYTES, 1024));
+    double* rowscale = Cm + mc * ldbm;
+    double* inv = rowscale + 2;
+    double* colscale = inv + 2;
+    int* list = reinterpret_cast<int*>(colscale + ldbm);  // [0] = count, [1..] = flagged points (only the count is returned)
+    const dim3 gs((unsigned)ceil_div(kblocks, 16), (unsigned)ptiles);
+#define SOCKS_OZ_CASE(DD)                                                                 \
+    case DD:                                                                              \
+        oz_slice_points_kernel<DD, S><<<gs, 128, 0, st>>>(X, n, Y, n, kmul, Aop, kblocks); \
+        break;
+    switch (d) {
+        SOCKS_OZ_CASE(1) SOCKS_OZ_CASE(2) SOCKS_OZ_CASE(3) SOCKS_OZ_CASE(4)
+        SOCKS_OZ_CASE(5) SOCKS_OZ_CASE(6) SOCKS_OZ_CASE(7) SOCKS_OZ_CASE(8)
+    }
+#undef SOCKS_OZ_CASE
+    SOCKS_CHECK_LAUNCH();
+    SOCKS_CUDA(cudaMemsetAsync(list, 0, sizeof(int), st));
+    for (int t = T - 2; t >= 0; --t) {
+        const double* vfp = vf + (int64_t)t * ldvf;  // row 1 of the pair = vf[t + 1]
+        oz_rowscale_kernel<<<2, 256, 0, st>>>(w, vfp, ldvf, n, rowscale, inv);
+        oz_colscale_kernel<<<(unsigned)ceil_div(ldbm, 256), 256, 0, st>>>(rowscale, P, 2, ldbm, colscale);
+        oz_slice_coef_kernel<S><<<dim3((unsigned)ceil_div(kblocks, 16), (unsigned)ctiles), 128, 0, st>>>(CUA, n, P, w, vfp, ldvf, 2,
+                                                                                                       inv, Bop, kblocks);
+        SOCKS_CHECK_LAUNCH();
+        oz_gemm_nt_kernel<S, 7><<<dim3((unsigned)ctiles, (unsigned)ptiles), OZ_THREADS, OgCfg<S>::SMEM_BYTES, st>>>(
+            Aop, nullptr, Bop, colscale, Cm, ldbm, kblocks, 0, 1, 0, 0);
+        SOCKS_CHECK_LAUNCH();
+        if (t == T - 2) {
+            oz_flag_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(Cm, ldbm, n, P, rowscale, tau, 0, list);
+            SOCKS_CHECK_LAUNCH();
+        }
+        rc = socks_srmax_step(Cm, ldbm, nullptr, 0, n, P, 2, t, Y, d, tubes, problem, T, vf, ldvf, 0, (socks_stream_t)st);
+        if (rc) return rc;
+    }
+    SOCKS_CUDA(cudaMemcpyAsync(flagged, list, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return SOCKS_OK;
+}
+
+}  // namespace socks
+
+extern "C" int64_t socks_srmax_fit_i8_work_bytes(int64_t n, int P, int slices) {
+    const int64_t kblocks = pad_to(n, OZ_KB) / OZ_KB, ldbm = pad_to(2 * (int64_t)P, 128), mc = pad_to(n, OZ_BM);
+    return pad_to((ldbm / OZ_BM) * kblocks * slices * OZ_A_BYTES, 1024) + pad_to((mc / OZ_BM) * kblocks * slices * OZ_A_BYTES, 1024) +
+           (mc * ldbm + 4 + ldbm) * 8 + (n + 2) * 4 + 2048;
+}
+
+extern "C" int socks_srmax_fit_i8(const double* X, const double* Y, const double* U, const double* A, const double* w, int64_t n,
+                                  int d, int du, int P, double scale, int divide, const double* tubes, int problem, int T,
+                                  double* CUA, double* vf, int64_t ldvf, void* work, int slices, double tau, int* flagged,
+                                  socks_stream_t stream) {
+    SOCKS_CHECK_ARG(X && Y && U && A && w, 1);
+    SOCKS_CHECK_ARG(n >= 1, 6);
+    SOCKS_CHECK_ARG(d >= 1 && d <= 8, 7);
+    SOCKS_CHECK_ARG(P >= 1, 9);
+    SOCKS_CHECK_ARG(scale == scale && (!divide || scale != 0.0), 10);
+    SOCKS_CHECK_ARG(T >= 1, 14);
+    SOCKS_CHECK_ARG(CUA != nullptr, 15);
+    SOCKS_CHECK_ARG(vf != nullptr && ldvf >= n, 16);
+    SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 1023) == 0, 18);
+    SOCKS_CHECK_ARG(slices >= 6 && slices <= 8, 19);
+    SOCKS_CHECK_ARG(tau >= 0.0, 20);
+    SOCKS_CHECK_ARG(flagged != nullptr, 21);
+    const double kmul = divide ? 1.0 / scale : scale;
+    SOCKS_CHECK_ARG(kmul < 0.0, 10);
+    int rc = socks_gram_rbf(U, n, A, P, du, scale, divide, nullptr, CUA, P, stream);  // kernel_sr_max.py:332
+    if (rc) return rc;
+    uint8_t* wk = reinterpret_cast<uint8_t*>(work);
+    // vf[T-1] = 1_target(Y) (:59); Cm is not read for R = 1
+    rc = socks_srmax_step(reinterpret_cast<const double*>(wk), 128, nullptr, 0, n, P, 1, 0, Y, d, tubes, problem, T, vf, ldvf, 1,
+                          stream);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (T == 1) return cudaMemsetAsync(flagged, 0, sizeof(int), st) == cudaSuccess ? SOCKS_OK : SOCKS_ECUDA;
+    switch (slices) {
+        case 6: return srmax_fit_i8_impl<6>(X, Y, CUA, w, n, d, P, kmul, tubes, problem, T, vf, ldvf, wk, tau, flagged, st);
+        case 7: return srmax_fit_i8_impl<7>(X, Y, CUA, w, n, d, P, kmul, tubes, problem, T, vf, ldvf, wk, tau, flagged, st);
+        default: return srmax_fit_i8_impl<8>(X, Y, CUA, w, n, d, P, kmul, tubes, problem, T, vf, ldvf, wk, tau, flagged, st);
+    }
+}
+
 extern "C" int64_t socks_srmax_predict_i8_work_bytes(int64_t n, int P, int T, int64_t chunk, int slices) {
     const int64_t kblocks = pad_to(n, OZ_KB) / OZ_KB, ldbm = pad_to((int64_t)T * P, 128), mc = pad_to(chunk, OZ_BM);
     return pad_to((ldbm / OZ_BM) * kblocks * slices * OZ_A_BYTES, 1024) + pad_to((mc / OZ_BM) * kblocks * slices * OZ_A_BYTES, 1024) +

@@ -388,3 +388,31 @@ def test_kernel_sr_max_int8_engine_matches_fp64_engine(slices):
     # flagged points come from the FP64 path itself: identical bits
     idx = np.arange(1500, len(pts))[-20:]
     assert np.array_equal(got[:, idx], want[:, idx], equal_nan=True)
+
+
+def test_kernel_sr_max_fit_int8_engine_matches_fp64_engine():
+    """KernelMaximalSR.fit: the backward recursion on the integer tensor cores (socks_srmax_fit_i8) against the FP64
+    engine and the oracle; a threshold that flags every sample must hand the whole fit to the FP64 engine (same bits)."""
+    _, _, KernelMaximalSR, _, _, rbf = _api()
+    n, T, P = 1237, 7, 37
+    X, U, Y = syn.integrator_sample(n, seed=91)
+    A = np.linspace(-1, 1, P).reshape(-1, 1)
+    ct, tt = syn.integrator_tubes(T)
+
+    def fit(engine, tau=None):
+        alg = KernelMaximalSR(time_horizon=T, constraint_tube=ct, target_tube=tt, problem="FHT",
+                              kernel_fn=partial(rbf, sigma=0.1), regularization_param=1.0)
+        alg.predict_engine = engine
+        if tau is not None:
+            alg.predict_tau = tau
+        alg.fit_arrays(X, U, Y, A)
+        return alg, alg._vf.cpu().numpy()
+
+    a64, v64 = fit("f64")
+    a8, v8 = fit("i8")
+    assert a8.last_fit_flagged == 0
+    assert np.max(np.abs(v8 - v64)) <= 1e-9
+    o = orc.KernelMaximalSROracle(T, ct, tt, "FHT", 0.1, 1.0).fit(X, U, Y, A)
+    assert np.max(np.abs(v8 - o.value_functions)) <= TOL
+    afb, vfb = fit("i8", tau=1e30)
+    assert afb.last_fit_flagged == n and np.array_equal(vfb, v64)
