@@ -479,6 +479,7 @@ def maximal_sr_extra(n, m, T, d, ct, tt, X, U, Y, pts, P=100):
            "predict_gemm_tflops": 2.0 * npad * m * cols / t_pred / 1e12,
            "engine": f"{alg.predict_engine} ({alg.predict_slices} slices)" if alg.predict_engine == "i8" else "f64",
            "flagged_points": getattr(alg, "last_flagged", None),
+           "fit_flagged_samples": getattr(alg, "last_fit_flagged", None),  # 0: the backward recursion ran on the i8 engine too
            "note": "predict = K(X,pts)^T [diag(coef_r) CUA]_r per chunk of test points + fused max/step; engine i8: Ozaki "
                    "digit splitting, exact int8 products on tcgen05.mma kind::i8 (predict_gemm_tflops is then the "
                    "fp64-EQUIVALENT rate of the contraction), FP64 DMMA for flagged points"}

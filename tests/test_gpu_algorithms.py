@@ -401,7 +401,7 @@ def test_kernel_sr_max_fit_int8_engine_matches_fp64_engine():
 
     def fit(engine, tau=None):
         alg = KernelMaximalSR(time_horizon=T, constraint_tube=ct, target_tube=tt, problem="FHT",
-                              kernel_fn=partial(rbf, sigma=0.1), regularization_param=1.0)
+                              kernel_fn=partial(rbf, sigma=0.25), regularization_param=1.0)
         alg.predict_engine = engine
         if tau is not None:
             alg.predict_tau = tau
@@ -410,9 +410,9 @@ def test_kernel_sr_max_fit_int8_engine_matches_fp64_engine():
 
     a64, v64 = fit("f64")
     a8, v8 = fit("i8")
-    assert a8.last_fit_flagged == 0
+    assert a8.last_fit_flagged == 0  # sigma = 0.25: every next state has neighbours for every action
     assert np.max(np.abs(v8 - v64)) <= 1e-9
-    o = orc.KernelMaximalSROracle(T, ct, tt, "FHT", 0.1, 1.0).fit(X, U, Y, A)
+    o = orc.KernelMaximalSROracle(T, ct, tt, "FHT", 0.25, 1.0).fit(X, U, Y, A)
     assert np.max(np.abs(v8 - o.value_functions)) <= TOL
     afb, vfb = fit("i8", tau=1e30)
     assert afb.last_fit_flagged == n and np.array_equal(vfb, v64)
