@@ -149,6 +149,9 @@ int socks_potrs(const double* M, int64_t n, int64_t ldm, double* B, int64_t nrhs
 
 /* W = M^T M = inv(G), full symmetric np x np (what regularized_inverse returns). */
 int socks_lauum(const double* M, int64_t n, int64_t ldm, double* W, int64_t ldw, socks_stream_t stream);
+/* The same product as an fp64-accurate digit GEMM on the integer tensor cores (8 digits); work: socks_lauum_i8_work_bytes. */
+int64_t socks_lauum_i8_work_bytes(int64_t n);
+int socks_lauum_i8(const double* M, int64_t n, int64_t ldm, double* W, int64_t ldw, void* work, socks_stream_t stream);
 
 /* ---- Stochastic reachability: gym_socks/algorithms/reach/kernel_sr.py:31-69 ------------ */
 

@@ -42,6 +42,8 @@ SIGNATURES = {
     "socks_diag_inv": (_I, [_P, _L, _L, _P, _P, _P]),
     "socks_potrs": (_I, [_P, _L, _L, _P, _L, _L, _P, _P]),
     "socks_lauum": (_I, [_P, _L, _L, _P, _L, _P]),
+    "socks_lauum_i8_work_bytes": (_L, [_L]),
+    "socks_lauum_i8": (_I, [_P, _L, _L, _P, _L, _P, _P]),
     "socks_sr_recursion": (_I, [_P, _L, _L, _L, _P, _I, _P, _I, _I, _P, _L, _P, _L, _P, _P]),
     "socks_sr_pack_bytes": (_L, [_L, _I, _I]),
     "socks_sr_pack": (_I, [_P, _P, _P, _L, _L, _I, _D, _I, _I, _P, _P]),

@@ -963,6 +963,29 @@ extern "C" int socks_potrs(const double* M, int64_t n, int64_t ldm, double* B, i
     return SOCKS_OK;
 }
 
+// The same product on the integer tensor cores: W = A A^T with A = M^T (operand rows = columns of M, zero for k before
+// the row: both K clips apply), 8 digits (the columns of inv(L) span many orders of magnitude, see g_potrf_merge_digits).
+extern "C" int64_t socks_lauum_i8_work_bytes(int64_t n) {
+    const int64_t np = socks_padded_dim(n);
+    return ozaki_operand_bytes(np, np, 8) + 2048;
+}
+
+extern "C" int socks_lauum_i8(const double* M, int64_t n, int64_t ldm, double* W, int64_t ldw, void* work,
+                              socks_stream_t stream) {
+    int rc = check_square(M, n, ldm, 1);
+    if (rc) return rc;
+    if ((rc = check_square(W, n, ldw, 4))) return rc;
+    SOCKS_CHECK_ARG(work != nullptr, 6);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t np = socks_padded_dim(n);
+    uint8_t* buf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(work) + 1023) & ~(uintptr_t)1023);
+    if ((rc = ozaki_slice_operand(M, np, np, ldm, 1, 2, buf, 8, st))) return rc;
+    if ((rc = ozaki_gemm_nt_sliced(buf, np, 0, buf, np, 0, np, W, ldw, np, np, 1, 1, 2, 1, 8, st))) return rc;
+    symmetrize_kernel<<<dim3((unsigned)(np / 32), (unsigned)(np / 32)), dim3(32, 8), 0, st>>>(W, ldw);
+    SOCKS_CHECK_LAUNCH();
+    return SOCKS_OK;
+}
+
 extern "C" int socks_lauum(const double* M, int64_t n, int64_t ldm, double* W, int64_t ldw, socks_stream_t stream) {
     int rc = check_square(M, n, ldm, 1);
     if (rc) return rc;

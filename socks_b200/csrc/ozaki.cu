@@ -450,7 +450,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     const int ctile = blockIdx.x, ptile = blockIdx.y;
     if (lower_only && ctile > ptile) return;
     int kb_lo = 0, kb_hi = kblocks;
-    if (tri_a) kb_hi = min(kb_hi, (ptile + 1) * (OZ_BM / OZ_KB));  // A(i, k) = 0 for k beyond row tile i
+    if (tri_a == 1) kb_hi = min(kb_hi, (ptile + 1) * (OZ_BM / OZ_KB));  // A(i, k) = 0 for k beyond row tile i
+    if (tri_a == 2) kb_lo = max(kb_lo, ptile * (OZ_BM / OZ_KB));        // A(i, k) = 0 for k before row tile i
     if (tri_b) kb_lo = max(kb_lo, ctile * (BN / OZ_KB));           // B(k, j) = 0 for k before column tile j
     const int nk = max(kb_hi - kb_lo, 0);
     const int nchunks = (nk + OG_KCHUNK - 1) / OG_KCHUNK;

@@ -13,7 +13,8 @@ int64_t ozaki_operand_bytes(int64_t rows, int64_t K, int S);
 int ozaki_slice_operand(const double* P, int64_t rows, int64_t K, int64_t ld, int trans, int tri, uint8_t* buf, int S,
                         cudaStream_t st);
 // C (m x n, ldc) (op)= A B^T with A = operand rows [128 a_tile0, ..) of abuf, B likewise (m % 128 == 0, n % 128 == 0);
-// mode 0: C -= AB^T, 1: C = AB^T, 2: C = -AB^T; tri_a / tri_b clip each tile's K range (A lower / B "k >= n").
+// mode 0: C -= AB^T, 1: C = AB^T, 2: C = -AB^T; tri_a / tri_b clip each tile's K range (tri_a 1: A(i,k) = 0 for k > i,
+// tri_a 2: A(i,k) = 0 for k < i; tri_b: B(k,j) = 0 for k < j), at 128-tile granularity.
 int ozaki_gemm_nt_sliced(const uint8_t* abuf, int64_t a_rows_total, int64_t a_tile0, const uint8_t* bbuf, int64_t b_rows_total,
                          int64_t b_tile0, int64_t K, double* C, int64_t ldc, int64_t m, int64_t n, int lower_only, int mode,
                          int tri_a, int tri_b, int S, cudaStream_t st);

@@ -169,6 +169,9 @@ def sharded_bandwidth_guard(spec):
                          "full set and pass kparams to predict_dev on every rank.")
 
 
+_ENGINE = {"factorization": "int8"}
+
+
 def set_factorization_engine(engine="int8"):
     """Which tensor cores the large GEMMs of the Cholesky + inverse run on (process-wide, csrc/chol.cu):
     "int8" (default): fp64-accurate digit GEMMs on tcgen05.mma kind::i8 -- 7 digits in the trailing updates, 8 in the
@@ -177,6 +180,7 @@ def set_factorization_engine(engine="int8"):
     Not part of the reference API (gym_socks has no such choice); call it before fitting."""
     if engine not in ("int8", "fp64"):
         raise ValueError(f"engine must be 'int8' or 'fp64', not {engine!r}")
+    _ENGINE["factorization"] = engine
     lib = _lib.load()
     lib.socks_potrf_inv_set_block(-4 if engine == "int8" else -3)
     lib.socks_potrf_inv_set_block(-6 if engine == "int8" else -5)
@@ -266,7 +270,11 @@ class Factorization:
         if self._W is None:
             M = self.inverse_factor()
             self._W = dv.empty(self.np, self.np)
-            _lib.call("socks_lauum", dv.ptr(M), self.n, self.np, dv.ptr(self._W), self.np, dv.stream())
+            if _ENGINE["factorization"] == "int8" and self.np > 2048:
+                wk = dv.work(_lib.load().socks_lauum_i8_work_bytes(self.n))
+                _lib.call("socks_lauum_i8", dv.ptr(M), self.n, self.np, dv.ptr(self._W), self.np, dv.ptr(wk), dv.stream())
+            else:
+                _lib.call("socks_lauum", dv.ptr(M), self.n, self.np, dv.ptr(self._W), self.np, dv.stream())
         return self._W
 
     def release_factors(self):

@@ -18,6 +18,7 @@ res, ref_w = [], None
 for name, upd, mrg, dg in (("fp64 DMMA everywhere", -3, -5, -8), ("integer updates (7 digits), DMMA merges", -4, -5, -8),
                            ("integer updates (7 digits) and merges (7 digits)", -4, -6, -7),
                            ("integer updates (7 digits) and merges (8 digits): shipped", -4, -6, -8)):
+    mt.set_factorization_engine("fp64" if upd == -3 else "int8")  # also selects the engine of W = M^T M (socks_lauum[_i8])
     lib.socks_potrf_inv_set_block(upd)
     lib.socks_potrf_inv_set_block(mrg)
     lib.socks_potrf_inv_set_block(dg)
@@ -31,14 +32,14 @@ for name, upd, mrg, dg in (("fp64 DMMA everywhere", -3, -5, -8), ("integer updat
     R[torch.arange(64), torch.arange(64)] -= 1.0
     if ref_w is None:
         ref_w = w
-    rec = {"N": n, "engine": name, "residual_max_WG_minus_I": float(R.abs().max()),
+    rec = {"N": n, "engine": name + ("; W = M^T M on FP64 DMMA" if upd == -3 else "; W = M^T M as an 8-digit integer GEMM"),
+           "residual_max_WG_minus_I": float(R.abs().max()),
            "diag_W_max_rel_diff_vs_dmma": float(((w - ref_w).abs() / ref_w.abs()).max())}
     print(json.dumps(rec), flush=True)
     res.append(rec)
     del fac, Wd, R, G
     torch.cuda.empty_cache()
-lib.socks_potrf_inv_set_block(-4)
-lib.socks_potrf_inv_set_block(-6)
+mt.set_factorization_engine("int8")
 lib.socks_potrf_inv_set_block(-8)
 if len(sys.argv) > 2:
     json.dump(res, open(sys.argv[2], "w"), indent=1)
