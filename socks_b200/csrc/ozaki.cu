@@ -866,8 +866,8 @@ extern "C" int socks_srmax_fit_i8(const double* X, const double* Y, const double
     if (rc) return rc;
     uint8_t* wk = reinterpret_cast<uint8_t*>(work);
     // vf[T-1] = 1_target(Y) (:59); Cm is not read for R = 1
-    rc = socks_srmax_step(reinterpret_cast<const double*>(wk), 128, nullptr, 0, n, P, 1, 0, Y, d, tubes, problem, T, vf, ldvf, 1,
-                          stream);
+    rc = socks_srmax_step(reinterpret_cast<const double*>(wk), pad_to(2 * (int64_t)P, 128), nullptr, 0, n, P, 1, 0, Y, d, tubes,
+                          problem, T, vf, ldvf, 1, stream);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (T == 1) return cudaMemsetAsync(flagged, 0, sizeof(int), st) == cudaSuccess ? SOCKS_OK : SOCKS_ECUDA;
