@@ -10,7 +10,25 @@ using namespace socks;
 constexpr int SLICE = 4096;           // 128 rows x 32 B
 constexpr int TILE_KB = 7 * SLICE;    // one K-block of one 128-row tile: 7 digit slices
 
-template <int NS, int STAGES>         // NS slices of each operand per K-block (4: pass A, 7: pass B)
+__device__ __forceinline__ void bulk_g2s_mc(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            umma::smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(umma::smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     umma::smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// MC = 1: cluster of two CTAs along x sharing the A tile: each loads half of the A slices and multicasts them to both
+template <int NS, int STAGES, int MC = 0>         // NS slices of each operand per K-block (4: pass A, 7: pass B)
 __global__ void __launch_bounds__(128, 1) pipe_kernel(const uint8_t* __restrict__ buf, int kblocks, int tiles, int col_tiles,
                                                        long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -24,17 +42,19 @@ __global__ void __launch_bounds__(128, 1) pipe_kernel(const uint8_t* __restrict_
     if (threadIdx.x == 32) {
         for (int i = 0; i < STAGES; ++i) {
             umma::mbar_init(full + i, 1);
-            umma::mbar_init(empty + i, 1);
+            umma::mbar_init(empty + i, MC ? 2 : 1);
         }
         umma::mbar_init(done, 1);
         umma::mbar_fence_init();
     }
     umma::tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
     umma::tc_fence_after();
     const uint32_t tmem = slot;
     const long long t0 = clock64();
-    const int a_tile = blockIdx.x / col_tiles, b_tile = 2 + blockIdx.x % col_tiles;
+    const int rank = MC ? (int)(blockIdx.x & 1) : 0;
+    const int a_tile = MC ? (int)(blockIdx.x >> 1) % 8 : blockIdx.x / col_tiles, b_tile = 8 + blockIdx.x % col_tiles;
     if (warp == 2 && lane == 0) {
         uint32_t it = 0;
         for (int t = 0; t < tiles; ++t) {
@@ -45,7 +65,12 @@ __global__ void __launch_bounds__(128, 1) pipe_kernel(const uint8_t* __restrict_
                 if (round > 0) umma::mbar_wait(empty + st, (round - 1) & 1u);
                 uint8_t* s = smem + st * STAGE;
                 umma::mbar_arrive_expect_tx(full + st, STAGE);
-                umma::bulk_g2s(s, a_src + (size_t)kb * TILE_KB, NS * SLICE, full + st);
+                if (MC) {
+                    constexpr int HALF = NS * SLICE / 2;  // multiple of 16 bytes
+                    bulk_g2s_mc(s + rank * HALF, a_src + (size_t)kb * TILE_KB + rank * HALF, HALF, full + st, (uint16_t)3);
+                } else {
+                    umma::bulk_g2s(s, a_src + (size_t)kb * TILE_KB, NS * SLICE, full + st);
+                }
                 umma::bulk_g2s(s + NS * SLICE, b_src + (size_t)kb * TILE_KB, NS * SLICE, full + st);
             }
         }
@@ -75,7 +100,8 @@ __global__ void __launch_bounds__(128, 1) pipe_kernel(const uint8_t* __restrict_
                                              umma::smem_desc_kmajor_noswizzle(sB + b * SLICE, 128, 256), idesc,
                                              (kb > 0 || a > 0) ? 1u : 0u);
                 }
-                umma::mma_commit(empty + st);
+                if (MC) mma_commit_mc(empty + st, (uint16_t)3);
+                else umma::mma_commit(empty + st);
             }
         }
         umma::mma_commit(done);
@@ -84,17 +110,33 @@ __global__ void __launch_bounds__(128, 1) pipe_kernel(const uint8_t* __restrict_
     }
     umma::tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();  // nobody leaves while the peer may still write into its shared memory
     if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
-template <int NS, int STAGES>
+template <int NS, int STAGES, int MC = 0>
 void run(const uint8_t* buf, long long* dout, int col_tiles) {
     const int kblocks = 32, tiles = 20;
     const int smem = STAGES * 2 * NS * SLICE + (2 * STAGES + 1) * 8 + 64;
-    cudaFuncSetAttribute(pipe_kernel<NS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(pipe_kernel<NS, STAGES, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     std::vector<long long> h(148);
     for (int rep = 0; rep < 2; ++rep) {
-        pipe_kernel<NS, STAGES><<<148, 128, smem>>>(buf, kblocks, tiles, col_tiles, dout);
+        if (MC) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(148);
+            cfg.blockDim = dim3(128);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, pipe_kernel<NS, STAGES, MC>, buf, kblocks, tiles, col_tiles, dout);
+        } else {
+            pipe_kernel<NS, STAGES><<<148, 128, smem>>>(buf, kblocks, tiles, col_tiles, dout);
+        }
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
             printf("error: %s\n", cudaGetErrorString(e));
@@ -106,9 +148,9 @@ void run(const uint8_t* buf, long long* dout, int col_tiles) {
     for (auto v : h) mx = v > mx ? v : mx;
     const int mmas = NS == 4 ? 10 : 18;
     const double per_kb = (double)mx / (tiles * kblocks);
-    printf("{\"slices\": %d, \"stages\": %d, \"col_tiles_per_row_tile\": %d, \"stage_kb\": %d, \"clk_per_kblock\": %.0f, \"ideal_clk\": %d, "
+    printf("{\"multicast_pairs\": %d, \"slices\": %d, \"stages\": %d, \"col_tiles_per_row_tile\": %d, \"stage_kb\": %d, \"clk_per_kblock\": %.0f, \"ideal_clk\": %d, "
            "\"bytes_per_clk_per_sm\": %.1f, \"mma_efficiency\": %.3f}\n",
-           NS, STAGES, col_tiles, 2 * NS * 4, per_kb, mmas * 64, 2.0 * NS * SLICE / per_kb, mmas * 64 / per_kb);
+           MC, NS, STAGES, col_tiles, 2 * NS * 4, per_kb, mmas * 64, 2.0 * NS * SLICE / per_kb, mmas * 64 / per_kb);
 }
 
 int main() {
@@ -123,5 +165,7 @@ int main() {
     run<4, 6>(buf, dout, 37);
     run<7, 3>(buf, dout, 37);
     run<4, 4>(buf, dout, 74);
+    run<4, 5, 1>(buf, dout, 74);
+    run<7, 3, 1>(buf, dout, 74);
     return 0;
 }
