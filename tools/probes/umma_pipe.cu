@@ -42,19 +42,19 @@ __global__ void __launch_bounds__(128, 1) pipe_kernel(const uint8_t* __restrict_
     if (threadIdx.x == 32) {
         for (int i = 0; i < STAGES; ++i) {
             umma::mbar_init(full + i, 1);
-            umma::mbar_init(empty + i, MC ? 2 : 1);
+            umma::mbar_init(empty + i, MC == 1 ? 2 : 1);
         }
         umma::mbar_init(done, 1);
         umma::mbar_fence_init();
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (MC) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
+    if (MC == 1) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
     umma::tc_fence_after();
     const uint32_t tmem = slot;
     const long long t0 = clock64();
-    const int rank = MC ? (int)(blockIdx.x & 1) : 0;
-    const int a_tile = MC ? (int)(blockIdx.x >> 1) % 8 : blockIdx.x / col_tiles, b_tile = 8 + blockIdx.x % col_tiles;
+    const int rank = MC == 1 ? (int)(blockIdx.x & 1) : 0;
+    const int a_tile = MC == 1 ? (int)(blockIdx.x >> 1) % 8 : blockIdx.x / col_tiles, b_tile = 8 + blockIdx.x % col_tiles;
     if (warp == 2 && lane == 0) {
         uint32_t it = 0;
         for (int t = 0; t < tiles; ++t) {
@@ -65,13 +65,19 @@ __global__ void __launch_bounds__(128, 1) pipe_kernel(const uint8_t* __restrict_
                 if (round > 0) umma::mbar_wait(empty + st, (round - 1) & 1u);
                 uint8_t* s = smem + st * STAGE;
                 umma::mbar_arrive_expect_tx(full + st, STAGE);
-                if (MC) {
+                if (MC == 1) {
                     constexpr int HALF = NS * SLICE / 2;  // multiple of 16 bytes
                     bulk_g2s_mc(s + rank * HALF, a_src + (size_t)kb * TILE_KB + rank * HALF, HALF, full + st, (uint16_t)3);
+                } else if (MC == 2) {  // one bulk copy per digit slice (4 KB) instead of one per operand
+#pragma unroll
+                    for (int q = 0; q < NS; ++q) {
+                        umma::bulk_g2s(s + q * SLICE, a_src + (size_t)kb * TILE_KB + q * SLICE, SLICE, full + st);
+                        umma::bulk_g2s(s + (NS + q) * SLICE, b_src + (size_t)kb * TILE_KB + q * SLICE, SLICE, full + st);
+                    }
                 } else {
                     umma::bulk_g2s(s, a_src + (size_t)kb * TILE_KB, NS * SLICE, full + st);
                 }
-                umma::bulk_g2s(s + NS * SLICE, b_src + (size_t)kb * TILE_KB, NS * SLICE, full + st);
+                if (MC != 2) umma::bulk_g2s(s + NS * SLICE, b_src + (size_t)kb * TILE_KB, NS * SLICE, full + st);
             }
         }
     } else if (warp == 3 && lane == 0) {
@@ -100,7 +106,7 @@ __global__ void __launch_bounds__(128, 1) pipe_kernel(const uint8_t* __restrict_
                                              umma::smem_desc_kmajor_noswizzle(sB + b * SLICE, 128, 256), idesc,
                                              (kb > 0 || a > 0) ? 1u : 0u);
                 }
-                if (MC) mma_commit_mc(empty + st, (uint16_t)3);
+                if (MC == 1) mma_commit_mc(empty + st, (uint16_t)3);
                 else umma::mma_commit(empty + st);
             }
         }
@@ -110,7 +116,7 @@ __global__ void __launch_bounds__(128, 1) pipe_kernel(const uint8_t* __restrict_
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (MC) cluster_sync_all();  // nobody leaves while the peer may still write into its shared memory
+    if (MC == 1) cluster_sync_all();  // nobody leaves while the peer may still write into its shared memory
     if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
@@ -121,7 +127,7 @@ void run(const uint8_t* buf, long long* dout, int col_tiles) {
     cudaFuncSetAttribute(pipe_kernel<NS, STAGES, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     std::vector<long long> h(148);
     for (int rep = 0; rep < 2; ++rep) {
-        if (MC) {
+        if (MC == 1) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(148);
             cfg.blockDim = dim3(128);
@@ -135,7 +141,7 @@ void run(const uint8_t* buf, long long* dout, int col_tiles) {
             cfg.numAttrs = 1;
             cudaLaunchKernelEx(&cfg, pipe_kernel<NS, STAGES, MC>, buf, kblocks, tiles, col_tiles, dout);
         } else {
-            pipe_kernel<NS, STAGES><<<148, 128, smem>>>(buf, kblocks, tiles, col_tiles, dout);
+            pipe_kernel<NS, STAGES, MC><<<148, 128, smem>>>(buf, kblocks, tiles, col_tiles, dout);
         }
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
@@ -148,7 +154,7 @@ void run(const uint8_t* buf, long long* dout, int col_tiles) {
     for (auto v : h) mx = v > mx ? v : mx;
     const int mmas = NS == 4 ? 10 : 18;
     const double per_kb = (double)mx / (tiles * kblocks);
-    printf("{\"multicast_pairs\": %d, \"slices\": %d, \"stages\": %d, \"col_tiles_per_row_tile\": %d, \"stage_kb\": %d, \"clk_per_kblock\": %.0f, \"ideal_clk\": %d, "
+    printf("{\"mode(0 plain, 1 multicast pairs, 2 one copy per slice)\": %d, \"slices\": %d, \"stages\": %d, \"col_tiles_per_row_tile\": %d, \"stage_kb\": %d, \"clk_per_kblock\": %.0f, \"ideal_clk\": %d, "
            "\"bytes_per_clk_per_sm\": %.1f, \"mma_efficiency\": %.3f}\n",
            MC, NS, STAGES, col_tiles, 2 * NS * 4, per_kb, mmas * 64, 2.0 * NS * SLICE / per_kb, mmas * 64 / per_kb);
 }
@@ -167,5 +173,7 @@ int main() {
     run<4, 4>(buf, dout, 74);
     run<4, 5, 1>(buf, dout, 74);
     run<7, 3, 1>(buf, dout, 74);
+    run<4, 5, 2>(buf, dout, 74);
+    run<7, 3, 2>(buf, dout, 74);
     return 0;
 }
