@@ -177,3 +177,10 @@ def test_sweep_repeat_rule_follows_the_reference():
     assert out[-1] == 5.0 and len(out) == 7  # the outlier ends the repeats, as the reference codes it
     assert sw.sample_mean([1.0, 1.01, 0.99, 1.0]) is True and sw.sample_mean([1.0, 1.01, 0.99, 1.0, 1.0, 1.0, 3.0]) is False
     assert len(sw.reference_repeats(lambda: 1.0, min_iter=3, max_iter=5, warmup=False, callback=None)) == 3
+
+
+def test_factorization_engine_argument_is_validated():
+    from socks_b200.kernel import metrics as mt
+
+    with pytest.raises(ValueError):
+        mt.set_factorization_engine("fp32")  # before anything touches the device
