@@ -51,8 +51,9 @@ constexpr int PI_LSTAGES = 16;       // K-blocks in flight in shared memory (coe
 constexpr int PI_TBL = 256;          // table of 2^(j/256) ...
 constexpr int PI_REP = 16;           // ... replicated 16x: lane l reads copy l % 16, so a lookup never bank-conflicts
 constexpr int PI_TW = 128;           // points per CTA = tensor-memory lanes
-constexpr int PI_GROUPS = 10;        // digit groups kept (weight of group g: 2^(-13 - 8 g)); the rest is < 2^-90 of the scale
-constexpr double PI_TAU = 6.103515625e-05;  // 2^-14: columns with a smaller normaliser (relative) take the direct form
+constexpr int PI_KDIG = 7;           // digits (bytes) of a kernel value: 51-bit fixed point, k = sum_s d_s 2^(-3 - 8 s)
+constexpr int PI_GROUPS = 10;        // digit groups kept (weight of group g: 2^(-10 - 8 g)); the rest is < 2^-87 of the scale
+constexpr double PI_TAU = 0.001953125;  // 2^-9: columns with a smaller normaliser (relative) take the direct form
 
 
 __host__ __device__ inline int64_t sp_npad(int64_t n) { return (n + SP_TS - 1) / SP_TS * SP_TS; }
@@ -160,12 +161,12 @@ __device__ __forceinline__ int pi_core_offset(int r, int c) { return (r >> 3) * 
 // coefD[b][kb]: the B operand of one K-block, 128 rows x 32 bytes: row 16 t + r = digit t (byte 7 - t, unsigned) of
 // rint(coefE[b][i][r] / cscale[b][r] * 2^63), column = sample i % 32.
 // xsD[kb][i % 32] = (x'_i[0..d), cx_i) with cx_i = kmul |x'_i|^2 * 256/ln2: the sample's share of the exponent.
-// tbl[j][rep] = 2^50 2^(j/256).
+// tbl[j][rep] = 2^51 2^(j/256).
 __global__ void pi_pack_kernel(const double* __restrict__ Xc, const double* __restrict__ coefE,
                                const double* __restrict__ cscale, int64_t n_pad, int d, int nblk, double kmul,
                                uint8_t* __restrict__ coefD, double* __restrict__ xsD, double* __restrict__ tbl) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < PI_TBL * PI_REP) tbl[i] = exp2((double)(i / PI_REP) / PI_TBL) * 0x1p50;  // pre-scaled: see the producers
+    if (i < PI_TBL * PI_REP) tbl[i] = exp2((double)(i / PI_REP) / PI_TBL) * 0x1p51;  // pre-scaled: see the producers
     if (i >= n_pad) return;
     const int64_t kb = i / PI_KB;
     const int e = (int)(i % PI_KB);
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 
 // ---- integer tensor-core engine ----------------------------------------------------------------------------------
 // Same contraction acc[r][j] = sum_i coef[i][r] k(x_i, p_j), but off the FP64 pipe: the kernel value k in (0, 1] is turned
-// into a 62-bit fixed-point integer whose BYTES are unsigned 8-bit digits, the coefficients (>= 0, row-scaled) likewise
+// into a 51-bit fixed-point integer whose BYTES are unsigned 8-bit digits, the coefficients (>= 0, row-scaled) likewise
 // (once per fit), and every digit product is an exact int8 x int8 -> int32 MMA (tcgen05.mma kind::i8, accumulators in
 // tensor memory).  The FP64 pipe is left with the exponent and the exponential alone (10 instructions per pair), the 32
 // DMMA cycles per 32 pairs of the fp64 kernel are gone.
@@ -423,22 +424,25 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 //   * Per K-block (32 samples) a producer thread evaluates its point against the 32 samples,
 //         a = ps . x' + cx_i + cp   (exponent in units of ln2/256, expanded form of -g |x - p|^2),
 //         2^(a/256) = 2^(k >> 8) * tbl[k & 255] * (1 + f (d1 + f (d2 + f d3))),   k = rint(a), f = a - k,
-//     takes the 62-bit fixed-point q = k(x, p) 2^62 out of the mantissa bits by shifts (no F2I/I2F: 64-bit conversions run
-//     at one lane per clock and scheduler), transposes the bytes of 4 q's at a time (PRMT) and writes the 8 digit rows
-//     of its lane straight into tensor memory (tcgen05.st): the A operand never touches shared memory.
+//     folds the power of two into the table value's exponent field and adds 2^52: the mantissa field of the sum IS the
+//     51-bit fixed-point value q = rint(k 2^51) (no F2I/I2F -- 64-bit conversions run at one lane per clock and scheduler
+//     -- and no variable shifts), transposes the bytes of 4 q's at a time (PRMT) and writes the 7 digit rows of its lane
+//     straight into tensor memory (tcgen05.st): the A operand never touches shared memory.
 //   * The B operand of the K-block stacks the 8 coefficient digits of the 16 rows: 128 "columns" n = 16 t + r.  The MMA of
 //     kernel digit s targets D columns 16 s .. 16 s + 127, so the product (s, t) lands in group g = s + t at columns
-//     16 g + r: 8 MMAs (128 x 128 x 32) per K-block accumulate all 64 digit pairs into 15 groups of 16 columns.
+//     16 g + r: 7 MMAs (128 x 128 x 32) per K-block accumulate all 56 digit pairs into 14 groups of 16 columns.
 //   * Epilogue: groups 0..9 -> exact 64-bit integer merge -> fp64 -> x cscale[r] -> partial sums of this split; the last
 //     CTA of the tile sums the splits in index order and finishes the column exactly like the fp64 kernel.  Integer sums
 //     are exact, the split boundaries are fixed: every column is bit-identical however the points are chunked or sharded.
-// MEASURED (configs[1], 250 000 points): 9.5 ms against 8.0 ms for the fp64 kernel above, so this engine is NOT the default
+// MEASURED (configs[1], 250 000 points): 8.5 ms against 8.0 ms for the fp64 kernel above, so this engine is NOT the default
 // (variant 6).  The contraction is indeed gone from the FP64 pipe (tensor pipe 23 % busy, FP64 29 %), but every
-// instruction that goes to a 16-lane pipe (FP64, ALU, IMAD) holds the scheduler's dispatch port for two cycles, and the
-// digit extraction + byte transposes + exponential are ~35 such instructions per pair-warp = 70 cycles against the 60
-// of the fp64 kernel (ncu: alu 45 % + fp64 29 % + lsu 15 % + fma 8 % + adu 6 % = 103 % of the issue bandwidth).
+// instruction that goes to a 16-lane pipe (FP64, ALU, IMAD) holds the scheduler's dispatch port for two cycles.  The
+// first version (62-bit values, variable shifts: ~35 such instructions per pair-warp = 70 cycles against the 60 of the
+// fp64 kernel; ncu: alu 45 % + fp64 29 % + lsu 15 % + fma 8 % + adu 6 % = 103 % of the issue bandwidth) took 9.5 ms; the
+// 51-bit extraction without shifts (~27 instructions) 8.5 ms.
 // A column stands only if the expanded exponent is accurate for it (same range test as the factored fp64 form), the
-// point is finite and its normaliser is >= 2^-14 of the scale (then the fixed-point error is < 1e-10 relative); every other
+// point is finite and its normaliser is >= 2^-9 of the scale (then the fixed-point error is < 3e-9 relative in the worst
+// case, ~1e-13 typically); every other
 // column is queued for the direct form, which reproduces numpy's underflow / 0/0 behaviour.
 template <int D>
 struct PiCfg {
@@ -516,7 +520,7 @@ __global__ void __launch_bounds__(128 * PW + 64, 1)
                 umma::tc_fence_after();
                 const uint64_t db = umma::smem_desc_kmajor_noswizzle(umma::smem_u32(stages + ls * Cfg::STAGE_BYTES), 128, 256);
 #pragma unroll
-                for (int sd = 0; sd < 8; ++sd)
+                for (int sd = 0; sd < PI_KDIG; ++sd)
                     umma::mma_i8_ts(tmem + (uint32_t)(16 * sd), tmem + A_COL + (uint32_t)(64 * st + 8 * sd), db, idesc, 1u);
                 umma::mma_commit(empty + st);
                 umma::mma_commit(ld_empty + ls);  // (the producers read the samples of this stage before they arrived)
@@ -554,7 +558,7 @@ __global__ void __launch_bounds__(128 * PW + 64, 1)
             const int ls = i % PI_LSTAGES, lround = i / PI_LSTAGES;
             umma::mbar_wait(ld_full + ls, (uint32_t)lround & 1u);
             const double* xs = reinterpret_cast<const double*>(stages + ls * Cfg::STAGE_BYTES + 4096) + sub * NS * (D + 1);
-            uint32_t dig[8][NW];  // [digit][word = 4 samples]
+            uint32_t dig[PI_KDIG][NW];  // [digit][word = 4 samples]
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
                 uint32_t qh[4], ql[4];
@@ -568,35 +572,32 @@ __global__ void __launch_bounds__(128 * PW + 64, 1)
                     const double t = a + kMagic;
                     const int ki = __double2loint(t);
                     const double f = a - (t - kMagic);  // no I2F / F2I below: 64-bit conversions run at 1 lane/clk/SMSP
-                    const double tb = *reinterpret_cast<const double*>(tb_lane + ((ki & (PI_TBL - 1)) << 7));  // 2^50 2^(j/256)
+                    const double tb = *reinterpret_cast<const double*>(tb_lane + ((ki & (PI_TBL - 1)) << 7));  // 2^51 2^(j/256)
                     double pl = fma(f, d3, d2);
                     pl = fma(f, pl, d1);
                     pl = fma(f, pl, 1.0);
-                    // Y = 2^52 + rint(2^50 tbl (1 + p)): the mantissa field IS the 51-bit integer M; k 2^62 = (M << 12) >> r
-                    const double y = fma(tb, pl, 4503599627370496.0);
-                    const uint32_t hi12 = __funnelshift_l((uint32_t)__double2loint(y), (uint32_t)__double2hiint(y), 12);
-                    const uint32_t lo12 = (uint32_t)__double2loint(y) << 12;
-                    const int r = min(-(ki >> 8), 63);  // values below 2^-63 shift out to 0; ki <= 0 up to rounding noise
-                    const uint32_t fa_ = __funnelshift_r(lo12, hi12, r), fb_ = __funnelshift_r(hi12, 0u, r);  // shift mod 32
-                    qh[e] = (r >= 32) ? 0u : fb_;
-                    ql[e] = (r >= 32) ? fb_ : fa_;
+                    // the power of two goes into the table value's exponent field (values below 2^-1000 do not matter),
+                    // then y = 2^52 + rint(k 2^51): the mantissa field IS the 51-bit fixed-point value -- no shifts
+                    const double tbs = __hiloint2double(__double2hiint(tb) + (max(ki >> 8, -1000) << 20), __double2loint(tb));
+                    const double y = fma(tbs, pl, 4503599627370496.0);
+                    qh[e] = (uint32_t)__double2hiint(y) & 0x000FFFFFu;
+                    ql[e] = (uint32_t)__double2loint(y);
                 }
-                // bytes of 4 q's -> one word per digit (4 x 4 byte transposes)
+                // bytes of 4 q's -> one word per digit (4 x 4 byte transposes; byte 7 is always 0)
                 {
                     const uint32_t a01 = __byte_perm(qh[0], qh[1], 0x5140), b01 = __byte_perm(qh[0], qh[1], 0x7362);
                     const uint32_t a23 = __byte_perm(qh[2], qh[3], 0x5140), b23 = __byte_perm(qh[2], qh[3], 0x7362);
-                    dig[3][w] = __byte_perm(a01, a23, 0x5410);  // byte 4 of q
-                    dig[2][w] = __byte_perm(a01, a23, 0x7632);  // byte 5
-                    dig[1][w] = __byte_perm(b01, b23, 0x5410);  // byte 6
-                    dig[0][w] = __byte_perm(b01, b23, 0x7632);  // byte 7 (top digit)
+                    dig[2][w] = __byte_perm(a01, a23, 0x5410);  // byte 4 of q
+                    dig[1][w] = __byte_perm(a01, a23, 0x7632);  // byte 5
+                    dig[0][w] = __byte_perm(b01, b23, 0x5410);  // byte 6 (top digit: 3 bits)
                 }
                 {
                     const uint32_t a01 = __byte_perm(ql[0], ql[1], 0x5140), b01 = __byte_perm(ql[0], ql[1], 0x7362);
                     const uint32_t a23 = __byte_perm(ql[2], ql[3], 0x5140), b23 = __byte_perm(ql[2], ql[3], 0x7362);
-                    dig[7][w] = __byte_perm(a01, a23, 0x5410);  // byte 0
-                    dig[6][w] = __byte_perm(a01, a23, 0x7632);
-                    dig[5][w] = __byte_perm(b01, b23, 0x5410);
-                    dig[4][w] = __byte_perm(b01, b23, 0x7632);  // byte 3
+                    dig[6][w] = __byte_perm(a01, a23, 0x5410);  // byte 0
+                    dig[5][w] = __byte_perm(a01, a23, 0x7632);
+                    dig[4][w] = __byte_perm(b01, b23, 0x5410);
+                    dig[3][w] = __byte_perm(b01, b23, 0x7632);  // byte 3
                 }
             }
             if (round > 0) {
@@ -604,7 +605,7 @@ __global__ void __launch_bounds__(128 * PW + 64, 1)
                 umma::tc_fence_after();
             }
 #pragma unroll
-            for (int sd = 0; sd < 8; ++sd) {
+            for (int sd = 0; sd < PI_KDIG; ++sd) {
                 const uint32_t ta = trow + A_COL + (uint32_t)(64 * st + 8 * sd + sub * NW);
                 if constexpr (NW == 8) umma::tmem_st8(ta, dig[sd]);
                 else if constexpr (NW == 4) umma::tmem_st4(ta, dig[sd]);
@@ -627,7 +628,7 @@ __global__ void __launch_bounds__(128 * PW + 64, 1)
             umma::tmem_ld16(trow + (uint32_t)(16 * g), u0);
             umma::tmem_ld16(trow + (uint32_t)(16 * (g + 1)), u1);
             umma::tmem_ld_wait();
-            const double wgt = __longlong_as_double((long long)(1023 - 13 - 8 * (g + 1)) << 52);  // 2^(-13 - 8 (g + 1))
+            const double wgt = __longlong_as_double((long long)(1023 - 10 - 8 * (g + 1)) << 52);  // 2^(-10 - 8 (g + 1))
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
                 const long long pr = ((long long)(int)u0[r] << 8) + (long long)(int)u1[r];  // < 2^40, exact
@@ -1059,7 +1060,7 @@ extern "C" int socks_sr_predict_packed(const double* pack, const double* X, int6
     SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 15) == 0, 14);
     // variant: 0 auto (factored form on the fp64 tensor cores, CTA shape by size) | 1 FMA-pipe kernel | 2 direct form on
     // the fp64 tensor cores | 3 / 4: auto with the CTA shape forced to 8 / 4 warps (measurement only) | 5: same as 0 |
-    // 6: integer tensor-core engine (tcgen05.mma kind::i8; correct to 3e-14 of variant 0 but 20 % slower: see DESIGN 4.5)
+    // 6: integer tensor-core engine (tcgen05.mma kind::i8; correct to 3e-14 of variant 0 but 6 % slower: see DESIGN 4.5)
     SOCKS_CHECK_ARG(variant >= 0 && variant <= 6, 15);
     if (m == 0) return SOCKS_OK;
     SOCKS_CHECK_ARG(pts != nullptr && out != nullptr, 7);
