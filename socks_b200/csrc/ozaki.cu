@@ -285,7 +285,7 @@ static inline int64_t pad_to(int64_t v, int64_t a) { return (v + a - 1) / a * a;
 // layout: Dop[tile][kb][s][128 rows x 32 B core-matrix layout].
 namespace socks {
 
-constexpr int OG_S = 7;  // digits of the trailing updates; the merges of inv(L) take 8 (see chol.cu)
+// (digit counts: 7 in the trailing updates, 8 in the merges of inv(L) and in W = M^T M -- see chol.cu)
 
 __device__ __forceinline__ double og_pow2(int e) {  // 2^e, e in the normal range (folds to a constant)
     return __longlong_as_double((long long)(1023 + e) << 52);

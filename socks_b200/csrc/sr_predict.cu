@@ -999,7 +999,8 @@ static void launch_tensor(const PackView& v, const double* X, int64_t n, const d
     }
 #undef SOCKS_FAST_LAUNCH
     const ExpScaled ex = make_exp_scaled(kmul);
-    sr_predict_dmma_kernel<D, 8, 3><<<dim3((unsigned)ceil_div(m, 256), (unsigned)splits), 256, 0, st>>>(
+    // 2 CTAs/SM (<= 128 registers): at 3 the direct form spilled 60-464 bytes per thread (d = 2..8)
+    sr_predict_dmma_kernel<D, 8, 2><<<dim3((unsigned)ceil_div(m, 256), (unsigned)splits), 256, 0, st>>>(
         X, ce, n, v.n_pad, pts, m, v.hdr, ex, R, force_direct, part, ldp);
 }
 
