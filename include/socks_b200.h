@@ -55,6 +55,9 @@ const char* socks_last_error(void);
 int64_t socks_padded_dim(int64_t n);
 /* rows x width_bytes strided copy in one enqueue (kind: 1 host->device, 2 device->host, 3 device->device): the read
  * of a column block of the (T, M) result into the caller's (pinned) ndarray, kernel_sr.py:344 `return out`. */
+/* out2[0] = min_i |A[i][i]|, out2[1] = max_i |A[i][i]| (i < n): on the diagonal of a Cholesky factor,
+ * (max / min)^2 is a lower bound of cond_2(G). */
+int socks_diag_range(const double* A, int64_t n, int64_t ld, double* out2, socks_stream_t stream);
 int socks_copy2d(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width_bytes, int64_t rows,
                  int kind, socks_stream_t stream);
 

@@ -21,6 +21,7 @@ SIGNATURES = {
     "socks_last_error": (c_char_p, []),
     "socks_padded_dim": (_L, [_L]),
     "socks_copy2d": (_I, [_P, _L, _P, _L, _L, _L, _I, _P]),
+    "socks_diag_range": (_I, [_P, _L, _L, _P, _P]),
     "socks_gram_rbf": (_I, [_P, _L, _P, _L, _I, _D, _I, _P, _P, _L, _P]),
     "socks_gram_kernel": (_I, [_I, _P, _L, _P, _L, _I, _D, _I, _P, _P, _L, _P]),
     "socks_gram_family": (_I, [_I, _P, _L, _P, _L, _I, _D, _I, _D, _D, _P, _P, _L, _P]),

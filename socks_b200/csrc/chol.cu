@@ -541,6 +541,7 @@ static int g_potrf_ozaki = 1;  // 1: trailing updates on the integer tensor core
 // relative to the row maximum; with 7 digits the residual |W G - I| rose from 3e-9 (DMMA) to 4e-7 at N = 20k, with 8 it is
 // back at the DMMA level (tools/inverse_residual.py).  The trailing updates (rows of L21: narrow range) keep 7.
 static int g_potrf_merge_digits = 8;
+static int g_potrf_update_digits = 7;  // digits of the trailing updates (7 or 8)
 static int g_potrf_ozaki_merge = 1;  // 1: the large merges of inv(L) on the integer tensor cores as well
 static int g_potrf_tail = 1;   // 1: half-width block columns over the last 4 NB columns
 static int g_potrf_nb = 1024;  // block-column width of the look-ahead factorisation (multiple of 128; 0 = pure recursion)
@@ -604,7 +605,7 @@ static inline int64_t trtri_scratch_doubles(int64_t np) {
 // T arena: every pair of distinct block columns meets in exactly one merge, so sum n1 n2 < np^2 / 2.
 constexpr int64_t kRecScratchDoubles = (int64_t)4096 * 4096;  // merges spanning <= 4 block columns of <= 2048
 static inline int64_t potrf_arena_doubles(int64_t np) { return np * np / 2; }
-static inline int64_t potrf_panel_digit_bytes(int64_t np) { return ozaki_operand_bytes(np, 2048, 7) + 1024; }
+static inline int64_t potrf_panel_digit_bytes(int64_t np) { return ozaki_operand_bytes(np, 2048, 8) + 1024; }
 // the two digit operands of the largest product (rows n1 + n2 <= np, K <= max(n1, n2) <= np/2 + 2 block columns)
 static inline int64_t potrf_merge_digit_bytes(int64_t np) {
     const int64_t kmax = std::min<int64_t>(np, np / 2 + 2048);
@@ -717,12 +718,13 @@ static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, i
         // next block column first (rows rem x cols b1), then the rest of the trailing lower triangle
         if (use_ozaki) {
             // A22 -= L21 L21^T on the integer tensor cores: the panel is split into digits once, both updates read them
-            if ((rc = ozaki_slice_operand(L21, rem, bk, ldm, 0, 0, digits, 7, su))) return rc;
-            if ((rc = ozaki_gemm_nt_sliced(digits, rem, 0, digits, rem, 0, bk, A22, lda, rem, b1, 1, 0, 0, 0, 7, su))) return rc;
+            const int SU = g_potrf_update_digits;
+            if ((rc = ozaki_slice_operand(L21, rem, bk, ldm, 0, 0, digits, SU, su))) return rc;
+            if ((rc = ozaki_gemm_nt_sliced(digits, rem, 0, digits, rem, 0, bk, A22, lda, rem, b1, 1, 0, 0, 0, SU, su))) return rc;
             g_trace.mark(4, k, su);
             c1.note(cudaEventRecord(la->ev_col, su));
             if (rem > b1 && (rc = ozaki_gemm_nt_sliced(digits, rem, b1 / LF, digits, rem, b1 / LF, bk, A22 + b1 * lda + b1,
-                                                       lda, rem - b1, rem - b1, 1, 0, 0, 0, 7, su)))
+                                                       lda, rem - b1, rem - b1, 1, 0, 0, 0, SU, su)))
                 return rc;
             g_trace.mark(5, k, su);
         } else {
@@ -875,7 +877,8 @@ extern "C" int socks_potrf_inv_set_block(int nb) {
         if (nb >= -2) g_potrf_tail = (nb == -2);
         else if (nb >= -4) g_potrf_ozaki = (nb == -4);
         else if (nb >= -6) g_potrf_ozaki_merge = (nb == -6);
-        else g_potrf_merge_digits = (nb == -7) ? 7 : 8;  // -7 / -8: 7 / 8 digits in the merges
+        else if (nb >= -8) g_potrf_merge_digits = (nb == -7) ? 7 : 8;  // -7 / -8: 7 / 8 digits in the merges
+        else g_potrf_update_digits = (nb == -9) ? 7 : 8;               // -9 / -10: 7 / 8 digits in the trailing updates
         return old;
     }
     if (nb % LF == 0 && nb <= 2048) g_potrf_nb = nb;  // the recursion scratch is sized for block columns of <= 2048

@@ -31,3 +31,47 @@ extern "C" int socks_copy2d(void* dst, int64_t dpitch, const void* src, int64_t 
                                  (cudaMemcpyKind)kind, (cudaStream_t)stream));
     return SOCKS_OK;
 }
+
+// out[0] = min_i |A[i][i]|, out[1] = max_i |A[i][i]| over the first n diagonal entries.  After a factorisation the
+// diagonal of the factor gives cond_2(G) >= (max l_ii / min l_ii)^2: the wrappers use it to decide whether the inverse
+// factor's rows span more dynamic range than the integer digit GEMMs carry.
+namespace socks {
+__global__ void __launch_bounds__(1024) diag_range_kernel(const double* __restrict__ A, int64_t n, int64_t ld,
+                                                          double* __restrict__ out) {
+    __shared__ double slo[32], shi[32];
+    double lo = INFINITY, hi = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = fabs(A[i * ld + i]);
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        slo[threadIdx.x >> 5] = lo;
+        shi[threadIdx.x >> 5] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            lo = fmin(lo, slo[w]);
+            hi = fmax(hi, shi[w]);
+        }
+        out[0] = lo;
+        out[1] = hi;
+    }
+}
+}  // namespace socks
+
+extern "C" int socks_diag_range(const double* A, int64_t n, int64_t ld, double* out2, socks_stream_t stream) {
+    SOCKS_CHECK_ARG(A != nullptr, 1);
+    SOCKS_CHECK_ARG(n >= 1, 2);
+    SOCKS_CHECK_ARG(ld >= n, 3);
+    SOCKS_CHECK_ARG(out2 != nullptr, 4);
+    socks::diag_range_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(A, n, ld, out2);
+    SOCKS_CHECK_LAUNCH();
+    return SOCKS_OK;
+}
+

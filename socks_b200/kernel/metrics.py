@@ -170,6 +170,10 @@ def sharded_bandwidth_guard(spec):
 
 
 _ENGINE = {"factorization": "int8"}
+# (max l_ii / min l_ii)^2 -- a lower bound of cond_2(G) read off the factor -- above which Factorization.check() redoes
+# the inverse with its GEMMs on the FP64 tensor cores.  Measured (tools/illcond_check.py): with the integer merges the
+# residual max|W G - I| is 1x / 3x / 7x / 19x / 500x the FP64 one at cond 2.5e6 / 1e7 / 2e8 / 5e10 / 8e11.
+COND_LIMIT_INT8 = 1e8
 
 
 def set_factorization_engine(engine="int8"):
@@ -197,33 +201,65 @@ class Factorization:
     def __init__(self, Zd, kparams, diag_add, kind=KIND_RBF, keep_l=False, two_pass=False, Ud=None, extra=(1.0, 3.0)):
         n, d = Zd.shape
         self.n, self.np = n, dv.padded(n)
-        npad = self.np
+        self._recipe = ("gram", Zd, kparams, float(diag_add), int(kind), bool(keep_l), bool(two_pass), Ud, extra)
+        self._w = None
+        self._W = None
+        self._fp64_inverse = _ENGINE["factorization"] != "int8"
+        self._factor()
+
+    def _factor(self):
+        """Build G and run the factorisation recorded in self._recipe (again, with the merges of inv(L) on the FP64
+        tensor cores, when check() finds the matrix too ill-conditioned for the digit GEMMs: see COND_LIMIT_INT8)."""
+        npad, n = self.np, self.n
         st = dv.stream()
         lib = _lib.load()
-        self.L = dv.empty(npad, npad)
+        what = self._recipe[0]
+        keep_l = two_pass = False
+        G = dv.empty(npad, npad)
         dv.mark("start")
-        if Ud is None and kind in (KIND_RBF, KIND_ABEL):
-            _lib.call("socks_gram_sym_kernel", int(kind), dv.ptr(Zd), n, d, float(kparams[0]), int(kparams[1]),
-                      float(diag_add), dv.ptr(self.L), npad, st)
-        else:  # any family, optional second factor k(U, U) with the same kernel (metrics.py:268-276)
-            _lib.call("socks_gram_sym_family", int(kind), dv.ptr(Zd), n, d, dv.ptr(Ud), 0 if Ud is None else Ud.shape[1],
-                      float(kparams[0]), int(kparams[1]), float(extra[0]), float(extra[1]), float(diag_add),
-                      dv.ptr(self.L), npad, st)
-        self.info = torch.zeros(1, dtype=torch.int32, device=Zd.device)
+        if what == "gram":
+            _, Zd, kparams, diag_add, kind, keep_l, two_pass, Ud, extra = self._recipe
+            d = Zd.shape[1]
+            if Ud is None and kind in (KIND_RBF, KIND_ABEL):
+                _lib.call("socks_gram_sym_kernel", int(kind), dv.ptr(Zd), n, d, float(kparams[0]), int(kparams[1]),
+                          float(diag_add), dv.ptr(G), npad, st)
+            else:  # any family, optional second factor k(U, U) with the same kernel (metrics.py:268-276)
+                _lib.call("socks_gram_sym_family", int(kind), dv.ptr(Zd), n, d, dv.ptr(Ud), 0 if Ud is None else Ud.shape[1],
+                          float(kparams[0]), int(kparams[1]), float(extra[0]), float(extra[1]), float(diag_add),
+                          dv.ptr(G), npad, st)
+            device = Zd.device
+        else:  # caller-supplied matrix
+            _, Gd, diag_add = self._recipe
+            _lib.call("socks_pad_spd", dv.ptr(Gd), n, Gd.stride(0), float(diag_add), dv.ptr(G), npad, st)
+            device = Gd.device
+        self.info = torch.zeros(1, dtype=torch.int32, device=device)
+        self._lrange = torch.zeros(2, dtype=torch.float64, device=device)
         self._M = dv.empty(npad, npad)
         wk = dv.work(lib.socks_trtri_work_bytes(n))
         dv.mark("gram_sym")
         if two_pass:
             dinv = dv.work(lib.socks_potrf_work_bytes(n))
-            _lib.call("socks_potrf", dv.ptr(self.L), n, npad, dv.ptr(dinv), dv.ptr(self.info), st)
-            _lib.call("socks_trtri", dv.ptr(self.L), n, npad, dv.ptr(dinv), dv.ptr(self._M), npad, dv.ptr(wk), st)
+            _lib.call("socks_potrf", dv.ptr(G), n, npad, dv.ptr(dinv), dv.ptr(self.info), st)
+            _lib.call("socks_trtri", dv.ptr(G), n, npad, dv.ptr(dinv), dv.ptr(self._M), npad, dv.ptr(wk), st)
+            self._fp64_inverse = True
         else:
-            _lib.call("socks_potrf_inv", dv.ptr(self.L), n, npad, dv.ptr(self._M), npad, dv.ptr(wk), dv.ptr(self.info),
-                      1 if keep_l else 0, st)
-            if not keep_l:
-                self.L = None  # only scratch is left in it
+            fallback = _ENGINE["factorization"] == "int8" and self._fp64_inverse  # only check() asks for this
+            if fallback:
+                lib.socks_potrf_inv_set_block(-5)  # merges of inv(L) on the FP64 tensor cores for this call
+            try:
+                _lib.call("socks_potrf_inv", dv.ptr(G), n, npad, dv.ptr(self._M), npad, dv.ptr(wk), dv.ptr(self.info),
+                          1 if keep_l else 0, st)
+            finally:
+                if fallback:
+                    lib.socks_potrf_inv_set_block(-6)
+        # the diagonal of L survives in G's diagonal blocks either way: (max / min)^2 <= cond_2(G)
+        _lib.call("socks_diag_range", dv.ptr(G), n, npad, dv.ptr(self._lrange), st)
+        self.L = G if (keep_l or two_pass) else None  # otherwise only scratch is left in it
         dv.mark("potrf_inv")
-        self._w = None
+        if self._w is not None:  # a refactorisation: refresh what was already handed out, in place
+            w, self._w = self._w, None
+            w.copy_(self.diag())
+            self._w = w
         self._W = None
 
     @classmethod
@@ -232,14 +268,11 @@ class Factorization:
         self = cls.__new__(cls)
         n = Gd.shape[0]
         self.n, self.np = n, dv.padded(n)
-        npad, st, lib = self.np, dv.stream(), _lib.load()
-        G = dv.empty(npad, npad)
-        _lib.call("socks_pad_spd", dv.ptr(Gd), n, Gd.stride(0), float(diag_add), dv.ptr(G), npad, st)
-        self.info = torch.zeros(1, dtype=torch.int32, device=Gd.device)
-        self._M = dv.empty(npad, npad)
-        wk = dv.work(lib.socks_trtri_work_bytes(n))
-        _lib.call("socks_potrf_inv", dv.ptr(G), n, npad, dv.ptr(self._M), npad, dv.ptr(wk), dv.ptr(self.info), 0, st)
-        self.L, self._w, self._W = None, None, None
+        self._recipe = ("matrix", Gd, float(diag_add))
+        self._w = None
+        self._W = None
+        self._fp64_inverse = _ENGINE["factorization"] != "int8"
+        self._factor()
         return self
 
     def check(self):
@@ -249,6 +282,17 @@ class Factorization:
                 f"regularised Gram matrix is not positive definite (pivot {info - 1}); the reference's LU inverse "
                 "would return a meaningless matrix here"
             )
+        lo, hi = self._lrange.tolist()
+        self.cond_estimate = (hi / lo) ** 2 if lo > 0 else float("inf")
+        if not self._fp64_inverse and self.cond_estimate > COND_LIMIT_INT8:
+            # the rows of inv(L) span more dynamic range than 8 digits carry: redo with the merges (and W = M^T M) on the
+            # FP64 tensor cores; the trailing updates stay on the integer ones (measured as accurate as FP64 up to
+            # cond 1e12: tools/illcond_check.py)
+            self._fp64_inverse = True
+            self._factor()
+            info = int(self.info.item())
+            if info != 0:
+                raise np.linalg.LinAlgError(f"regularised Gram matrix is not positive definite (pivot {info - 1})")
 
     def inverse_factor(self):
         if self._M is None:
@@ -270,7 +314,7 @@ class Factorization:
         if self._W is None:
             M = self.inverse_factor()
             self._W = dv.empty(self.np, self.np)
-            if _ENGINE["factorization"] == "int8" and self.np > 2048:
+            if not self._fp64_inverse and self.np > 2048:
                 wk = dv.work(_lib.load().socks_lauum_i8_work_bytes(self.n))
                 _lib.call("socks_lauum_i8", dv.ptr(M), self.n, self.np, dv.ptr(self._W), self.np, dv.ptr(wk), dv.stream())
             else:
