@@ -20,6 +20,7 @@ for n, sigma, lam in ((3000, 0.5, 1e-9), (3000, 1.0, 1e-11), (6000, 0.3, 1e-8), 
         limit, mt.COND_LIMIT_INT8 = mt.COND_LIMIT_INT8, (float("inf") if "guard off" in engine else mt.COND_LIMIT_INT8)
         try:
             fac = mt.factorize(X, None, mt.RBFSpec(sigma=sigma), lam)
+            fac.check()  # as every algorithm does right after the factorisation: this is where the guard acts
             W = fac.full()[:n, :n].cpu().numpy()
             R = W @ G - np.eye(n)
             out[engine + ": residual_max"] = float(np.abs(R).max())
