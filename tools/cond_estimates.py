@@ -1,3 +1,5 @@
+"""diag(L)-based conditioning estimate (Factorization.cond_estimate) of the BASELINE configs: all below
+metrics.COND_LIMIT_INT8, i.e. on the integer tensor-core engine.  Usage: python tools/cond_estimates.py"""
 import sys; import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from socks_b200 import _device as dv, synthetic as syn
