@@ -540,6 +540,7 @@ static int g_potrf_ozaki = 1;  // 1: trailing updates on the integer tensor core
 // Digits of the merges: the entries of inv(L) span many orders of magnitude WITHIN a row, and the digit scheme truncates
 // relative to the row maximum; with 7 digits the residual |W G - I| rose from 3e-9 (DMMA) to 4e-7 at N = 20k, with 8 it is
 // back at the DMMA level (tools/inverse_residual.py).  The trailing updates (rows of L21: narrow range) keep 7.
+static int g_potrf_kbalance = 1;  // balance the two operands of a merge product along K (csrc/ozaki.cu: oz_kmax_kernel)
 static int g_potrf_merge_digits = 8;
 static int g_potrf_update_digits = 7;  // digits of the trailing updates (7 or 8)
 static int g_potrf_ozaki_merge = 1;  // 1: the large merges of inv(L) on the integer tensor cores as well
@@ -576,13 +577,26 @@ static void merge_product(CholCtx& cx, int which, double* M, int64_t ldm, const 
         int rc = SOCKS_OK;
         uint8_t* da = digits;
         uint8_t* db = digits + ozaki_operand_bytes(n2, K, S);
+        // per-k balancing scales, after the digit operands (2 K doubles; digit_bytes leaves 1 KB + this much spare)
+        double* kw = g_potrf_kbalance ? reinterpret_cast<double*>(digits + digit_bytes) : nullptr;
+        const double *ksa = nullptr, *ksb = nullptr;
         if (which == 1) {  // A = rows of L21, B = columns of M11 (zero above the diagonal: k >= j), K = n1
-            if (!rc) rc = ozaki_slice_operand(M21, n2, n1, ldm, 0, 0, da, S, cx.st);
-            if (!rc) rc = ozaki_slice_operand(M11, n1, n1, ldm, 1, 2, db, S, cx.st);
+            if (kw) {
+                rc = ozaki_kbalance(M21, n2, ldm, 0, 0, M11, n1, ldm, 1, 2, n1, kw, cx.st);
+                ksa = kw;
+                ksb = kw + n1;
+            }
+            if (!rc) rc = ozaki_slice_operand(M21, n2, n1, ldm, 0, 0, da, S, ksa, cx.st);
+            if (!rc) rc = ozaki_slice_operand(M11, n1, n1, ldm, 1, 2, db, S, ksb, cx.st);
             if (!rc) rc = ozaki_gemm_nt_sliced(da, n2, 0, db, n1, 0, n1, T, n1, n2, n1, 0, 1, 0, 1, S, cx.st);
         } else {  // A = rows of M22 (lower triangular: k <= i), B = columns of T, K = n2
-            if (!rc) rc = ozaki_slice_operand(M22, n2, n2, ldm, 0, 1, da, S, cx.st);
-            if (!rc) rc = ozaki_slice_operand(T, n1, n2, n1, 1, 0, db, S, cx.st);
+            if (kw) {
+                rc = ozaki_kbalance(M22, n2, ldm, 0, 1, T, n1, n1, 1, 0, n2, kw, cx.st);
+                ksa = kw;
+                ksb = kw + n2;
+            }
+            if (!rc) rc = ozaki_slice_operand(M22, n2, n2, ldm, 0, 1, da, S, ksa, cx.st);
+            if (!rc) rc = ozaki_slice_operand(T, n1, n2, n1, 1, 0, db, S, ksb, cx.st);
             if (!rc) rc = ozaki_gemm_nt_sliced(da, n2, 0, db, n1, 0, n2, M21, ldm, n2, n1, 0, 2, 1, 0, S, cx.st);
         }
         cx.note_rc(rc);
@@ -609,7 +623,7 @@ static inline int64_t potrf_panel_digit_bytes(int64_t np) { return ozaki_operand
 // the two digit operands of the largest product (rows n1 + n2 <= np, K <= max(n1, n2) <= np/2 + 2 block columns)
 static inline int64_t potrf_merge_digit_bytes(int64_t np) {
     const int64_t kmax = std::min<int64_t>(np, np / 2 + 2048);
-    return 2 * ozaki_operand_bytes((np + 1) / 2 + 2048, kmax, 8) + 1024;
+    return 2 * ozaki_operand_bytes((np + 1) / 2 + 2048, kmax, 8) + 1024 + 2 * np * 8;  // + the K-balancing scales
 }
 static inline int64_t potrf_lookahead_bytes(int64_t np) {
     return (kRecScratchDoubles + potrf_arena_doubles(np)) * 8 + potrf_panel_digit_bytes(np) + potrf_merge_digit_bytes(np) + 2048;
@@ -625,7 +639,7 @@ static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, i
     uint8_t* digits = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(arena + potrf_arena_doubles(np)) + 1023) & ~(uintptr_t)1023);
     uint8_t* mdigits = digits + ((potrf_panel_digit_bytes(np) + 1023) & ~(int64_t)1023);
-    const int64_t mdigit_bytes = potrf_merge_digit_bytes(np) - 1024;
+    const int64_t mdigit_bytes = potrf_merge_digit_bytes(np) - 1024 - 2 * np * 8;
     const bool use_ozaki = g_potrf_ozaki && NB <= 2048;
     cudaStream_t su = la->su, s3 = la->s3;
     CholCtx c1{su}, c2{la->s2}, c3{s3};
@@ -719,7 +733,7 @@ static int potrf_inv_lookahead(double* A, int64_t lda, double* M, int64_t ldm, i
         if (use_ozaki) {
             // A22 -= L21 L21^T on the integer tensor cores: the panel is split into digits once, both updates read them
             const int SU = g_potrf_update_digits;
-            if ((rc = ozaki_slice_operand(L21, rem, bk, ldm, 0, 0, digits, SU, su))) return rc;
+            if ((rc = ozaki_slice_operand(L21, rem, bk, ldm, 0, 0, digits, SU, nullptr, su))) return rc;
             if ((rc = ozaki_gemm_nt_sliced(digits, rem, 0, digits, rem, 0, bk, A22, lda, rem, b1, 1, 0, 0, 0, SU, su))) return rc;
             g_trace.mark(4, k, su);
             c1.note(cudaEventRecord(la->ev_col, su));
@@ -878,7 +892,8 @@ extern "C" int socks_potrf_inv_set_block(int nb) {
         else if (nb >= -4) g_potrf_ozaki = (nb == -4);
         else if (nb >= -6) g_potrf_ozaki_merge = (nb == -6);
         else if (nb >= -8) g_potrf_merge_digits = (nb == -7) ? 7 : 8;  // -7 / -8: 7 / 8 digits in the merges
-        else g_potrf_update_digits = (nb == -9) ? 7 : 8;               // -9 / -10: 7 / 8 digits in the trailing updates
+        else if (nb >= -10) g_potrf_update_digits = (nb == -9) ? 7 : 8;  // -9 / -10: 7 / 8 digits in the trailing updates
+        else g_potrf_kbalance = (nb == -12);                             // -11 / -12: K-balancing of the merge products off / on
         return old;
     }
     if (nb % LF == 0 && nb <= 2048) g_potrf_nb = nb;  // the recursion scratch is sized for block columns of <= 2048
@@ -982,7 +997,7 @@ extern "C" int socks_lauum_i8(const double* M, int64_t n, int64_t ldm, double* W
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t np = socks_padded_dim(n);
     uint8_t* buf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(work) + 1023) & ~(uintptr_t)1023);
-    if ((rc = ozaki_slice_operand(M, np, np, ldm, 1, 2, buf, 8, st))) return rc;
+    if ((rc = ozaki_slice_operand(M, np, np, ldm, 1, 2, buf, 8, nullptr, st))) return rc;
     if ((rc = ozaki_gemm_nt_sliced(buf, np, 0, buf, np, 0, np, W, ldw, np, np, 1, 1, 2, 1, 8, st))) return rc;
     symmetrize_kernel<<<dim3((unsigned)(np / 32), (unsigned)(np / 32)), dim3(32, 8), 0, st>>>(W, ldw);
     SOCKS_CHECK_LAUNCH();

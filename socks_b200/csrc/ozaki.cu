@@ -307,27 +307,27 @@ __device__ __forceinline__ bool oz_in_range(int tri, int64_t r, int64_t k) {
 // K x rows matrix, i.e. the B of an "NN" product).
 // scale[r] = 2^(e) with 2^(e-1) <= max_k |op(r, k)| < 2^e (1 for an all-zero row).
 __global__ void oz_rowscale_rows_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t ld, int tri,
-                                        double* __restrict__ scale) {
+                                        const double* __restrict__ kscale, double* __restrict__ scale) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= rows) return;
     const double* p = P + r * ld;
     double mx = 0.0;
     for (int64_t k = lane; k < K; k += 32)
-        if (oz_in_range(tri, r, k)) mx = fmax(mx, fabs(p[k]));
+        if (oz_in_range(tri, r, k)) mx = fmax(mx, fabs(p[k]) * (kscale ? kscale[k] : 1.0));
     for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
     if (lane == 0) scale[r] = (mx > 0.0 && mx < INFINITY) ? ldexp(1.0, ilogb(mx) + 1) : 1.0;
 }
 // transposed operand: thread = operand row (= column of P, coalesced across threads), blockIdx.y = 256-sample K chunk;
 // the maxima are combined as integers (non-negative doubles order like their bit patterns), then turned into scales.
 __global__ void oz_colmax_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t ld, int tri,
-                                 unsigned long long* __restrict__ mxbits) {
+                                 const double* __restrict__ kscale, unsigned long long* __restrict__ mxbits) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     const int64_t k0 = (int64_t)blockIdx.y * 256, k1 = min(K, k0 + 256);
     double mx = 0.0;
     for (int64_t k = k0; k < k1; ++k)
-        if (oz_in_range(tri, r, k)) mx = fmax(mx, fabs(P[k * ld + r]));
+        if (oz_in_range(tri, r, k)) mx = fmax(mx, fabs(P[k * ld + r]) * (kscale ? kscale[k] : 1.0));
     if (mx > 0.0) atomicMax(mxbits + r, (unsigned long long)__double_as_longlong(mx));
 }
 __global__ void oz_scale_from_max_kernel(double* __restrict__ scale, int64_t rows) {
@@ -336,6 +336,48 @@ __global__ void oz_scale_from_max_kernel(double* __restrict__ scale, int64_t row
     const double mx = scale[r];
     scale[r] = (mx > 0.0 && mx < INFINITY) ? ldexp(1.0, ilogb(mx) + 1) : 1.0;
 }
+// ---- balancing along K -------------------------------------------------------------------------------------------------
+// The digit split truncates relative to an operand ROW's maximum.  In the merges of inv(L) the two operands have opposite
+// magnitude profiles along K (columns of L decay like l_kk, rows of inv(L) grow like 1 / l_kk): terms a_ik b_jk of order one
+// are products of a tiny and a huge factor, and the tiny factor is truncated away.  A power-of-two scale per k,
+//     A B^T = (A D^-1) (B D)^T,   D_k = 2^round((log2 max_i |a_ik| - log2 max_j |b_jk|) / 2),
+// equalises the K-profiles of the two operands exactly (the scales are exponent shifts) before their rows are scaled and
+// split: on Gram matrices with cond up to 8e11 the 7-digit product is then as accurate as FP64.
+// kmax[k] = max over operand rows r of |op(r, k)| (mask as in oz_in_range), combined as integer bit patterns.
+template <bool TRANS>
+__global__ void oz_kmax_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t ld, int tri,
+                               unsigned long long* __restrict__ kmax) {
+    if (TRANS) {  // op(r, k) = P[k][r]: one warp per k, lanes over r (coalesced)
+        const int lane = threadIdx.x & 31;
+        const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        if (k >= K) return;
+        double mx = 0.0;
+        for (int64_t r = lane; r < rows; r += 32)
+            if (oz_in_range(tri, r, k)) mx = fmax(mx, fabs(P[k * ld + r]));
+        for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        if (lane == 0 && mx > 0.0) kmax[k] = (unsigned long long)__double_as_longlong(mx);
+    } else {  // op(r, k) = P[r][k]: thread = k (coalesced), blockIdx.y = chunk of 256 operand rows
+        const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (k >= K) return;
+        const int64_t r0 = (int64_t)blockIdx.y * 256, r1 = min(rows, r0 + 256);
+        double mx = 0.0;
+        for (int64_t r = r0; r < r1; ++r)
+            if (oz_in_range(tri, r, k)) mx = fmax(mx, fabs(P[r * ld + k]));
+        if (mx > 0.0) atomicMax(kmax + k, (unsigned long long)__double_as_longlong(mx));
+    }
+}
+// sa[k] = 2^-e_k (applied to A), sb[k] = 2^e_k (applied to B); in place over the two kmax arrays
+__global__ void oz_kbalance_kernel(double* __restrict__ ka, double* __restrict__ kb, int64_t K) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const double a = ka[k], b = kb[k];
+    int e = 0;
+    if (a > 0.0 && b > 0.0 && a < INFINITY && b < INFINITY) e = (int)rint(0.5 * (double)(ilogb(a) - ilogb(b)));
+    e = max(-500, min(500, e));
+    ka[k] = ldexp(1.0, -e);
+    kb[k] = ldexp(1.0, e);
+}
+
 // K-blocks of operand tile `rtile` that a clipped GEMM reads (the others are neither written nor read)
 __device__ __forceinline__ bool oz_kb_live(int tri, int64_t rtile, int kb) {
     if (tri == OZ_TRI_K_LE_ROW) return kb < (rtile + 1) * (OZ_BM / OZ_KB);
@@ -361,7 +403,8 @@ constexpr int OZ_SLICE_KB = 2;
 template <bool TRANS, int S>
 __global__ void __launch_bounds__(128)
     oz_slice_rows_kernel(const double* __restrict__ P, int64_t rows, int64_t K, int64_t ld, int tri,
-                         const double* __restrict__ scale, uint8_t* __restrict__ Dop, int kblocks) {
+                         const double* __restrict__ scale, const double* __restrict__ kscale, uint8_t* __restrict__ Dop,
+                         int kblocks) {
     const int r = threadIdx.x;
     const int64_t rtile = blockIdx.y, row = rtile * OZ_BM + r;
     const bool live = row < rows;
@@ -383,7 +426,8 @@ __global__ void __launch_bounds__(128)
             for (int e = 0; e < 16; ++e) {
                 const int64_t k = (int64_t)kb * 32 + c * 16 + e;
                 double v = 0.0;
-                if (live && k < K && oz_in_range(tri, row, k)) v = TRANS ? P[k * ld + row] : P[row * ld + k];
+                if (live && k < K && oz_in_range(tri, row, k))
+                    v = (TRANS ? P[k * ld + row] : P[row * ld + k]) * (kscale ? kscale[k] : 1.0);  // exact: power of two
                 uint32_t d[S];
                 oz_signed_digits<S>(__double2ll_rn(v * inv), d);
 #pragma unroll
@@ -675,7 +719,7 @@ int64_t ozaki_operand_bytes(int64_t rows, int64_t K, int S) {
 }
 // trans == 0: operand(r, k) = P[r][k];  trans != 0: operand(r, k) = P[k][r].  tri: OzTri mask of the operand.
 int ozaki_slice_operand(const double* P, int64_t rows, int64_t K, int64_t ld, int trans, int tri, uint8_t* buf, int S,
-                        cudaStream_t st) {
+                        const double* kscale, cudaStream_t st) {
     const int64_t rt = pad_to(rows, OZ_BM) / OZ_BM;
     const int kb = (int)(pad_to(K, OZ_KB) / OZ_KB);
     double* scale = reinterpret_cast<double*>(buf + pad_to(rt * kb * S * OZ_A_BYTES, 1024));
@@ -683,14 +727,14 @@ int ozaki_slice_operand(const double* P, int64_t rows, int64_t K, int64_t ld, in
     if (trans) {
         cudaMemsetAsync(scale, 0, (size_t)rt * OZ_BM * 8, st);
         oz_colmax_kernel<<<dim3((unsigned)ceil_div(rows, 128), (unsigned)ceil_div(K, 256)), 128, 0, st>>>(
-            P, rows, K, ld, tri, reinterpret_cast<unsigned long long*>(scale));
+            P, rows, K, ld, tri, kscale, reinterpret_cast<unsigned long long*>(scale));
         oz_scale_from_max_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, st>>>(scale, rows);
-        if (S == 8) oz_slice_rows_kernel<true, 8><<<gs, 128, 0, st>>>(P, rows, K, ld, tri, scale, buf, kb);
-        else oz_slice_rows_kernel<true, 7><<<gs, 128, 0, st>>>(P, rows, K, ld, tri, scale, buf, kb);
+        if (S == 8) oz_slice_rows_kernel<true, 8><<<gs, 128, 0, st>>>(P, rows, K, ld, tri, scale, kscale, buf, kb);
+        else oz_slice_rows_kernel<true, 7><<<gs, 128, 0, st>>>(P, rows, K, ld, tri, scale, kscale, buf, kb);
     } else {
-        oz_rowscale_rows_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(P, rows, K, ld, tri, scale);
-        if (S == 8) oz_slice_rows_kernel<false, 8><<<gs, 128, 0, st>>>(P, rows, K, ld, tri, scale, buf, kb);
-        else oz_slice_rows_kernel<false, 7><<<gs, 128, 0, st>>>(P, rows, K, ld, tri, scale, buf, kb);
+        oz_rowscale_rows_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(P, rows, K, ld, tri, kscale, scale);
+        if (S == 8) oz_slice_rows_kernel<false, 8><<<gs, 128, 0, st>>>(P, rows, K, ld, tri, scale, kscale, buf, kb);
+        else oz_slice_rows_kernel<false, 7><<<gs, 128, 0, st>>>(P, rows, K, ld, tri, scale, kscale, buf, kb);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -699,6 +743,27 @@ int ozaki_slice_operand(const double* P, int64_t rows, int64_t K, int64_t ld, in
     }
     return SOCKS_OK;
 }
+
+// Power-of-two scales along K that balance the two operands of one product (see oz_kmax_kernel): on return
+// kwork[0 .. K) is the scale for operand A, kwork[K .. 2K) the one for operand B (pass them to ozaki_slice_operand).
+int ozaki_kbalance(const double* PA, int64_t rows_a, int64_t lda, int trans_a, int tri_a, const double* PB, int64_t rows_b,
+                   int64_t ldb, int trans_b, int tri_b, int64_t K, double* kwork, cudaStream_t st) {
+    cudaMemsetAsync(kwork, 0, (size_t)(2 * K) * 8, st);
+    unsigned long long* ka = reinterpret_cast<unsigned long long*>(kwork);
+    unsigned long long* kb = ka + K;
+    if (trans_a) oz_kmax_kernel<true><<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(PA, rows_a, K, lda, tri_a, ka);
+    else oz_kmax_kernel<false><<<dim3((unsigned)ceil_div(K, 128), (unsigned)ceil_div(rows_a, 256)), 128, 0, st>>>(PA, rows_a, K, lda, tri_a, ka);
+    if (trans_b) oz_kmax_kernel<true><<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(PB, rows_b, K, ldb, tri_b, kb);
+    else oz_kmax_kernel<false><<<dim3((unsigned)ceil_div(K, 128), (unsigned)ceil_div(rows_b, 256)), 128, 0, st>>>(PB, rows_b, K, ldb, tri_b, kb);
+    oz_kbalance_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(kwork, kwork + K, K);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("ozaki_kbalance: %s", cudaGetErrorString(e));
+        return SOCKS_ECUDA;
+    }
+    return SOCKS_OK;
+}
+
 // C (m x n) (op)= A B^T from sliced operands (tile offsets in units of 128 operand rows); mode 0: -=, 1: =, 2: = -.
 int ozaki_gemm_nt_sliced(const uint8_t* abuf, int64_t a_rows_total, int64_t a_tile0, const uint8_t* bbuf, int64_t b_rows_total,
                          int64_t b_tile0, int64_t K, double* C, int64_t ldc, int64_t m, int64_t n, int lower_only, int mode,
@@ -936,8 +1001,8 @@ extern "C" int socks_dev_ozaki_gemm_nt(const double* A, int64_t lda, const doubl
     const int S = (syrk & 2) ? 8 : 7;  // bit 1 of `syrk`: 8 digits
     syrk &= 1;
     uint8_t* bbuf = syrk ? abuf : abuf + ozaki_operand_bytes(m, K, S);
-    int rc = ozaki_slice_operand(A, m, K, lda, 0, 0, abuf, S, st);
+    int rc = ozaki_slice_operand(A, m, K, lda, 0, 0, abuf, S, nullptr, st);
     if (rc) return rc;
-    if (!syrk && (rc = ozaki_slice_operand(B, n, K, ldb, 0, 0, bbuf, S, st))) return rc;
+    if (!syrk && (rc = ozaki_slice_operand(B, n, K, ldb, 0, 0, bbuf, S, nullptr, st))) return rc;
     return ozaki_gemm_nt_sliced(abuf, m, 0, bbuf, syrk ? m : n, 0, K, C, ldc, m, n, lower_only, 0, 0, 0, S, st);
 }
