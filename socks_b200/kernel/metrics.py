@@ -171,12 +171,12 @@ def sharded_bandwidth_guard(spec):
 
 _ENGINE = {"factorization": "int8"}
 # e = (max l_ii / min l_ii)^2, read off the diagonal of the Cholesky factor: a (loose, 100-5000x) lower bound of cond_2(G).
-# Above this value Factorization.check() redoes the inverse with its GEMMs on the FP64 tensor cores.  Measured
-# (tools/illcond_check.py, tools/cond_estimates.py): with the integer merges the residual max|W G - I| is 1.0x / 1.5x / 3x
-# the FP64 engine's at e = 5.5e3 / 3.9e4 (configs[3], N = 40 000) / 1.6e4, and 7x / 19x / 500x at e = 3.3e5 / 3.3e7 / 1.7e8
-# (cond 2e8 / 5e10 / 8e11); every BASELINE config has e <= 3.9e4.  The trailing updates stay on the integer tensor cores
-# either way: they are as accurate as FP64 up to cond 8e11.
-COND_LIMIT_INT8 = 1e5
+# Above this value Factorization.check() redoes the inverse with its GEMMs on the FP64 tensor cores (the trailing updates
+# stay on the integer ones).  A safety net beyond what has been measured: with the merge products balanced along K
+# (csrc/ozaki.cu) the integer inverse's residual max|W G - I| equals the FP64 engine's up to e = 1.7e8 (cond 8e11), the
+# worst case tried (tools/illcond_check.py); without the balancing it was 7x / 19x / 500x worse at e = 3.3e5 / 3.3e7 / 1.7e8.
+# Every BASELINE config has e <= 3.9e4 (tools/cond_estimates.py).
+COND_LIMIT_INT8 = 1e10
 
 
 def set_factorization_engine(engine="int8"):

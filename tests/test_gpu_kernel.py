@@ -146,9 +146,9 @@ def test_factorization_pieces(n, d, sigma, lam, with_u, two_pass):
         assert np.array_equal(Wp[n:, n:], np.eye(npad - n)) and not Wp[n:, :n].any() and not Wp[:n, n:].any()
 
 
-def test_ill_conditioned_matrix_sends_the_inverse_to_fp64():
-    """The rows of inv(L) of a badly conditioned Gram matrix span more dynamic range than the digit GEMMs carry:
-    Factorization.check() sees it on the diagonal of L and redoes the inverse on the FP64 tensor cores."""
+def test_ill_conditioned_matrix_on_the_integer_engine_and_its_guard():
+    """cond(G) = 5e10: the merge products' operands are balanced along K before the digit split, so the integer inverse is
+    as accurate as the FP64 one; lowering COND_LIMIT_INT8 exercises the safety net (inverse redone on FP64)."""
     torch, dv, _lib, mt = _mods()
     rng = np.random.default_rng(3)
     n, sigma, lam = 3000, 1.0, 1e-11
@@ -156,20 +156,20 @@ def test_ill_conditioned_matrix_sends_the_inverse_to_fp64():
     G = orc.rbf_kernel(X, X, sigma)
     G[np.diag_indices(n)] += lam * n
     res = {}
+    limit = mt.COND_LIMIT_INT8
     try:
-        for engine in ("fp64", "int8"):
+        for name, engine, lim in (("fp64", "fp64", limit), ("int8", "int8", limit), ("guard", "int8", 1e5)):
             mt.set_factorization_engine(engine)
+            mt.COND_LIMIT_INT8 = lim
             fac = mt.factorize(X, None, mt.RBFSpec(sigma=sigma), lam)
             fac.check()
-            assert fac.cond_estimate > mt.COND_LIMIT_INT8 and fac._fp64_inverse
-            res[engine] = np.abs(fac.full()[:n, :n].cpu().numpy() @ G - np.eye(n)).max()
+            assert fac.cond_estimate > 1e6
+            assert fac._fp64_inverse == (name != "int8")
+            res[name] = np.abs(fac.full()[:n, :n].cpu().numpy() @ G - np.eye(n)).max()
     finally:
+        mt.COND_LIMIT_INT8 = limit
         mt.set_factorization_engine("int8")
-    assert res["int8"] <= 2 * res["fp64"]
-    # a well-conditioned matrix stays on the integer engine
-    fac = mt.factorize(rng.uniform(-1.1, 1.1, (3000, 2)), None, mt.RBFSpec(sigma=0.1), 1e-4)
-    fac.check()
-    assert fac.cond_estimate < mt.COND_LIMIT_INT8 and not fac._fp64_inverse
+    assert res["int8"] <= 2 * res["fp64"] and res["guard"] <= 2 * res["fp64"]
 
 
 def test_factorization_engine_switch():
