@@ -24,7 +24,7 @@ int socks_dev_i8gemm_check(const void* A, const void* B, void* C, int M, int N, 
 /* FP64-equivalent C (m x n) -= A (m x K) B (n x K)^T on the integer tensor cores (Ozaki scheme: 7 balanced base-256
  * digits per operand, 28 exact int8 GEMMs on tcgen05.mma kind::i8, fp64 recombination); m, n % 128 == 0, K % 32 == 0
  * (longer K than one int32 accumulation chunk is handed over chunk by chunk); syrk bit 0: B = A, bit 1: 8 digits
- * (36 GEMMs, 256x smaller truncation error).  The factorisation's trailing updates (7 digits) and the merges of
+ * (36 GEMMs, 256x smaller truncation error), bit 2: balance the two operands along K with power-of-two scales first.  The factorisation's trailing updates (7 digits) and the merges of
  * inv(L) (8 digits) run through the same kernels. */
 int64_t socks_dev_ozaki_gemm_work_bytes(int64_t m, int64_t n, int64_t K);
 int socks_dev_ozaki_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t m,

@@ -981,11 +981,12 @@ extern "C" int socks_srmax_predict_i8(const double* X, const double* w, const do
 
 
 extern "C" int64_t socks_dev_ozaki_gemm_work_bytes(int64_t m, int64_t n, int64_t K) {
-    return ozaki_operand_bytes(m, K, 8) + ozaki_operand_bytes(n, K, 8) + 2048;
+    return ozaki_operand_bytes(m, K, 8) + ozaki_operand_bytes(n, K, 8) + 2048 + 2 * K * 8;  // + balancing scales
 }
 
 // C (m x n, ldc) -= A (m x K, lda) B (n x K, ldb)^T through the integer tensor cores; m, n multiples of 128, K of 32,
-// K <= 16384.  syrk != 0: B is A (sliced once), lower_only as in socks_gemm_f64.  work: 1024-byte aligned.
+// `syrk` is a bit set: 1 = B is A (sliced once), 2 = 8 digits instead of 7, 4 = balance the operands along K (ozaki_kbalance;
+// ignored with bit 0); lower_only as in socks_gemm_f64.  work: 1024-byte aligned.
 extern "C" int socks_dev_ozaki_gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                                        int64_t m, int64_t n, int64_t K, int syrk, int lower_only, void* work,
                                        socks_stream_t stream) {
@@ -998,11 +999,20 @@ extern "C" int socks_dev_ozaki_gemm_nt(const double* A, int64_t lda, const doubl
     SOCKS_CHECK_ARG(work != nullptr && (reinterpret_cast<uintptr_t>(work) & 1023) == 0, 12);
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* abuf = reinterpret_cast<uint8_t*>(work);
-    const int S = (syrk & 2) ? 8 : 7;  // bit 1 of `syrk`: 8 digits
+    const int S = (syrk & 2) ? 8 : 7;
+    const bool balance = (syrk & 4) && !(syrk & 1);
     syrk &= 1;
     uint8_t* bbuf = syrk ? abuf : abuf + ozaki_operand_bytes(m, K, S);
-    int rc = ozaki_slice_operand(A, m, K, lda, 0, 0, abuf, S, nullptr, st);
+    int rc = SOCKS_OK;
+    const double *ksa = nullptr, *ksb = nullptr;
+    if (balance) {
+        double* kw = reinterpret_cast<double*>(abuf + ozaki_operand_bytes(m, K, 8) + ozaki_operand_bytes(n, K, 8) + 1024);
+        if ((rc = ozaki_kbalance(A, m, lda, 0, 0, B, n, ldb, 0, 0, K, kw, st))) return rc;
+        ksa = kw;
+        ksb = kw + K;
+    }
+    rc = ozaki_slice_operand(A, m, K, lda, 0, 0, abuf, S, ksa, st);
     if (rc) return rc;
-    if (!syrk && (rc = ozaki_slice_operand(B, n, K, ldb, 0, 0, bbuf, S, nullptr, st))) return rc;
+    if (!syrk && (rc = ozaki_slice_operand(B, n, K, ldb, 0, 0, bbuf, S, ksb, st))) return rc;
     return ozaki_gemm_nt_sliced(abuf, m, 0, bbuf, syrk ? m : n, 0, K, C, ldc, m, n, lower_only, 0, 0, 0, S, st);
 }

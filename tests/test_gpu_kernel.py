@@ -146,6 +146,30 @@ def test_factorization_pieces(n, d, sigma, lam, with_u, two_pass):
         assert np.array_equal(Wp[n:, n:], np.eye(npad - n)) and not Wp[n:, :n].any() and not Wp[:n, n:].any()
 
 
+def test_ozaki_gemm_k_balancing_recovers_opposite_profiles():
+    """Operands whose magnitudes run in opposite directions along K (what L21 and inv(L11) look like in a merge): every
+    term a_ik b_jk is of order one, but without balancing the small factors are truncated against their row maximum."""
+    torch, dv, _lib, mt = _mods()
+    lib = _lib.load()
+    m = n = 256
+    K = 1024
+    g = torch.Generator(device="cuda").manual_seed(5)
+    prof = torch.pow(10.0, torch.linspace(0, -12, K, dtype=torch.float64, device="cuda"))
+    A = torch.randn(m, K, dtype=torch.float64, device="cuda", generator=g) * prof
+    B = torch.randn(n, K, dtype=torch.float64, device="cuda", generator=g) / prof
+    ref = (A.cpu().numpy().astype(np.longdouble) @ B.cpu().numpy().T.astype(np.longdouble)).astype(np.float64)
+    wk = dv.work(lib.socks_dev_ozaki_gemm_work_bytes(m, n, K) + 2048)
+    base = (wk.data_ptr() + 1023) // 1024 * 1024
+    err = {}
+    for name, flags in (("plain", 0), ("balanced", 4)):
+        C = torch.zeros(m, n, dtype=torch.float64, device="cuda")
+        _lib.call("socks_dev_ozaki_gemm_nt", A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), n, m, n, K, flags, 0, base,
+                  dv.stream())
+        torch.cuda.synchronize()
+        err[name] = np.abs(-C.cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert err["balanced"] < 1e-14 and err["plain"] > 1e3 * err["balanced"]
+
+
 def test_ill_conditioned_matrix_on_the_integer_engine_and_its_guard():
     """cond(G) = 5e10: the merge products' operands are balanced along K before the digit split, so the integer inverse is
     as accurate as the FP64 one; lowering COND_LIMIT_INT8 exercises the safety net (inverse redone on FP64)."""
